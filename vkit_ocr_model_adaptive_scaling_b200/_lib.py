@@ -1,0 +1,100 @@
+"""ctypes binding of ``libvkocr_b200.so`` (the C ABI declared in ``include/vkocr_b200.h``).
+
+The product path has no CPU or PyTorch fallback: if the shared object cannot be built or loaded, importing this
+module raises.
+"""
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from . import _build
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_float = ctypes.c_float
+
+F32 = 0
+BF16 = 1
+
+
+def dtype_tag(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f'vkocr_b200 kernels support float32 and bfloat16 storage, got {dtype}')
+
+
+class ConvGeom(ctypes.Structure):
+    _fields_ = [
+        ('batch', c_int), ('H', c_int), ('W', c_int), ('ks', c_int), ('C', c_int),
+        ('ld_x', c_ll), ('c_pad', c_int),
+    ]
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [
+        ('out', c_void_p), ('ldo', c_ll), ('out_f32', c_int), ('accumulate', c_int),
+        ('out_pre', c_void_p), ('ld_pre', c_ll),
+        ('bias', c_void_p), ('act', c_int),
+        ('col_scale', c_void_p), ('row_scale', c_void_p), ('rows_per_group', c_int),
+        ('residual', c_void_p), ('ld_res', c_ll),
+    ]
+
+
+_P = ctypes.POINTER
+
+# name -> argtypes of every compute entry point declared in include/vkocr_b200.h (all return int status)
+_SIGNATURES = {
+    'vkocr_abi_version': [],
+    'vkocr_device_check': [c_int],
+    'vkocr_gemm_nt': [c_int, c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, _P(Epilogue), c_void_p],
+    'vkocr_gemm_tn': [c_int, c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, c_ll, _P(Epilogue), c_void_p],
+}
+
+
+def _load() -> ctypes.CDLL:
+    path = _build.LIB
+    if not os.path.exists(path) or os.environ.get('VKOCR_B200_REBUILD') == '1':
+        path = _build.build()
+    lib = ctypes.CDLL(path)
+    lib.vkocr_last_error.restype = ctypes.c_char_p
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here == the .so does not export a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    return lib
+
+
+LIB = _load()
+
+
+class VkocrError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = '') -> None:
+    if rc != 0:
+        msg = LIB.vkocr_last_error().decode('utf-8', 'replace')
+        raise VkocrError(f'vkocr_b200 {what} failed with status {rc}: {msg}')
+
+
+def ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr(device: Optional[torch.device] = None) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise VkocrError(
+                'vkocr_b200 operators run only on CUDA (sm_100a) tensors; there is no CPU fallback '
+                f'(got a tensor on {t.device})')

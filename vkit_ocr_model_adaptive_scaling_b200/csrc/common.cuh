@@ -1,0 +1,128 @@
+// Shared helpers for the sm_100a kernels of the adaptive-scaling hot path.
+// Everything here is device/host plumbing: error convention of the C ABI, dtype tags,
+// 16-byte vector access, warp/block reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+// ---- C-ABI error convention (include/vkocr_b200.h) -------------------------------------------
+enum VkocrStatus {
+    VKOCR_OK = 0,
+    VKOCR_BAD_SHAPE = -1,
+    VKOCR_BAD_ALIGN = -2,
+    VKOCR_UNSUPPORTED_DTYPE = -3,
+    VKOCR_CUDA_ERROR = -4,
+    VKOCR_WORKSPACE_TOO_SMALL = -5,
+    VKOCR_BAD_ARGUMENT = -6,
+};
+
+enum VkocrDtype { VKOCR_F32 = 0, VKOCR_BF16 = 1 };
+
+void vkocr_set_error(const char* fmt, ...);
+int vkocr_sm_count();
+
+#define VK_FAIL(code, ...)               \
+    do {                                 \
+        vkocr_set_error(__VA_ARGS__);    \
+        return (code);                   \
+    } while (0)
+
+#define VK_REQUIRE(cond, code, ...)      \
+    do {                                 \
+        if (!(cond)) VK_FAIL(code, __VA_ARGS__); \
+    } while (0)
+
+#define VK_CHECK_LAUNCH(name)                                                        \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess)                                                      \
+            VK_FAIL(VKOCR_CUDA_ERROR, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+// Dispatch on a storage dtype tag; T is the storage type (math is always fp32).
+#define VK_DISPATCH_DTYPE(dtype, T, ...)                                  \
+    do {                                                                  \
+        if ((dtype) == VKOCR_F32) { using T = float; __VA_ARGS__; }        \
+        else if ((dtype) == VKOCR_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+        else VK_FAIL(VKOCR_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)(dtype)); \
+    } while (0)
+
+static inline int vk_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- scalar conversions -----------------------------------------------------------------------
+__device__ __forceinline__ float vk_to_f32(float v) { return v; }
+__device__ __forceinline__ float vk_to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T vk_from_f32(float v);
+template <> __device__ __forceinline__ float vk_from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 vk_from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- vectors of VEC storage elements = 16 bytes -------------------------------------------------
+template <typename T> struct VkVec;
+template <> struct VkVec<float> {
+    static constexpr int N = 4;
+    float4 raw;
+    __device__ __forceinline__ void load(const float* p) { raw = *reinterpret_cast<const float4*>(p); }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = raw; }
+    __device__ __forceinline__ void unpack(float* f) const { f[0] = raw.x; f[1] = raw.y; f[2] = raw.z; f[3] = raw.w; }
+    __device__ __forceinline__ void pack(const float* f) { raw = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct VkVec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    uint4 raw;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+    __device__ __forceinline__ void unpack(float* f) const {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 v = __bfloat1622float2(h[i]);
+            f[2 * i] = v.x;
+            f[2 * i + 1] = v.y;
+        }
+    }
+    __device__ __forceinline__ void pack(const float* f) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    }
+};
+
+// ---- reductions ---------------------------------------------------------------------------------
+__device__ __forceinline__ float vk_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the whole block; result valid in every thread. `scratch` needs 33 floats.
+__device__ __forceinline__ float vk_block_sum(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarp = (blockDim.x + 31) >> 5;
+    v = vk_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < nwarp ? scratch[lane] : 0.f;
+        t = vk_warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// ---- math ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float vk_gelu(float x) {  // exact erf GELU (reference helper.py:100-101)
+    return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float vk_gelu_grad(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+__device__ __forceinline__ float vk_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float vk_softplus(float x) {  // beta 1, threshold 20 (torch.nn.Softplus)
+    return x > 20.f ? x : log1pf(expf(x));
+}

@@ -1,0 +1,60 @@
+// Geometry + epilogue description shared by the tcgen05 GEMM (gemm_tc.cu) and the SIMT fp32 GEMM (gemm_simt.cu).
+//
+// Both kernels compute the same two contractions over NHWC ("pixel-major, channel-contiguous") activations:
+//
+//   NT  (forward / data-gradient):  D[m, n]      = sum_{tap, c} X[pix(m) + off(tap), c] * Wp[n, tap, c]
+//   TN  (weight-gradient):          G[tap, i, j] = sum_{pix}    P[pix, i] * Q[pix + off(tap), j]
+//
+// ks == 1 degenerates to a plain row-major GEMM (Linear / 1x1 conv / patchified conv).  ks == 3/5 is the
+// zero-padded 'same' convolution of reference helper.py:25-40 expressed as an implicit GEMM.
+#pragma once
+#include "common.cuh"
+
+struct VkocrConvGeom {
+    int batch, H, W;       // pixel grid of the activation operand(s); plain GEMM: batch=1, H=1, W=rows
+    int ks;                // square kernel size (1, 3, 5); padding = ks/2
+    int C;                 // channels contracted per tap (NT) / channels of P (TN)
+    long long ld_x;        // pixel stride (elements) of X (NT) / of P (TN)
+    int c_pad;             // NT: per-tap K extent of the packed weight (multiple of 64 for the tcgen05 path)
+};
+
+struct VkocrEpilogue {
+    void* out;             // [rows, ldo] storage dtype (or fp32 when out_f32 != 0)
+    long long ldo;
+    int out_f32;           // 1: `out` is fp32 regardless of the activation dtype
+    int accumulate;        // 1: out += value (fp32 atomics; requires out_f32)
+    void* out_pre;         // optional copy of (acc + bias) before the activation, storage dtype
+    long long ld_pre;
+    const float* bias;     // [N] or null
+    int act;               // 0 none, 1 exact GELU
+    const float* col_scale;  // [N] or null  (ConvNeXt layer scale, convnext.py:38,56)
+    const float* row_scale;  // [rows / rows_per_group] or null (stochastic-depth mask, convnext.py:41-53)
+    int rows_per_group;
+    const void* residual;  // optional [rows, ld_res] storage dtype, added last (convnext.py:58)
+    long long ld_res;
+};
+
+// Apply the epilogue to one accumulator value and return the value to store in `out`.
+// Side effect: writes out_pre when requested.
+template <typename T>
+__device__ __forceinline__ float vk_epilogue_value(const VkocrEpilogue& ep, long long m, int n, float acc) {
+    float v = acc;
+    if (ep.bias) v += __ldg(ep.bias + n);
+    if (ep.out_pre) reinterpret_cast<T*>(ep.out_pre)[m * ep.ld_pre + n] = vk_from_f32<T>(v);
+    if (ep.act == 1) v = vk_gelu(v);
+    if (ep.col_scale) v *= __ldg(ep.col_scale + n);
+    if (ep.row_scale) v *= __ldg(ep.row_scale + (m / ep.rows_per_group));
+    if (ep.residual) v += vk_to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + n]);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void vk_epilogue_store(const VkocrEpilogue& ep, long long m, int n, float v) {
+    if (ep.out_f32) {
+        float* o = reinterpret_cast<float*>(ep.out) + m * ep.ldo + n;
+        if (ep.accumulate) atomicAdd(o, v);
+        else *o = v;
+    } else {
+        reinterpret_cast<T*>(ep.out)[m * ep.ldo + n] = vk_from_f32<T>(v);
+    }
+}

@@ -1,0 +1,563 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: the tensor-core kernel behind every dense contraction of the
+// adaptive-scaling network (Linear / 1x1, patchify convs, 3x3 neck + head convs; forward, data-gradient and
+// weight-gradient).  bf16 operands, fp32 accumulation in tensor memory.
+//
+// One persistent, warp-specialised kernel:
+//   warp 0 (1 lane)  TMA producer: 4-D tiled tensor maps over NHWC activations (zero-filled out-of-bounds boxes
+//                    give the conv padding for free), 2-D map over the packed weights; SWIZZLE_128B smem tiles.
+//   warp 1 (1 lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN (16..256), K=16 per instruction,
+//                    accumulators double-buffered in TMEM (2 x 256 columns).
+//   warp 2           TMEM allocator.
+//   warps 4..7       epilogue: tcgen05.ld -> registers -> bias / GELU / layer-scale / residual -> global.
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
+//
+// Modes (see gemm_common.cuh):
+//   NT  D[m,n] = sum_{tap,c} X[pix(m)+off(tap), c] * Wp[n, tap, c]       A,B K-major
+//   TN  G[tap,i,j] = sum_pix P[pix,i] * Q[pix+off(tap), j]               A,B MN-major, split over pixels, fp32 red.add
+#include "gemm_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 elements in one 128-byte swizzle row
+constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int MAX_SMEM = 200 * 1024;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;
+
+struct TcParams {
+    int mode;                // 0 NT, 1 TN
+    int batch, H, W;
+    int BW, BH;              // pixel box (BW*BH == 128 for NT, 64 for TN)
+    int tiles_x, tiles_y;
+    int ks;
+    int kb_per_tap;          // NT: 64-wide K blocks per tap
+    int N, BN, n_tiles;      // NT: output channels; TN: J (channels of Q)
+    int I, i_tiles;          // TN: channels of P
+    int splits;              // TN: split of the pixel-tile range
+    int num_stages;
+    int stage_bytes;
+    long long units;
+    VkocrEpilogue ep;
+};
+
+// ------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a broken pipeline traps (kernel error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {
+            printf("vkocr gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+                   (int)threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.  Offsets are in 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(lbo16 & 0x3FFF) << 16;
+    d |= (uint64_t)(sbo16 & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // layout type: SWIZZLE_128B
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.num_stages;
+    const uint32_t bar_base = smem_base + (uint32_t)S * (uint32_t)p.stage_bytes;
+    // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base address word
+    auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    const int BN = p.BN;
+    const int pix_tiles = p.batch * p.tiles_y * p.tiles_x;
+    const int half = p.ks >> 1;
+
+    // unit -> coordinates
+    struct Unit {
+        int n0, b, y0, x0;          // NT
+        int tap, i0, kt_begin, kt_end;  // TN
+        int num_kb;
+    };
+    auto decode = [&](long long u) {
+        Unit t;
+        if (p.mode == 0) {
+            const int nt = (int)(u % p.n_tiles);
+            long long mt = u / p.n_tiles;
+            const int tx = (int)(mt % p.tiles_x);
+            mt /= p.tiles_x;
+            const int ty = (int)(mt % p.tiles_y);
+            t.b = (int)(mt / p.tiles_y);
+            t.n0 = nt * BN;
+            t.x0 = tx * p.BW;
+            t.y0 = ty * p.BH;
+            t.num_kb = p.ks * p.ks * p.kb_per_tap;
+            t.tap = 0; t.i0 = 0; t.kt_begin = 0; t.kt_end = 0;
+        } else {
+            const int jt = (int)(u % p.n_tiles);
+            long long r = u / p.n_tiles;
+            const int it = (int)(r % p.i_tiles);
+            r /= p.i_tiles;
+            t.tap = (int)(r % (p.ks * p.ks));
+            const int sp = (int)(r / (p.ks * p.ks));
+            t.n0 = jt * BN;
+            t.i0 = it * BM;
+            t.kt_begin = (int)((long long)pix_tiles * sp / p.splits);
+            t.kt_end = (int)((long long)pix_tiles * (sp + 1) / p.splits);
+            t.num_kb = t.kt_end - t.kt_begin;
+            t.b = 0; t.y0 = 0; t.x0 = 0;
+        }
+        return t;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ================================================================ TMA producer
+        int s = 0;
+        uint32_t ph = 0;
+        const uint32_t tx_bytes = (p.mode == 0) ? (uint32_t)(A_BYTES + BN * 128) : (uint32_t)(2 * 8192 + (BN / 64) * 8192);
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit t = decode(u);
+            for (int kb = 0; kb < t.num_kb; ++kb) {
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                const uint32_t sb = sa + A_BYTES;
+                mbar_expect_tx(full_bar(s), tx_bytes);
+                if (p.mode == 0) {
+                    const int tap = kb / p.kb_per_tap;
+                    const int c0 = (kb - tap * p.kb_per_tap) * BK;
+                    const int dy = tap / p.ks - half, dx = tap % p.ks - half;
+                    tma_load_4d(sa, &mapA, full_bar(s), c0, t.x0 + dx, t.y0 + dy, t.b);
+                    tma_load_2d(sb, &mapB, full_bar(s), kb * BK, t.n0);
+                } else {
+                    int kt = t.kt_begin + kb;
+                    const int tx = kt % p.tiles_x;
+                    kt /= p.tiles_x;
+                    const int ty = kt % p.tiles_y;
+                    const int b = kt / p.tiles_y;
+                    const int dy = t.tap / p.ks - half, dx = t.tap % p.ks - half;
+                    const int x0 = tx * p.BW, y0 = ty * p.BH;
+                    tma_load_4d(sa, &mapA, full_bar(s), t.i0, x0, y0, b);
+                    tma_load_4d(sa + 8192, &mapA, full_bar(s), t.i0 + 64, x0, y0, b);
+                    for (int g = 0; g < BN / 64; ++g)
+                        tma_load_4d(sb + (uint32_t)g * 8192u, &mapB, full_bar(s), t.n0 + g * 64, x0 + dx, y0 + dy, b);
+                }
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================================================================ MMA issuer
+        int s = 0;
+        uint32_t ph = 0;
+        int as = 0;
+        uint32_t aph = 0;
+        const uint32_t major = (p.mode == 0) ? 0u : 1u;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (major << 15) | (major << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit t = decode(u);
+            if (t.num_kb == 0) continue;
+            mbar_wait(tempty_bar(as), aph ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC_STRIDE);
+            for (int kb = 0; kb < t.num_kb; ++kb) {
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                const uint32_t sb = sa + A_BYTES;
+                if (p.mode == 0) {
+                    // K-major SWIZZLE_128B: 8-row atoms of 1024 B; advance 32 B per K=16 slice inside the atom.
+                    const uint64_t ad = make_smem_desc(sa, 1, 64);
+                    const uint64_t bd = make_smem_desc(sb, 1, 64);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                } else {
+                    // MN-major SWIZZLE_128B: 64-channel groups 8192 B apart (LBO), 8-pixel atoms 1024 B apart (SBO);
+                    // one K=16 slice = 2 atoms = 2048 B.
+                    const uint64_t ad = make_smem_desc(sa, 512, 64);
+                    const uint64_t bd = make_smem_desc(sb, 512, 64);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma(tmem_d, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kb | k) ? 1u : 0u);
+                }
+                tc_commit(empty_bar(s));
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            tc_commit(tfull_bar(as));
+            if (++as == 2) { as = 0; aph ^= 1u; }
+        }
+    } else if (warp >= 4) {
+        // ================================================================ epilogue (TMEM -> registers -> global)
+        const int q = warp & 3;                 // TMEM lane quarter owned by this warp
+        const int r = q * 32 + lane;            // accumulator row
+        int as = 0;
+        uint32_t aph = 0;
+        const VkocrEpilogue& ep = p.ep;
+        const int chunks = (BN + 31) / 32;
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit t = decode(u);
+            bool row_ok;
+            long long row;
+            if (p.mode == 0) {
+                const int y = t.y0 + r / p.BW, x = t.x0 + r % p.BW;
+                row_ok = (y < p.H) && (x < p.W);
+                row = ((long long)t.b * p.H + y) * p.W + x;
+            } else {
+                row_ok = (t.i0 + r) < p.I;
+                row = (long long)t.tap * p.I + t.i0 + r;
+            }
+            if (t.num_kb == 0) continue;
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
+            const bool vec_ok = (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
+                                (!ep.residual || (ep.ld_res & 7) == 0);
+            for (int c = 0; c < chunks; ++c) {
+                uint32_t acc[32];
+                tc_ld32(taddr + (uint32_t)(c * 32), acc);
+                if (!row_ok) continue;
+                const int nbase = t.n0 + c * 32;
+                if (vec_ok && (nbase + 32 <= p.N) && (c * 32 + 32 <= BN) && ((nbase & 7) == 0)) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                    if (ep.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nbase + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    if (ep.out_pre) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out_pre) + row * ep.ld_pre + nbase;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            VkVec<__nv_bfloat16> pk;
+                            pk.pack(v + 8 * j);
+                            pk.store(o + 8 * j);
+                        }
+                    }
+                    if (ep.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
+                    }
+                    if (ep.col_scale) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nbase + j));
+                            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+                        }
+                    }
+                    if (ep.row_scale) {
+                        const float rs = __ldg(ep.row_scale + (row / ep.rows_per_group));
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= rs;
+                    }
+                    if (ep.residual) {
+                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + row * ep.ld_res + nbase;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            VkVec<__nv_bfloat16> pk;
+                            pk.load(rp + 8 * j);
+                            float f[8];
+                            pk.unpack(f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
+                        }
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + row * ep.ldo + nbase;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        VkVec<__nv_bfloat16> pk;
+                        pk.pack(v + 8 * j);
+                        pk.store(o + 8 * j);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nbase + j;
+                        if (n < p.N && (c * 32 + j) < BN) {
+                            const float v = vk_epilogue_value<__nv_bfloat16>(ep, row, n, __uint_as_float(acc[j]));
+                            vk_epilogue_store<__nv_bfloat16>(ep, row, n, v);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aph ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, inner box = 64 elements (128 B), zero OOB fill.
+int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    VK_REQUIRE(fn != nullptr, VKOCR_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bdim[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VK_REQUIRE(r == CUDA_SUCCESS, VKOCR_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu box %u %u",
+               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return VKOCR_OK;
+}
+
+// NHWC activation map: dims (C, W, H, B), pixel stride ld (elements).
+int encode_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int B, long long ld, int bw, int bh) {
+    VK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, VKOCR_BAD_ALIGN, "activation base not 16-byte aligned");
+    VK_REQUIRE(((ld * 2) & 15) == 0, VKOCR_BAD_ALIGN, "activation pixel stride %lld not a multiple of 8 elements", ld);
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * W, (uint64_t)ld * 2 * W * H};
+    const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+    return encode_map(map, base, 4, dims, str, box);
+}
+
+void pick_box(int W, int H, int pixels, int* bw_out, int* bh_out) {
+    // choose the BW x BH == pixels box that wastes the fewest out-of-image pixels
+    long long best = -1;
+    for (int bw = pixels; bw >= 1; bw >>= 1) {
+        const int bh = pixels / bw;
+        if (bw > 256 || bh > 256) continue;
+        const long long cover = (long long)vk_cdiv(W, bw) * bw * (long long)vk_cdiv(H, bh) * bh;
+        if (best < 0 || cover < best) {
+            best = cover;
+            *bw_out = bw;
+            *bh_out = bh;
+        }
+    }
+}
+
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    const int smem = MAX_SMEM + 1024 + 256;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(vkocr_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    p.num_stages = MAX_SMEM / p.stage_bytes;
+    if (p.num_stages > 8) p.num_stages = 8;
+    const long long sms = vkocr_sm_count();
+    const int grid = (int)(p.units < sms ? p.units : sms);
+    if (grid <= 0) return VKOCR_OK;
+    vkocr_gemm_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, p);
+    VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
+    return VKOCR_OK;
+}
+
+}  // namespace
+
+// NT: D[m,n] = sum_{tap,c} X[pix(m)+off(tap), c] * Wp[n, tap*c_pad + c]   (bf16 in, fp32 accumulate)
+int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed, int N, const VkocrEpilogue* ep,
+                     cudaStream_t stream) {
+    VK_REQUIRE(g->ks == 1 || g->ks == 3 || g->ks == 5, VKOCR_BAD_SHAPE, "gemm_tc_nt: kernel size %d", g->ks);
+    VK_REQUIRE(g->c_pad % BK == 0 && g->c_pad >= g->C, VKOCR_BAD_SHAPE, "gemm_tc_nt: c_pad %d (C %d)", g->c_pad, g->C);
+    VK_REQUIRE(N >= 1, VKOCR_BAD_SHAPE, "gemm_tc_nt: N %d", N);
+    if ((long long)g->batch * g->H * g->W == 0) return VKOCR_OK;
+    TcParams p{};
+    p.mode = 0;
+    p.batch = g->batch; p.H = g->H; p.W = g->W; p.ks = g->ks;
+    pick_box(g->W, g->H, BM, &p.BW, &p.BH);
+    p.tiles_x = vk_cdiv(g->W, p.BW);
+    p.tiles_y = vk_cdiv(g->H, p.BH);
+    p.kb_per_tap = g->c_pad / BK;
+    p.N = N;
+    // N tile: multiple of 16, <= 256, splitting N as evenly as possible
+    const int n_tiles = vk_cdiv(N, 256);
+    p.BN = ((vk_cdiv(N, n_tiles) + 15) / 16) * 16;
+    p.n_tiles = vk_cdiv(N, p.BN);
+    p.stage_bytes = A_BYTES + p.BN * 128;
+    p.units = (long long)p.batch * p.tiles_y * p.tiles_x * p.n_tiles;
+    p.ep = *ep;
+    CUtensorMap mapA, mapB;
+    int rc = encode_nhwc(&mapA, x, g->C, g->W, g->H, g->batch, g->ld_x, p.BW, p.BH);
+    if (rc) return rc;
+    const long long kw = (long long)g->ks * g->ks * g->c_pad;
+    const uint64_t dims[2] = {(uint64_t)kw, (uint64_t)N};
+    const uint64_t str[1] = {(uint64_t)kw * 2};
+    const uint32_t box[2] = {64, (uint32_t)p.BN};
+    VK_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, VKOCR_BAD_ALIGN, "packed weight not 16-byte aligned");
+    rc = encode_map(&mapB, w_packed, 2, dims, str, box);
+    if (rc) return rc;
+    return launch(mapA, mapB, p, stream);
+}
+
+// TN: G[tap,i,j] += sum_pix P[pix,i] * Q[pix+off(tap), j]   (bf16 in, fp32 out accumulated with red.add)
+// ep->out must be fp32 [ks*ks*I, ldo] and is accumulated into (caller zeroes it).
+int vkocr_gemm_tc_tn(const void* pmat, const VkocrConvGeom* g, const void* qmat, int J, long long ld_q,
+                     const VkocrEpilogue* ep, cudaStream_t stream) {
+    VK_REQUIRE(g->ks == 1 || g->ks == 3 || g->ks == 5, VKOCR_BAD_SHAPE, "gemm_tc_tn: kernel size %d", g->ks);
+    VK_REQUIRE(ep->out_f32 && ep->accumulate, VKOCR_BAD_ARGUMENT, "gemm_tc_tn: output must be fp32 accumulate");
+    if ((long long)g->batch * g->H * g->W == 0) return VKOCR_OK;
+    TcParams p{};
+    p.mode = 1;
+    p.batch = g->batch; p.H = g->H; p.W = g->W; p.ks = g->ks;
+    pick_box(g->W, g->H, 64, &p.BW, &p.BH);
+    p.tiles_x = vk_cdiv(g->W, p.BW);
+    p.tiles_y = vk_cdiv(g->H, p.BH);
+    p.I = g->C;
+    p.i_tiles = vk_cdiv(p.I, BM);
+    p.N = J;
+    const int n_tiles = vk_cdiv(J, 256);
+    p.BN = ((vk_cdiv(J, n_tiles) + 63) / 64) * 64;
+    p.n_tiles = vk_cdiv(J, p.BN);
+    p.stage_bytes = A_BYTES + p.BN * 128;
+    const long long out_tiles = (long long)p.ks * p.ks * p.i_tiles * p.n_tiles;
+    const long long pix_tiles = (long long)p.batch * p.tiles_y * p.tiles_x;
+    // split the pixel range so that the machine is filled ~2x, keeping >= 8 k-blocks per unit
+    long long splits = (2LL * vkocr_sm_count() + out_tiles - 1) / out_tiles;
+    if (splits > pix_tiles / 8) splits = pix_tiles / 8;
+    if (splits < 1) splits = 1;
+    p.splits = (int)splits;
+    p.units = out_tiles * splits;
+    p.ep = *ep;
+    CUtensorMap mapA, mapB;
+    int rc = encode_nhwc(&mapA, pmat, g->C, g->W, g->H, g->batch, g->ld_x, p.BW, p.BH);
+    if (rc) return rc;
+    rc = encode_nhwc(&mapB, qmat, J, g->W, g->H, g->batch, ld_q, p.BW, p.BH);
+    if (rc) return rc;
+    return launch(mapA, mapB, p, stream);
+}
