@@ -42,6 +42,8 @@ class Epilogue(ctypes.Structure):
         ('bias', c_void_p), ('act', c_int),
         ('col_scale', c_void_p), ('row_scale', c_void_p), ('rows_per_group', c_int),
         ('residual', c_void_p), ('ld_res', c_ll),
+        ('aux', c_void_p), ('ld_aux', c_ll),
+        ('tn_s_tap', c_ll), ('tn_s_i', c_ll), ('tn_s_j', c_ll),
     ]
 
 
@@ -53,6 +55,44 @@ _SIGNATURES = {
     'vkocr_device_check': [c_int],
     'vkocr_gemm_nt': [c_int, c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, _P(Epilogue), c_void_p],
     'vkocr_gemm_tn': [c_int, c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, c_ll, _P(Epilogue), c_void_p],
+    'vkocr_layernorm_fwd': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_float, c_int,
+                            c_void_p, c_void_p, c_void_p],
+    'vkocr_layernorm_bwd': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                            c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'vkocr_colsum': [c_int, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p],
+    'vkocr_dwconv7_fwd': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                          c_void_p, c_ll, c_void_p],
+    'vkocr_dwconv7_wgrad': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    'vkocr_upsample_fwd': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_void_p],
+    'vkocr_upsample_bwd': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_void_p],
+    'vkocr_avgpool_fwd': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+    'vkocr_avgpool_bwd': [c_int, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'vkocr_patchify_image': [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    'vkocr_space_to_depth2': [c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_void_p],
+    'vkocr_copy_channels': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_int, c_void_p],
+    'vkocr_head_tail_fwd': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                            c_void_p, c_ll, c_ll, c_void_p],
+    'vkocr_head_tail_bwd': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                            c_void_p, c_ll, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'vkocr_rough_loss_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p],
+    'vkocr_rough_loss_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'vkocr_precise_loss_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                               c_void_p, c_void_p, c_void_p, c_void_p],
+    'vkocr_precise_loss_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'vkocr_pack_weight': [c_void_p, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_ll, c_ll,
+                          c_void_p],
+    'vkocr_unpack_grad': [c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_ll, c_ll, c_void_p],
+    'vkocr_mlp2_grad_finalize': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p],
+    'vkocr_accumulate_f32': [c_void_p, c_void_p, c_ll, c_void_p],
+    'vkocr_scale_rows': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p],
 }
 
 

@@ -26,12 +26,17 @@ struct VkocrEpilogue {
     void* out_pre;         // optional copy of (acc + bias) before the activation, storage dtype
     long long ld_pre;
     const float* bias;     // [N] or null
-    int act;               // 0 none, 1 exact GELU
+    int act;               // 0 none, 1 exact GELU, 2 multiply by gelu'(aux)
     const float* col_scale;  // [N] or null  (ConvNeXt layer scale, convnext.py:38,56)
     const float* row_scale;  // [rows / rows_per_group] or null (stochastic-depth mask, convnext.py:41-53)
     int rows_per_group;
     const void* residual;  // optional [rows, ld_res] storage dtype, added last (convnext.py:58)
     long long ld_res;
+    const void* aux;       // act == 2: value *= gelu'(aux[m, n]) (GELU backward fused into the data-gradient GEMM)
+    long long ld_aux;
+    // TN only: element (tap, i, j) is accumulated at out[tap*tn_s_tap + i*tn_s_i + j*tn_s_j] (lets the weight gradient
+    // land directly in the parameter's own layout, e.g. Conv2d OIHW: s_tap=1, s_i=Cin*taps, s_j=taps)
+    long long tn_s_tap, tn_s_i, tn_s_j;
 };
 
 // Apply the epilogue to one accumulator value and return the value to store in `out`.
@@ -42,6 +47,7 @@ __device__ __forceinline__ float vk_epilogue_value(const VkocrEpilogue& ep, long
     if (ep.bias) v += __ldg(ep.bias + n);
     if (ep.out_pre) reinterpret_cast<T*>(ep.out_pre)[m * ep.ld_pre + n] = vk_from_f32<T>(v);
     if (ep.act == 1) v = vk_gelu(v);
+    else if (ep.act == 2) v *= vk_gelu_grad(vk_to_f32(reinterpret_cast<const T*>(ep.aux)[m * ep.ld_aux + n]));
     if (ep.col_scale) v *= __ldg(ep.col_scale + n);
     if (ep.row_scale) v *= __ldg(ep.row_scale + (m / ep.rows_per_group));
     if (ep.residual) v += vk_to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + n]);
@@ -57,4 +63,9 @@ __device__ __forceinline__ void vk_epilogue_store(const VkocrEpilogue& ep, long 
     } else {
         reinterpret_cast<T*>(ep.out)[m * ep.ldo + n] = vk_from_f32<T>(v);
     }
+}
+
+// TN (weight-gradient) store: fp32 atomic accumulate at the caller's strides.
+__device__ __forceinline__ void vk_epilogue_store_tn(const VkocrEpilogue& ep, int tap, int i, int j, float v) {
+    atomicAdd(reinterpret_cast<float*>(ep.out) + tap * ep.tn_s_tap + i * ep.tn_s_i + j * ep.tn_s_j, v);
 }

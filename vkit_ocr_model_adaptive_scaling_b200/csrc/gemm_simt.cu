@@ -152,7 +152,7 @@ simt_tn_kernel(const T* __restrict__ pm, VkocrConvGeom g, const T* __restrict__ 
         for (int j = 0; j < 4; ++j) {
             const int jj = j0 + tx * 4 + j;
             if (jj >= J) continue;
-            vk_epilogue_store<T>(ep, (long long)tap * I + ii, jj, acc[i][j]);
+            vk_epilogue_store_tn(ep, tap, ii, jj, acc[i][j]);
         }
     }
 }

@@ -316,8 +316,8 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
-            const bool vec_ok = (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
-                                (!ep.residual || (ep.ld_res & 7) == 0);
+            const bool vec_ok = (p.mode == 0) && (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
+                                (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0);
             for (int c = 0; c < chunks; ++c) {
                 uint32_t acc[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), acc);
@@ -346,6 +346,17 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     if (ep.act == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
+                    } else if (ep.act == 2) {
+                        const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + row * ep.ld_aux + nbase;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            VkVec<__nv_bfloat16> pk;
+                            pk.load(ap + 8 * j);
+                            float f[8];
+                            pk.unpack(f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
+                        }
                     }
                     if (ep.col_scale) {
 #pragma unroll
@@ -378,8 +389,14 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         pk.pack(v + 8 * j);
                         pk.store(o + 8 * j);
                     }
+                } else if (p.mode == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nbase + j;
+                        if (n < p.N && (c * 32 + j) < BN) vk_epilogue_store_tn(ep, t.tap, t.i0 + r, n, __uint_as_float(acc[j]));
+                    }
                 } else {
-#pragma unroll 1
+#pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = nbase + j;
                         if (n < p.N && (c * 32 + j) < BN) {

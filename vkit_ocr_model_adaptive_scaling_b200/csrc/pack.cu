@@ -1,0 +1,138 @@
+// Parameter staging between the reference state_dict layout (fp32 master weights: Linear (out,in), Conv2d OIHW,
+// depthwise (C,1,7,7)) and the operand layouts of the kernels, plus small gradient finalisers.
+#include "common.cuh"
+
+namespace {
+
+// out[r*o_row + t*o_tap + c] = w[r*s_row + tt*s_tap + c*s_col] * (col_scale ? col_scale[c] : 1),  tt = flip ? taps-1-t : t,
+// for r < rows, t < taps, c < cols.  Padding (rows/columns the GEMM tiles expect beyond the logical extents) is the
+// caller's zero-initialised buffer; this kernel only writes the logical region.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, long long s_row, long long s_tap, long long s_col, int rows, int taps, int cols,
+                   int flip, const float* __restrict__ col_scale, T* __restrict__ out, long long o_row, long long o_tap) {
+    const long long total = (long long)rows * taps * cols;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % cols);
+    const int t = (int)((idx / cols) % taps);
+    const int r = (int)(idx / ((long long)cols * taps));
+    const int tt = flip ? taps - 1 - t : t;
+    float v = w[r * s_row + tt * s_tap + c * s_col];
+    if (col_scale) v *= col_scale[c];
+    out[r * o_row + t * o_tap + c] = vk_from_f32<T>(v);
+}
+
+// y[n*s_n + t*s_t + c*s_c] += g[(n*T + t)*C + c]   (weight gradient from GEMM order back to the parameter's layout)
+__global__ void __launch_bounds__(256)
+unpack_grad_kernel(const float* __restrict__ g, int N, int T, int C, float* __restrict__ y, long long s_n, long long s_t,
+                   long long s_c) {
+    const long long total = (long long)N * T * C;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % C);
+    const int t = (int)((idx / C) % T);
+    const long long n = idx / ((long long)C * T);
+    y[n * s_n + t * s_t + c * s_c] += g[idx];
+}
+
+// ConvNeXt MLP second Linear: S[c,k] = sum_p U[p,c] G[p,k] (U = layer-output gradient x drop mask), sU[c] = sum_p U[p,c]
+//   dW2[c,k] += gamma[c] * S[c,k];  dgamma[c] += sum_k W2[c,k] S[c,k] + b2[c] sU[c];  db2[c] += gamma[c] sU[c]
+// (out = x + gamma * (G W2^T + b2), convnext.py:35-38,56-58)
+__global__ void __launch_bounds__(256)
+mlp2_grad_finalize_kernel(const float* __restrict__ S, const float* __restrict__ sU, const float* __restrict__ W2,
+                          const float* __restrict__ b2, const float* __restrict__ gamma, int C, int K, float* __restrict__ dW2,
+                          float* __restrict__ dgamma, float* __restrict__ db2) {
+    __shared__ float scratch[33];
+    const int c = blockIdx.x;
+    const float g = gamma[c];
+    float dot = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float s = S[(long long)c * K + k];
+        dW2[(long long)c * K + k] += g * s;
+        dot = fmaf(W2[(long long)c * K + k], s, dot);
+    }
+    dot = vk_block_sum(dot, scratch);
+    if (threadIdx.x == 0) {
+        dgamma[c] += dot + b2[c] * sU[c];
+        db2[c] += g * sU[c];
+    }
+}
+
+// y[i] += a[i] * s[i % n_s]  (bias-gradient style finalisers)
+__global__ void axpy_kernel(const float* __restrict__ a, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a[i];
+}
+
+// x[row, c] *= scale[row / rows_per_group]   (stochastic-depth mask applied to a gradient, convnext.py:41-53)
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, long long rows, int C,
+                  const float* __restrict__ scale, int rows_per_group) {
+    const long long total = rows * C;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % C);
+    const long long r = idx / C;
+    y[r * ld_y + c] = vk_from_f32<T>(vk_to_f32(x[r * ld_x + c]) * scale[r / rows_per_group]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vkocr_pack_weight(const float* w, long long s_row, long long s_tap, long long s_col, int rows, int taps, int cols, int flip,
+                      const float* col_scale, void* out, int out_dtype, long long o_row, long long o_tap, void* stream) {
+    VK_REQUIRE(w && out, VKOCR_BAD_ARGUMENT, "pack_weight: null argument");
+    VK_REQUIRE(taps >= 1, VKOCR_BAD_SHAPE, "pack_weight: taps %d", taps);
+    const long long total = (long long)rows * taps * cols;
+    if (total == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(out_dtype, T, (pack_weight_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                        w, s_row, s_tap, s_col, rows, taps, cols, flip, col_scale, reinterpret_cast<T*>(out), o_row,
+                                        o_tap)));
+    VK_CHECK_LAUNCH("pack_weight_kernel");
+    return VKOCR_OK;
+}
+
+int vkocr_mlp2_grad_finalize(const float* S, const float* sU, const float* W2, const float* b2, const float* gamma, int C, int K,
+                             float* dW2, float* dgamma, float* db2, void* stream) {
+    VK_REQUIRE(S && sU && W2 && b2 && gamma && dW2 && dgamma && db2, VKOCR_BAD_ARGUMENT, "mlp2_grad_finalize: null argument");
+    if (C == 0) return VKOCR_OK;
+    mlp2_grad_finalize_kernel<<<C, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(S, sU, W2, b2, gamma, C, K, dW2, dgamma, db2);
+    VK_CHECK_LAUNCH("mlp2_grad_finalize_kernel");
+    return VKOCR_OK;
+}
+
+int vkocr_unpack_grad(const float* g, int N, int T, int C, float* y, long long s_n, long long s_t, long long s_c, void* stream) {
+    VK_REQUIRE(g && y, VKOCR_BAD_ARGUMENT, "unpack_grad: null argument");
+    const long long total = (long long)N * T * C;
+    if (total == 0) return VKOCR_OK;
+    unpack_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, N, T, C, y, s_n, s_t, s_c);
+    VK_CHECK_LAUNCH("unpack_grad_kernel");
+    return VKOCR_OK;
+}
+
+// y += a  (fp32 vectors; gradient accumulation into .grad)
+int vkocr_accumulate_f32(const float* a, float* y, long long n, void* stream) {
+    VK_REQUIRE(a && y, VKOCR_BAD_ARGUMENT, "accumulate_f32: null argument");
+    if (n == 0) return VKOCR_OK;
+    axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, y, n);
+    VK_CHECK_LAUNCH("axpy_kernel");
+    return VKOCR_OK;
+}
+
+int vkocr_scale_rows(int dtype, const void* x, long long ld_x, void* y, long long ld_y, long long rows, int C, const float* scale,
+                     int rows_per_group, void* stream) {
+    VK_REQUIRE(x && y && scale && rows_per_group > 0, VKOCR_BAD_ARGUMENT, "scale_rows: bad argument");
+    const long long total = rows * C;
+    if (total == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (scale_rows_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                    reinterpret_cast<const T*>(x), ld_x, reinterpret_cast<T*>(y), ld_y, rows, C, scale, rows_per_group)));
+    VK_CHECK_LAUNCH("scale_rows_kernel");
+    return VKOCR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,470 @@
+// Memory-movement kernels of the neck / stem on NHWC activations:
+//   * bilinear / nearest up-sampling, forward (overwrite or add into a channel slice) and gather-form backward
+//     (F.interpolate(mode='bilinear'|'nearest', align_corners=False): upernext.py:79,178,191,237; fpn.py:125,138,197)
+//   * AdaptiveAvgPool2d forward/backward (upernext.py:59-65)
+//   * patchify gathers for the stride==kernel convolutions (helper.py:43-58), image and NHWC variants
+//   * channel-slice copy (torch.cat replacement: upernext.py:82,197; fpn.py:144)
+// All are HBM-bound: one thread per (pixel, 16-byte channel vector), coalesced along C.
+#include "common.cuh"
+
+namespace {
+
+struct Axis {
+    int i0, i1;
+    float w0, w1;
+};
+
+// PyTorch area_pixel_compute_source_index(align_corners=False) + clamp, for one destination coordinate.
+__device__ __forceinline__ Axis bilinear_axis(int d, int in, int out) {
+    const float scale = (float)in / (float)out;
+    float s = scale * (d + 0.5f) - 0.5f;
+    if (s < 0.f) s = 0.f;
+    int i0 = (int)s;
+    if (i0 > in - 1) i0 = in - 1;
+    const int i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    const float l = s - i0;
+    Axis a;
+    a.i0 = i0; a.i1 = i1; a.w0 = 1.f - l; a.w1 = l;
+    return a;
+}
+__device__ __forceinline__ int nearest_src(int d, int in, int out) {
+    const float scale = (float)in / (float)out;
+    int i = (int)floorf(d * scale);
+    return i < in - 1 ? i : in - 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_fwd_kernel(const T* __restrict__ src, long long ld_s, int h, int w, T* __restrict__ dst, long long ld_d, int H, int W,
+                    int B, int C, int mode, int accumulate) {
+    constexpr int V = VkVec<T>::N;
+    const int CV = C / V;
+    const long long total = (long long)B * H * W * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int X = (int)(r % W);
+    r /= W;
+    const int Y = (int)(r % H);
+    const int b = (int)(r / H);
+    const int c = cv * V;
+    float o[V];
+    const T* sb = src + (long long)b * h * w * ld_s + c;
+    if (mode == 0) {
+        const Axis ay = bilinear_axis(Y, h, H), ax = bilinear_axis(X, w, W);
+        VkVec<T> v00, v01, v10, v11;
+        v00.load(sb + ((long long)ay.i0 * w + ax.i0) * ld_s);
+        v01.load(sb + ((long long)ay.i0 * w + ax.i1) * ld_s);
+        v10.load(sb + ((long long)ay.i1 * w + ax.i0) * ld_s);
+        v11.load(sb + ((long long)ay.i1 * w + ax.i1) * ld_s);
+        float f00[V], f01[V], f10[V], f11[V];
+        v00.unpack(f00); v01.unpack(f01); v10.unpack(f10); v11.unpack(f11);
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            o[i] = ay.w0 * (ax.w0 * f00[i] + ax.w1 * f01[i]) + ay.w1 * (ax.w0 * f10[i] + ax.w1 * f11[i]);
+    } else {
+        const int sy = nearest_src(Y, h, H), sx = nearest_src(X, w, W);
+        VkVec<T> v;
+        v.load(sb + ((long long)sy * w + sx) * ld_s);
+        v.unpack(o);
+    }
+    T* dp = dst + (((long long)b * H + Y) * W + X) * ld_d + c;
+    if (accumulate) {
+        VkVec<T> d;
+        d.load(dp);
+        float f[V];
+        d.unpack(f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] += f[i];
+    }
+    VkVec<T> out;
+    out.pack(o);
+    out.store(dp);
+}
+
+// Gather-form adjoint: dsrc[b,i,j,:] (+)= sum over destination pixels that read (i,j) of weight * ddst.
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_bwd_kernel(const T* __restrict__ ddst, long long ld_d, int H, int W, T* __restrict__ dsrc, long long ld_s, int h, int w,
+                    int B, int C, int mode, int accumulate) {
+    constexpr int V = VkVec<T>::N;
+    const int CV = C / V;
+    const long long total = (long long)B * h * w * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int j = (int)(r % w);
+    r /= w;
+    const int i = (int)(r % h);
+    const int b = (int)(r / h);
+    const int c = cv * V;
+    // conservative candidate ranges of destination rows/cols touching source row i / col j
+    const float ry = (float)H / (float)h, rx = (float)W / (float)w;
+    int Ylo = (int)floorf((i - 1) * ry) - 2, Yhi = (int)ceilf((i + 2) * ry) + 2;
+    int Xlo = (int)floorf((j - 1) * rx) - 2, Xhi = (int)ceilf((j + 2) * rx) + 2;
+    if (Ylo < 0) Ylo = 0;
+    if (Xlo < 0) Xlo = 0;
+    if (Yhi > H - 1) Yhi = H - 1;
+    if (Xhi > W - 1) Xhi = W - 1;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    const T* db = ddst + (long long)b * H * W * ld_d + c;
+    for (int Y = Ylo; Y <= Yhi; ++Y) {
+        float wy;
+        if (mode == 0) {
+            const Axis a = bilinear_axis(Y, h, H);
+            wy = (a.i0 == i ? a.w0 : 0.f) + (a.i1 == i ? a.w1 : 0.f);
+        } else {
+            wy = nearest_src(Y, h, H) == i ? 1.f : 0.f;
+        }
+        if (wy == 0.f) continue;
+        for (int X = Xlo; X <= Xhi; ++X) {
+            float wx;
+            if (mode == 0) {
+                const Axis a = bilinear_axis(X, w, W);
+                wx = (a.i0 == j ? a.w0 : 0.f) + (a.i1 == j ? a.w1 : 0.f);
+            } else {
+                wx = nearest_src(X, w, W) == j ? 1.f : 0.f;
+            }
+            if (wx == 0.f) continue;
+            VkVec<T> v;
+            v.load(db + ((long long)Y * W + X) * ld_d);
+            float f[V];
+            v.unpack(f);
+            const float ww = wy * wx;
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] = fmaf(ww, f[e], acc[e]);
+        }
+    }
+    T* sp = dsrc + (((long long)b * h + i) * w + j) * ld_s + c;
+    if (accumulate) {
+        VkVec<T> d;
+        d.load(sp);
+        float f[V];
+        d.unpack(f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += f[e];
+    }
+    VkVec<T> out;
+    out.pack(acc);
+    out.store(sp);
+}
+
+// AdaptiveAvgPool2d: bin i = [floor(i*in/s), ceil((i+1)*in/s))
+__device__ __forceinline__ int bin_lo(int i, int in, int s) { return (i * in) / s; }
+__device__ __forceinline__ int bin_hi(int i, int in, int s) { return ((i + 1) * in + s - 1) / s; }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_fwd_kernel(const T* __restrict__ x, long long ld_x, int H, int W, T* __restrict__ y, long long ld_y, int S, int B, int C) {
+    constexpr int V = VkVec<T>::N;
+    const int CV = C / V;
+    const long long total = (long long)B * S * S * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int j = (int)(r % S);
+    r /= S;
+    const int i = (int)(r % S);
+    const int b = (int)(r / S);
+    const int c = cv * V;
+    const int y0 = bin_lo(i, H, S), y1 = bin_hi(i, H, S), x0 = bin_lo(j, W, S), x1 = bin_hi(j, W, S);
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx) {
+            VkVec<T> v;
+            v.load(x + (((long long)b * H + yy) * W + xx) * ld_x + c);
+            float f[V];
+            v.unpack(f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += f[e];
+        }
+    const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] *= inv;
+    VkVec<T> out;
+    out.pack(acc);
+    out.store(y + (((long long)b * S + i) * S + j) * ld_y + c);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_bwd_kernel(const T* __restrict__ dy, long long ld_y, int S, T* __restrict__ dx, long long ld_x, int H, int W, int B, int C,
+                   int accumulate) {
+    constexpr int V = VkVec<T>::N;
+    const int CV = C / V;
+    const long long total = (long long)B * H * W * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int xx = (int)(r % W);
+    r /= W;
+    const int yy = (int)(r % H);
+    const int b = (int)(r / H);
+    const int c = cv * V;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    for (int i = 0; i < S; ++i) {
+        const int y0 = bin_lo(i, H, S), y1 = bin_hi(i, H, S);
+        if (yy < y0 || yy >= y1) continue;
+        for (int j = 0; j < S; ++j) {
+            const int x0 = bin_lo(j, W, S), x1 = bin_hi(j, W, S);
+            if (xx < x0 || xx >= x1) continue;
+            VkVec<T> v;
+            v.load(dy + (((long long)b * S + i) * S + j) * ld_y + c);
+            float f[V];
+            v.unpack(f);
+            const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] = fmaf(inv, f[e], acc[e]);
+        }
+    }
+    T* dp = dx + (((long long)b * H + yy) * W + xx) * ld_x + c;
+    if (accumulate) {
+        VkVec<T> d;
+        d.load(dp);
+        float f[V];
+        d.unpack(f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += f[e];
+    }
+    VkVec<T> out;
+    out.pack(acc);
+    out.store(dp);
+}
+
+// image (B,Cin,H,W) fp32 NCHW -> rows [B*Ho*Wo, c_pad], k = (ky*p + kx)*Cin + ch, zero-padded to c_pad
+template <typename T>
+__global__ void __launch_bounds__(256)
+patchify_image_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, int p, T* __restrict__ out, int c_pad) {
+    const int Ho = H / p, Wo = W / p;
+    const long long total = (long long)B * Ho * Wo * c_pad;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k = (int)(idx % c_pad);
+    long long m = idx / c_pad;
+    const int xo = (int)(m % Wo);
+    m /= Wo;
+    const int yo = (int)(m % Ho);
+    const int b = (int)(m / Ho);
+    float v = 0.f;
+    if (k < p * p * Cin) {
+        const int ch = k % Cin;
+        const int kx = (k / Cin) % p;
+        const int ky = k / (Cin * p);
+        v = img[(((long long)b * Cin + ch) * H + yo * p + ky) * W + xo * p + kx];
+    }
+    out[idx] = vk_from_f32<T>(v);
+}
+
+// NHWC (B,H,W,C) -> (B,H/2,W/2,4C) with k = (ky*2+kx)*C + c  (dir 0), or the adjoint scatter (dir 1; pixels of an odd
+// trailing row/column get zero).  accumulate only applies to dir 1.
+template <typename T>
+__global__ void __launch_bounds__(256)
+space_to_depth2_kernel(T* __restrict__ x, long long ld_x, int B, int H, int W, int C, T* __restrict__ y, long long ld_y, int dir,
+                       int accumulate) {
+    constexpr int V = VkVec<T>::N;
+    const int CV = C / V;
+    const long long total = (long long)B * H * W * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int xx = (int)(r % W);
+    r /= W;
+    const int yy = (int)(r % H);
+    const int b = (int)(r / H);
+    const int c = cv * V;
+    const int Ho = H / 2, Wo = W / 2;
+    const int yo = yy >> 1, xo = xx >> 1;
+    const bool inside = yo < Ho && xo < Wo;
+    T* xp = x + (((long long)b * H + yy) * W + xx) * ld_x + c;
+    T* yp = y + (((long long)b * Ho + yo) * Wo + xo) * ld_y + ((yy & 1) * 2 + (xx & 1)) * C + c;
+    if (dir == 0) {
+        if (!inside) return;
+        VkVec<T> v;
+        v.load(xp);
+        v.store(yp);
+    } else {
+        float f[V];
+        if (inside) {
+            VkVec<T> v;
+            v.load(yp);
+            v.unpack(f);
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] = 0.f;
+        }
+        if (accumulate) {
+            VkVec<T> d;
+            d.load(xp);
+            float g[V];
+            d.unpack(g);
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] += g[e];
+        }
+        VkVec<T> out;
+        out.pack(f);
+        out.store(xp);
+    }
+}
+
+// dst[r, 0:C] (=|+=) src[r, 0:C]  with independent row strides (channel-slice concat / gradient accumulation)
+template <typename T>
+__global__ void __launch_bounds__(256)
+copy_channels_kernel(const T* __restrict__ src, long long ld_s, T* __restrict__ dst, long long ld_d, long long rows, int C,
+                     int accumulate, int vec) {
+    constexpr int V = VkVec<T>::N;
+    const int CV = vec ? C / V : C;
+    const long long total = rows * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    const long long r = idx / CV;
+    if (vec) {
+        VkVec<T> v;
+        v.load(src + r * ld_s + cv * V);
+        if (accumulate) {
+            VkVec<T> d;
+            d.load(dst + r * ld_d + cv * V);
+            float f[V], g[V];
+            v.unpack(f);
+            d.unpack(g);
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] += g[e];
+            v.pack(f);
+        }
+        v.store(dst + r * ld_d + cv * V);
+    } else {
+        float f = vk_to_f32(src[r * ld_s + cv]);
+        if (accumulate) f += vk_to_f32(dst[r * ld_d + cv]);
+        dst[r * ld_d + cv] = vk_from_f32<T>(f);
+    }
+}
+
+inline bool vec_ok(int dtype, int C, long long a, long long b) {
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    return C % V == 0 && a % V == 0 && b % V == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// mode 0 bilinear (align_corners=False), 1 nearest.  dst[b,Y,X,0:C] (=|+=) resample(src)[b,Y,X,0:C]
+int vkocr_upsample_fwd(int dtype, const void* src, long long ld_s, int h, int w, void* dst, long long ld_d, int H, int W, int B,
+                       int C, int mode, int accumulate, void* stream) {
+    VK_REQUIRE(src && dst, VKOCR_BAD_ARGUMENT, "upsample_fwd: null argument");
+    VK_REQUIRE(mode == 0 || mode == 1, VKOCR_BAD_ARGUMENT, "upsample_fwd: mode %d", mode);
+    VK_REQUIRE(vec_ok(dtype, C, ld_s, ld_d), VKOCR_BAD_ALIGN, "upsample_fwd: C %d / strides not vector aligned", C);
+    VK_REQUIRE(h > 0 && w > 0, VKOCR_BAD_SHAPE, "upsample_fwd: empty source");
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    const long long total = (long long)B * H * W * (C / V);
+    if (total == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (upsample_fwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                    reinterpret_cast<const T*>(src), ld_s, h, w, reinterpret_cast<T*>(dst), ld_d, H, W, B, C, mode,
+                                    accumulate)));
+    VK_CHECK_LAUNCH("upsample_fwd_kernel");
+    return VKOCR_OK;
+}
+
+// dsrc[b,i,j,0:C] (=|+=) adjoint of vkocr_upsample_fwd applied to ddst
+int vkocr_upsample_bwd(int dtype, const void* ddst, long long ld_d, int H, int W, void* dsrc, long long ld_s, int h, int w, int B,
+                       int C, int mode, int accumulate, void* stream) {
+    VK_REQUIRE(ddst && dsrc, VKOCR_BAD_ARGUMENT, "upsample_bwd: null argument");
+    VK_REQUIRE(mode == 0 || mode == 1, VKOCR_BAD_ARGUMENT, "upsample_bwd: mode %d", mode);
+    VK_REQUIRE(vec_ok(dtype, C, ld_s, ld_d), VKOCR_BAD_ALIGN, "upsample_bwd: C %d / strides not vector aligned", C);
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    const long long total = (long long)B * h * w * (C / V);
+    if (total == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (upsample_bwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                    reinterpret_cast<const T*>(ddst), ld_d, H, W, reinterpret_cast<T*>(dsrc), ld_s, h, w, B, C, mode,
+                                    accumulate)));
+    VK_CHECK_LAUNCH("upsample_bwd_kernel");
+    return VKOCR_OK;
+}
+
+int vkocr_avgpool_fwd(int dtype, const void* x, long long ld_x, int H, int W, void* y, long long ld_y, int S, int B, int C,
+                      void* stream) {
+    VK_REQUIRE(x && y && S >= 1, VKOCR_BAD_ARGUMENT, "avgpool_fwd: bad argument");
+    VK_REQUIRE(vec_ok(dtype, C, ld_x, ld_y), VKOCR_BAD_ALIGN, "avgpool_fwd: C %d / strides not vector aligned", C);
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    const long long total = (long long)B * S * S * (C / V);
+    if (total == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (avgpool_fwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                    reinterpret_cast<const T*>(x), ld_x, H, W, reinterpret_cast<T*>(y), ld_y, S, B, C)));
+    VK_CHECK_LAUNCH("avgpool_fwd_kernel");
+    return VKOCR_OK;
+}
+
+int vkocr_avgpool_bwd(int dtype, const void* dy, long long ld_y, int S, void* dx, long long ld_x, int H, int W, int B, int C,
+                      int accumulate, void* stream) {
+    VK_REQUIRE(dy && dx && S >= 1, VKOCR_BAD_ARGUMENT, "avgpool_bwd: bad argument");
+    VK_REQUIRE(vec_ok(dtype, C, ld_x, ld_y), VKOCR_BAD_ALIGN, "avgpool_bwd: C %d / strides not vector aligned", C);
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    const long long total = (long long)B * H * W * (C / V);
+    if (total == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (avgpool_bwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                    reinterpret_cast<const T*>(dy), ld_y, S, reinterpret_cast<T*>(dx), ld_x, H, W, B, C, accumulate)));
+    VK_CHECK_LAUNCH("avgpool_bwd_kernel");
+    return VKOCR_OK;
+}
+
+// img fp32 NCHW (B,Cin,H,W) -> out [B*(H/p)*(W/p), c_pad] storage dtype
+int vkocr_patchify_image(int dtype, const float* img, int B, int Cin, int H, int W, int p, void* out, int c_pad, void* stream) {
+    VK_REQUIRE(img && out && p >= 1, VKOCR_BAD_ARGUMENT, "patchify_image: bad argument");
+    VK_REQUIRE(c_pad >= p * p * Cin, VKOCR_BAD_SHAPE, "patchify_image: c_pad %d < %d", c_pad, p * p * Cin);
+    const long long total = (long long)B * (H / p) * (W / p) * c_pad;
+    if (total == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (patchify_image_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                    img, B, Cin, H, W, p, reinterpret_cast<T*>(out), c_pad)));
+    VK_CHECK_LAUNCH("patchify_image_kernel");
+    return VKOCR_OK;
+}
+
+// dir 0: y[B,H/2,W/2,4C] = gather(x[B,H,W,C]);  dir 1: x (=|+=) scatter(y)
+int vkocr_space_to_depth2(int dtype, void* x, long long ld_x, int B, int H, int W, int C, void* y, long long ld_y, int dir,
+                          int accumulate, void* stream) {
+    VK_REQUIRE(x && y, VKOCR_BAD_ARGUMENT, "space_to_depth2: null argument");
+    VK_REQUIRE(vec_ok(dtype, C, ld_x, ld_y), VKOCR_BAD_ALIGN, "space_to_depth2: C %d / strides not vector aligned", C);
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    const long long total = (long long)B * H * W * (C / V);
+    if (total == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (space_to_depth2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                    reinterpret_cast<T*>(x), ld_x, B, H, W, C, reinterpret_cast<T*>(y), ld_y, dir, accumulate)));
+    VK_CHECK_LAUNCH("space_to_depth2_kernel");
+    return VKOCR_OK;
+}
+
+int vkocr_copy_channels(int dtype, const void* src, long long ld_s, void* dst, long long ld_d, long long rows, int C, int accumulate,
+                        void* stream) {
+    VK_REQUIRE(src && dst, VKOCR_BAD_ARGUMENT, "copy_channels: null argument");
+    if (rows == 0 || C == 0) return VKOCR_OK;
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    const int esz = dtype == VKOCR_F32 ? 4 : 2;
+    const int vec = vec_ok(dtype, C, ld_s, ld_d) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+    (void)esz;
+    const long long total = rows * (vec ? C / V : C);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (copy_channels_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                    reinterpret_cast<const T*>(src), ld_s, reinterpret_cast<T*>(dst), ld_d, rows, C, accumulate, vec)));
+    VK_CHECK_LAUNCH("copy_channels_kernel");
+    return VKOCR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,722 @@
+"""Host-side operators of the adaptive-scaling hot path: thin Python over the C ABI of ``libvkocr_b200.so``.
+
+Every compute step is a hand-written sm_100a kernel reached through ``_lib.LIB``; PyTorch here only owns device
+memory, streams and the autograd tape (``torch.autograd.Function`` nodes whose forward/backward call the C ABI).
+
+Activation layout: logical ``(B, C, H, W)`` tensors whose memory is NHWC ("channels last") with a pixel stride
+``ld >= C`` that is a multiple of 8 elements, so that a channel vector is 16 bytes and TMA strides are legal.
+Parameter gradients are accumulated by the kernels straight into ``param.grad`` (fp32), which is what the
+data-parallel bucket views alias (see ``parallel.py``).
+"""
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+LN_EPS = 1e-6  # reference helper.ln: nn.LayerNorm(C, eps=1e-6) (model/helper.py:96-97)
+
+BILINEAR = 0
+NEAREST = 1
+
+
+def _ceil_to(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+# ----------------------------------------------------------------------------------------------------- layout helpers
+def alloc_nhwc(B: int, H: int, W: int, C: int, dtype: torch.dtype, device, zero: bool = False, ld: Optional[int] = None) -> Tensor:
+    """(B, C, H, W)-shaped view of a fresh NHWC buffer with pixel stride ``ld`` (default: C rounded up to 8)."""
+    ld = _ceil_to(C, 8) if ld is None else ld
+    buf = (torch.zeros if zero else torch.empty)((B, H, W, ld), dtype=dtype, device=device)
+    return buf[..., :C].permute(0, 3, 1, 2)
+
+
+def is_nhwc(x: Tensor) -> bool:
+    if x.dim() != 4:
+        return False
+    B, C, H, W = x.shape
+    ld = x.stride(3)
+    if C > 1 and x.stride(1) != 1:
+        return False
+    if ld < C or ld % 8 != 0:
+        return False
+    if W > 1 and False:
+        return False
+    ok = (H == 1 or x.stride(2) == W * ld) and (B == 1 or x.stride(0) == H * W * ld)
+    return bool(ok) and x.data_ptr() % 16 == 0
+
+
+def to_nhwc(x: Tensor, dtype: torch.dtype) -> Tensor:
+    """Boundary conversion of a caller's (B,C,H,W) tensor to the internal layout / storage dtype."""
+    L.require_cuda(x)
+    if x.dtype == dtype and is_nhwc(x):
+        return x
+    B, C, H, W = x.shape
+    out = alloc_nhwc(B, H, W, C, dtype, x.device)
+    out.copy_(x)  # boundary plumbing only (layout/dtype change of caller-provided tensors)
+    return out
+
+
+def geom(x: Tensor) -> Tuple[int, int, int, int, int]:
+    B, C, H, W = x.shape
+    return B, H, W, C, x.stride(3)
+
+
+def grad_buffer(p: Tensor) -> Tensor:
+    """fp32 ``.grad`` of a parameter, created zeroed on first use; kernels accumulate into it."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+    g = p.grad
+    if g.dtype != torch.float32 or not g.is_contiguous():
+        raise L.VkocrError('vkocr_b200 accumulates parameter gradients into contiguous fp32 .grad buffers')
+    return g
+
+
+def _s() -> ctypes.c_void_p:
+    return L.stream_ptr()
+
+
+def _tag(dtype: torch.dtype) -> int:
+    return L.dtype_tag(dtype)
+
+
+# ----------------------------------------------------------------------------------------------------- packed weights
+class _PackCache:
+    """Kernel-layout copies of the fp32 master weights, refreshed when the parameter's version counter moves."""
+
+    def __init__(self) -> None:
+        self.entries: Dict[Tuple, Tuple[int, Tensor]] = {}
+
+    def get(self, key: Tuple, params: Sequence[Tensor], shape: Tuple[int, ...], dtype: torch.dtype, fill) -> Tensor:
+        version = tuple(int(p._version) for p in params) + tuple(int(p.data_ptr()) for p in params)
+        ent = self.entries.get(key)
+        if ent is not None and ent[0] == version and ent[1].device == params[0].device:
+            return ent[1]
+        if ent is not None and ent[1].shape == shape and ent[1].dtype == dtype and ent[1].device == params[0].device:
+            buf = ent[1]
+        else:
+            buf = torch.zeros(shape, dtype=dtype, device=params[0].device)
+        fill(buf)
+        self.entries[key] = (version, buf)
+        return buf
+
+    def clear(self) -> None:
+        self.entries.clear()
+
+
+PACK = _PackCache()
+
+
+def _pack(w: Tensor, s_row: int, s_tap: int, s_col: int, rows: int, taps: int, cols: int, flip: int,
+          col_scale: Optional[Tensor], out: Tensor, out_offset: int, o_row: int, o_tap: int) -> None:
+    esz = out.element_size()
+    L.check(L.LIB.vkocr_pack_weight(L.ptr(w), s_row, s_tap, s_col, rows, taps, cols, flip, L.ptr(col_scale),
+                                    ctypes.c_void_p(out.data_ptr() + out_offset * esz), _tag(out.dtype), o_row, o_tap, _s()),
+            'pack_weight')
+
+
+def packed_linear_fwd(w: Tensor, dtype: torch.dtype) -> Tuple[Tensor, int]:
+    """Linear weight (N, K) -> [N, c_pad] K-major operand."""
+    N, K = w.shape
+    c_pad = _ceil_to(K, 64)
+    buf = PACK.get(('lin_fwd', id(w), dtype), [w], (N, c_pad), dtype,
+                   lambda b: _pack(w.detach(), K, 0, 1, N, 1, K, 0, None, b, 0, c_pad, 0))
+    return buf, c_pad
+
+
+def packed_linear_dgrad(w: Tensor, dtype: torch.dtype, col_scale: Optional[Tensor] = None) -> Tuple[Tensor, int]:
+    """Linear weight (N, K) -> [K, n_pad] operand of dX = dY . W (optionally with W rows scaled by col_scale[n])."""
+    N, K = w.shape
+    n_pad = _ceil_to(N, 64)
+    params = [w] if col_scale is None else [w, col_scale]
+    buf = PACK.get(('lin_dgrad', id(w), dtype, col_scale is not None), params, (K, n_pad), dtype,
+                   lambda b: _pack(w.detach(), 1, 0, K, K, 1, N, 0, None if col_scale is None else col_scale.detach(), b, 0, n_pad, 0))
+    return buf, n_pad
+
+
+def packed_conv_fwd(ws: Sequence[Tensor], dtype: torch.dtype, n_slot: Optional[int] = None) -> Tuple[Tensor, int, int]:
+    """Conv2d weights (N_h, C, k, k) of one or several heads -> [sum slots, k*k, c_pad]; each head gets ``n_slot`` rows."""
+    C, k = ws[0].shape[1], ws[0].shape[2]
+    T = k * k
+    c_pad = _ceil_to(C, 64)
+    slot = n_slot if n_slot is not None else ws[0].shape[0]
+    rows = slot * len(ws)
+
+    def fill(b: Tensor) -> None:
+        for h, w in enumerate(ws):
+            _pack(w.detach(), C * T, 1, T, w.shape[0], T, C, 0, None, b, h * slot * T * c_pad, T * c_pad, c_pad)
+
+    buf = PACK.get(('conv_fwd', tuple(id(w) for w in ws), dtype, slot), list(ws), (rows, T * c_pad), dtype, fill)
+    return buf, c_pad, rows
+
+
+def packed_conv_dgrad(ws: Sequence[Tensor], dtype: torch.dtype, n_slot: Optional[int] = None) -> Tuple[Tensor, int]:
+    """Conv2d weights -> [C, k*k (mirrored), n_pad] operand of the data gradient (a 'same' conv of dY with flipped taps)."""
+    C, k = ws[0].shape[1], ws[0].shape[2]
+    T = k * k
+    slot = n_slot if n_slot is not None else ws[0].shape[0]
+    n_pad = _ceil_to(slot * len(ws), 64)
+
+    def fill(b: Tensor) -> None:
+        for h, w in enumerate(ws):
+            _pack(w.detach(), T, 1, C * T, C, T, w.shape[0], 1, None, b, h * slot, T * n_pad, n_pad)
+
+    buf = PACK.get(('conv_dgrad', tuple(id(w) for w in ws), dtype, slot), list(ws), (C, T * n_pad), dtype, fill)
+    return buf, n_pad
+
+
+def packed_patch_fwd(w: Tensor, dtype: torch.dtype) -> Tuple[Tensor, int]:
+    """Patchify conv weight (N, C, p, p), stride p -> [N, c_pad] with k = (ky*p+kx)*C + c."""
+    N, C, p, _ = w.shape
+    T = p * p
+    c_pad = _ceil_to(T * C, 64)
+    buf = PACK.get(('patch_fwd', id(w), dtype), [w], (N, c_pad), dtype,
+                   lambda b: _pack(w.detach(), C * T, 1, T, N, T, C, 0, None, b, 0, c_pad, C))
+    return buf, c_pad
+
+
+def packed_patch_dgrad(w: Tensor, dtype: torch.dtype) -> Tuple[Tensor, int]:
+    """Patchify conv weight (N, C, p, p) -> [(t*C + c), n_pad] operand of dA = dY . W."""
+    N, C, p, _ = w.shape
+    T = p * p
+    n_pad = _ceil_to(N, 64)
+    buf = PACK.get(('patch_dgrad', id(w), dtype), [w], (T * C, n_pad), dtype,
+                   lambda b: _pack(w.detach(), T, 1, C * T, C, T, N, 0, None, b, 0, n_pad, C * n_pad))
+    return buf, n_pad
+
+
+def packed_dwconv(w: Tensor, flip: bool) -> Tensor:
+    """Depthwise weight (C,1,7,7) -> fp32 tap table [49][C] (mirrored for the data gradient)."""
+    C = w.shape[0]
+    return PACK.get(('dw', id(w), flip), [w], (49, C), torch.float32,
+                    lambda b: _pack(w.detach(), 0, 1, 49, 1, 49, C, 1 if flip else 0, None, b, 0, 0, C))
+
+
+# ----------------------------------------------------------------------------------------------------- raw kernel calls
+def _epilogue(out: Tensor, ldo: int, *, out_f32: bool = False, accumulate: bool = False, out_pre: Optional[Tensor] = None,
+              ld_pre: int = 0, bias: Optional[Tensor] = None, act: int = 0, col_scale: Optional[Tensor] = None,
+              row_scale: Optional[Tensor] = None, rows_per_group: int = 1, residual: Optional[Tensor] = None, ld_res: int = 0,
+              aux: Optional[Tensor] = None, ld_aux: int = 0, tn: Tuple[int, int, int] = (0, 0, 0)) -> L.Epilogue:
+    return L.Epilogue(out.data_ptr(), ldo, int(out_f32), int(accumulate),
+                      None if out_pre is None else out_pre.data_ptr(), ld_pre,
+                      None if bias is None else bias.data_ptr(), act,
+                      None if col_scale is None else col_scale.data_ptr(),
+                      None if row_scale is None else row_scale.data_ptr(), rows_per_group,
+                      None if residual is None else residual.data_ptr(), ld_res,
+                      None if aux is None else aux.data_ptr(), ld_aux, tn[0], tn[1], tn[2])
+
+
+SIMT_BACKEND = 0  # tests set this to 1 to route bf16 GEMMs through the SIMT kernel (cross-check of the tcgen05 path)
+
+
+def gemm_nt(x: Tensor, B: int, H: int, W: int, C: int, ld_x: int, ks: int, wp: Tensor, c_pad: int, N: int, ep: L.Epilogue) -> None:
+    g = L.ConvGeom(B, H, W, ks, C, ld_x, c_pad)
+    L.check(L.LIB.vkocr_gemm_nt(_tag(x.dtype), SIMT_BACKEND, L.ptr(x), ctypes.byref(g), L.ptr(wp), N, ctypes.byref(ep), _s()), 'gemm_nt')
+
+
+def gemm_tn(p: Tensor, B: int, H: int, W: int, I: int, ld_p: int, ks: int, q: Tensor, J: int, ld_q: int, ep: L.Epilogue) -> None:
+    g = L.ConvGeom(B, H, W, ks, I, ld_p, 0)
+    L.check(L.LIB.vkocr_gemm_tn(_tag(p.dtype), SIMT_BACKEND, L.ptr(p), ctypes.byref(g), L.ptr(q), J, ld_q, ctypes.byref(ep), _s()), 'gemm_tn')
+
+
+def layernorm_fwd(x: Tensor, ld_x: int, y: Tensor, ld_y: int, rows: int, C: int, gamma: Tensor, beta: Tensor, act: int,
+                  mean: Optional[Tensor], rstd: Optional[Tensor]) -> None:
+    L.check(L.LIB.vkocr_layernorm_fwd(_tag(x.dtype), L.ptr(x), ld_x, L.ptr(y), ld_y, rows, C, L.ptr(gamma), L.ptr(beta), LN_EPS, act,
+                                      L.ptr(mean), L.ptr(rstd), _s()), 'layernorm_fwd')
+
+
+def layernorm_bwd(dy: Tensor, ld_dy: int, x: Tensor, ld_x: int, mean: Tensor, rstd: Tensor, gamma: Tensor, beta: Tensor, act: int,
+                  dx: Tensor, ld_dx: int, rows: int, C: int, dgamma: Optional[Tensor], dbeta: Optional[Tensor],
+                  dxsum: Optional[Tensor]) -> None:
+    L.check(L.LIB.vkocr_layernorm_bwd(_tag(x.dtype), L.ptr(dy), ld_dy, L.ptr(x), ld_x, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
+                                      L.ptr(beta), act, L.ptr(dx), ld_dx, rows, C, L.ptr(dgamma), L.ptr(dbeta), L.ptr(dxsum), _s()),
+            'layernorm_bwd')
+
+
+def colsum(x: Tensor, ld: int, rows: int, C: int, out: Tensor) -> None:
+    L.check(L.LIB.vkocr_colsum(_tag(x.dtype), L.ptr(x), ld, rows, C, L.ptr(out), _s()), 'colsum')
+
+
+def dwconv7(x: Tensor, y: Tensor, wt: Tensor, bias: Optional[Tensor], add: Optional[Tensor]) -> None:
+    B, H, W, C, ld_x = geom(x)
+    L.check(L.LIB.vkocr_dwconv7_fwd(_tag(x.dtype), L.ptr(x), ld_x, L.ptr(y), y.stride(3), B, H, W, C, L.ptr(wt), L.ptr(bias),
+                                    L.ptr(add), 0 if add is None else add.stride(3), _s()), 'dwconv7_fwd')
+
+
+def dwconv7_wgrad(dy: Tensor, x: Tensor, dw: Tensor) -> None:
+    B, H, W, C, ld_x = geom(x)
+    L.check(L.LIB.vkocr_dwconv7_wgrad(_tag(x.dtype), L.ptr(dy), dy.stride(3), L.ptr(x), ld_x, B, H, W, C, L.ptr(dw), _s()),
+            'dwconv7_wgrad')
+
+
+def upsample_fwd(src: Tensor, dst: Tensor, C: int, mode: int, accumulate: bool) -> None:
+    """dst[:, :C] (=|+=) resample(src[:, :C]); src/dst are NHWC views (possibly channel slices of wider buffers)."""
+    B, _, h, w = src.shape
+    _, _, H, W = dst.shape
+    L.check(L.LIB.vkocr_upsample_fwd(_tag(src.dtype), L.ptr(src), src.stride(3), h, w, L.ptr(dst), dst.stride(3), H, W, B, C, mode,
+                                     int(accumulate), _s()), 'upsample_fwd')
+
+
+def upsample_bwd(ddst: Tensor, dsrc: Tensor, C: int, mode: int, accumulate: bool) -> None:
+    B, _, h, w = dsrc.shape
+    _, _, H, W = ddst.shape
+    L.check(L.LIB.vkocr_upsample_bwd(_tag(ddst.dtype), L.ptr(ddst), ddst.stride(3), H, W, L.ptr(dsrc), dsrc.stride(3), h, w, B, C,
+                                     mode, int(accumulate), _s()), 'upsample_bwd')
+
+
+def copy_channels(src: Tensor, dst: Tensor, C: int, accumulate: bool = False) -> None:
+    B, _, H, W = src.shape
+    L.check(L.LIB.vkocr_copy_channels(_tag(src.dtype), L.ptr(src), src.stride(3), L.ptr(dst), dst.stride(3), B * H * W, C,
+                                      int(accumulate), _s()), 'copy_channels')
+
+
+def _zeros_f32(n: int, device) -> Tensor:
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+def _needs_grad(*ts: Optional[Tensor]) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+# ----------------------------------------------------------------------------------------------------- autograd nodes
+class StemFn(torch.autograd.Function):
+    """pconv(p x p, stride p) + bias -> LayerNorm, image NCHW fp32 -> NHWC (convnext.py:106-123, helper.py:43-58)."""
+
+    @staticmethod
+    def forward(ctx, image: Tensor, w: Tensor, b: Tensor, ln_w: Tensor, ln_b: Tensor, dtype: torch.dtype) -> Tensor:
+        L.require_cuda(image, w)
+        image = image.contiguous().float()
+        B, Cin, H, W = image.shape
+        N, _, p, _ = w.shape
+        Ho, Wo = H // p, W // p
+        M = B * Ho * Wo
+        wp, c_pad = packed_patch_fwd(w, dtype)
+        a = torch.empty((M, c_pad), dtype=dtype, device=image.device)
+        L.check(L.LIB.vkocr_patchify_image(_tag(dtype), L.ptr(image), B, Cin, H, W, p, L.ptr(a), c_pad, _s()), 'patchify_image')
+        pre = alloc_nhwc(B, Ho, Wo, N, dtype, image.device)
+        gemm_nt(a, 1, 1, M, c_pad, c_pad, 1, wp, c_pad, N, _epilogue(pre, pre.stride(3), bias=b.detach()))
+        y = alloc_nhwc(B, Ho, Wo, N, dtype, image.device)
+        train = _needs_grad(w, b, ln_w, ln_b)
+        mean = torch.empty(M, dtype=torch.float32, device=image.device) if train else None
+        rstd = torch.empty(M, dtype=torch.float32, device=image.device) if train else None
+        layernorm_fwd(pre, pre.stride(3), y, y.stride(3), M, N, ln_w.detach(), ln_b.detach(), 0, mean, rstd)
+        if train:
+            ctx.save_for_backward(a, pre, mean, rstd, w, b, ln_w, ln_b)
+            ctx.meta = (M, N, c_pad, Cin, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        a, pre, mean, rstd, w, b, ln_w, ln_b = ctx.saved_tensors
+        M, N, c_pad, Cin, p = ctx.meta
+        dy = to_nhwc(dy, pre.dtype)
+        dpre = torch.empty_like(pre)
+        layernorm_bwd(dy, dy.stride(3), pre, pre.stride(3), mean, rstd, ln_w.detach(), ln_b.detach(), 0, dpre, dpre.stride(3), M, N,
+                      grad_buffer(ln_w), grad_buffer(ln_b), grad_buffer(b))
+        K = p * p * Cin
+        g = _zeros_f32(N * K, dy.device)
+        gemm_tn(dpre, 1, 1, M, N, dpre.stride(3), 1, a, K, c_pad, _epilogue(g, K, out_f32=True, accumulate=True, tn=(0, K, 1)))
+        # GEMM order k = (t, c)  ->  parameter layout (n, c, t)
+        L.check(L.LIB.vkocr_unpack_grad(L.ptr(g), N, p * p, Cin, L.ptr(grad_buffer(w)), Cin * p * p, 1, p * p, _s()), 'unpack_grad')
+        return None, None, None, None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    """Channels-last LayerNorm, optionally followed by exact GELU (helper.py:96-101)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Tensor, act: int) -> Tensor:
+        B, H, W, C, ld = geom(x)
+        y = alloc_nhwc(B, H, W, C, x.dtype, x.device)
+        train = _needs_grad(x, w, b)
+        M = B * H * W
+        mean = torch.empty(M, dtype=torch.float32, device=x.device) if train else None
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device) if train else None
+        layernorm_fwd(x, ld, y, y.stride(3), M, C, w.detach(), b.detach(), act, mean, rstd)
+        if train:
+            ctx.save_for_backward(x, mean, rstd, w, b)
+            ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, mean, rstd, w, b = ctx.saved_tensors
+        B, H, W, C, ld = geom(x)
+        dy = to_nhwc(dy, x.dtype)
+        dx = alloc_nhwc(B, H, W, C, x.dtype, x.device)
+        layernorm_bwd(dy, dy.stride(3), x, ld, mean, rstd, w.detach(), b.detach(), ctx.act, dx, dx.stride(3), B * H * W, C,
+                      grad_buffer(w), grad_buffer(b), None)
+        return dx, None, None, None
+
+
+class ConvNextLayerFn(torch.autograd.Function):
+    """x + mask * scale * Linear2(GELU(Linear1(LN(dwconv7x7(x)))))  (ConvNextBlockLayer, convnext.py:20-59)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale, drop_mask: Optional[Tensor]) -> Tensor:
+        B, H, W, C, ld = geom(x)
+        M = B * H * W
+        dt, dev = x.dtype, x.device
+        train = _needs_grad(x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale)
+        conv = alloc_nhwc(B, H, W, C, dt, dev)
+        dwconv7(x, conv, packed_dwconv(dw_w, False), dw_b.detach(), None)
+        lnout = alloc_nhwc(B, H, W, C, dt, dev)
+        mean = torch.empty(M, dtype=torch.float32, device=dev) if train else None
+        rstd = torch.empty(M, dtype=torch.float32, device=dev) if train else None
+        layernorm_fwd(conv, conv.stride(3), lnout, lnout.stride(3), M, C, ln_w.detach(), ln_b.detach(), 0, mean, rstd)
+        hid = 4 * C
+        w1p, c1 = packed_linear_fwd(w1, dt)
+        g = torch.empty((M, hid), dtype=dt, device=dev)
+        hpre = torch.empty((M, hid), dtype=dt, device=dev) if train else None
+        gemm_nt(lnout, 1, 1, M, C, lnout.stride(3), 1, w1p, c1, hid,
+                _epilogue(g, hid, out_pre=hpre, ld_pre=hid, bias=b1.detach(), act=1))
+        w2p, c2 = packed_linear_fwd(w2, dt)
+        y = alloc_nhwc(B, H, W, C, dt, dev)
+        gamma = scale.detach().reshape(-1)
+        gemm_nt(g, 1, 1, M, hid, hid, 1, w2p, c2, C,
+                _epilogue(y, y.stride(3), bias=b2.detach(), col_scale=gamma, row_scale=drop_mask, rows_per_group=H * W,
+                          residual=x, ld_res=ld))
+        if train:
+            ctx.save_for_backward(x, conv, mean, rstd, lnout, hpre, g, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale,
+                                  drop_mask if drop_mask is not None else torch.empty(0, device=dev))
+            ctx.has_mask = drop_mask is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, conv, mean, rstd, lnout, hpre, g, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale, mask = ctx.saved_tensors
+        B, H, W, C, ld = geom(x)
+        M = B * H * W
+        hid = 4 * C
+        dt, dev = x.dtype, x.device
+        dy = to_nhwc(dy, dt)
+        gamma = scale.detach().reshape(-1)
+        if ctx.has_mask:
+            u = alloc_nhwc(B, H, W, C, dt, dev)
+            L.check(L.LIB.vkocr_scale_rows(_tag(dt), L.ptr(dy), dy.stride(3), L.ptr(u), u.stride(3), M, C, L.ptr(mask), H * W, _s()),
+                    'scale_rows')
+        else:
+            u = dy
+        su = _zeros_f32(C, dev)
+        colsum(u, u.stride(3), M, C, su)
+        # dH_pre = (U . (gamma * W2)) * gelu'(H_pre)
+        w2d, n2 = packed_linear_dgrad(w2, dt, gamma)
+        dh = torch.empty((M, hid), dtype=dt, device=dev)
+        gemm_nt(u, 1, 1, M, C, u.stride(3), 1, w2d, n2, hid, _epilogue(dh, hid, act=2, aux=hpre, ld_aux=hid))
+        # S[c,k] = sum_p U[p,c] G[p,k]  -> dW2, dscale, db2
+        s = _zeros_f32(C * hid, dev)
+        gemm_tn(u, 1, 1, M, C, u.stride(3), 1, g, hid, hid, _epilogue(s, hid, out_f32=True, accumulate=True, tn=(0, hid, 1)))
+        L.check(L.LIB.vkocr_mlp2_grad_finalize(L.ptr(s), L.ptr(su), L.ptr(w2.detach()), L.ptr(b2.detach()), L.ptr(gamma), C, hid,
+                                               L.ptr(grad_buffer(w2)), L.ptr(grad_buffer(scale)), L.ptr(grad_buffer(b2)), _s()),
+                'mlp2_grad_finalize')
+        del s, g
+        colsum(dh, hid, M, hid, grad_buffer(b1))
+        gw1 = grad_buffer(w1)
+        gemm_tn(dh, 1, 1, M, hid, hid, 1, lnout, C, lnout.stride(3), _epilogue(gw1, C, out_f32=True, accumulate=True, tn=(0, C, 1)))
+        w1d, n1 = packed_linear_dgrad(w1, dt)
+        dln = alloc_nhwc(B, H, W, C, dt, dev)
+        gemm_nt(dh, 1, 1, M, hid, hid, 1, w1d, n1, C, _epilogue(dln, dln.stride(3)))
+        del dh
+        dconv = alloc_nhwc(B, H, W, C, dt, dev)
+        layernorm_bwd(dln, dln.stride(3), conv, conv.stride(3), mean, rstd, ln_w.detach(), ln_b.detach(), 0, dconv, dconv.stride(3), M,
+                      C, grad_buffer(ln_w), grad_buffer(ln_b), grad_buffer(dw_b))
+        dwconv7_wgrad(dconv, x, grad_buffer(dw_w))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = alloc_nhwc(B, H, W, C, dt, dev)
+            dwconv7(dconv, dx, packed_dwconv(dw_w, True), None, dy)   # + residual gradient
+        return (dx,) + (None,) * 10
+
+
+class PatchConvFn(torch.autograd.Function):
+    """pconv2x2 (kernel 2, stride 2) on NHWC = space-to-depth gather + GEMM (helper.py:43-49, convnext.py:89-99)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Tensor) -> Tensor:
+        B, H, W, C, ld = geom(x)
+        N = w.shape[0]
+        if w.shape[2] != 2:
+            raise L.VkocrError('vkocr_b200 PatchConvFn supports the 2x2/stride-2 down-sampling conv only')
+        Ho, Wo = H // 2, W // 2
+        M = B * Ho * Wo
+        dt, dev = x.dtype, x.device
+        wp, c_pad = packed_patch_fwd(w, dt)
+        zero = c_pad != 4 * C
+        a = (torch.zeros if zero else torch.empty)((M, c_pad), dtype=dt, device=dev)
+        L.check(L.LIB.vkocr_space_to_depth2(_tag(dt), L.ptr(x), ld, B, H, W, C, L.ptr(a), c_pad, 0, 0, _s()), 'space_to_depth2')
+        y = alloc_nhwc(B, Ho, Wo, N, dt, dev)
+        gemm_nt(a, 1, 1, M, 4 * C, c_pad, 1, wp, c_pad, N, _epilogue(y, y.stride(3), bias=b.detach()))
+        if _needs_grad(x, w, b):
+            ctx.save_for_backward(a, w, b)
+            ctx.meta = (B, H, W, C, N, c_pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        a, w, b = ctx.saved_tensors
+        B, H, W, C, N, c_pad = ctx.meta
+        dt, dev = a.dtype, a.device
+        M = a.shape[0]
+        dy = to_nhwc(dy, dt)
+        colsum(dy, dy.stride(3), M, N, grad_buffer(b))
+        K = 4 * C
+        g = _zeros_f32(N * K, dev)
+        gemm_tn(dy, 1, 1, M, N, dy.stride(3), 1, a, K, c_pad, _epilogue(g, K, out_f32=True, accumulate=True, tn=(0, K, 1)))
+        L.check(L.LIB.vkocr_unpack_grad(L.ptr(g), N, 4, C, L.ptr(grad_buffer(w)), C * 4, 1, 4, _s()), 'unpack_grad')
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wd, n_pad = packed_patch_dgrad(w, dt)
+            da = torch.empty((M, K), dtype=dt, device=dev)
+            gemm_nt(dy, 1, 1, M, N, dy.stride(3), 1, wd, n_pad, K, _epilogue(da, K))
+            dx = alloc_nhwc(B, H, W, C, dt, dev)
+            L.check(L.LIB.vkocr_space_to_depth2(_tag(dt), L.ptr(dx), dx.stride(3), B, H, W, C, L.ptr(da), K, 1, 0, _s()),
+                    'space_to_depth2(adjoint)')
+        return dx, None, None
+
+
+class ConvLnGeluFn(torch.autograd.Function):
+    """k x k 'same' conv (k = 1 is the Linear of build_conv1x1_block) + bias -> LayerNorm -> GELU
+    (upernext.py:21-45, fpn.py:21-48), as an implicit GEMM on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Tensor, ln_w: Tensor, ln_b: Tensor) -> Tensor:
+        B, H, W, C, ld = geom(x)
+        dt, dev = x.dtype, x.device
+        if w.dim() == 2:
+            N, ks = w.shape[0], 1
+            wp, c_pad = packed_linear_fwd(w, dt)
+        else:
+            N, ks = w.shape[0], w.shape[2]
+            wp, c_pad, _ = packed_conv_fwd([w], dt)
+        M = B * H * W
+        pre = alloc_nhwc(B, H, W, N, dt, dev)
+        if ks == 1:
+            gemm_nt(x, 1, 1, M, C, ld, 1, wp, c_pad, N, _epilogue(pre, pre.stride(3), bias=b.detach()))
+        else:
+            gemm_nt(x, B, H, W, C, ld, ks, wp, c_pad, N, _epilogue(pre, pre.stride(3), bias=b.detach()))
+        train = _needs_grad(x, w, b, ln_w, ln_b)
+        mean = torch.empty(M, dtype=torch.float32, device=dev) if train else None
+        rstd = torch.empty(M, dtype=torch.float32, device=dev) if train else None
+        y = alloc_nhwc(B, H, W, N, dt, dev)
+        layernorm_fwd(pre, pre.stride(3), y, y.stride(3), M, N, ln_w.detach(), ln_b.detach(), 1, mean, rstd)
+        if train:
+            ctx.save_for_backward(x, pre, mean, rstd, w, b, ln_w, ln_b)
+            ctx.ks = ks
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, pre, mean, rstd, w, b, ln_w, ln_b = ctx.saved_tensors
+        ks = ctx.ks
+        B, H, W, C, ld = geom(x)
+        N = w.shape[0]
+        M = B * H * W
+        dt, dev = x.dtype, x.device
+        dy = to_nhwc(dy, dt)
+        dpre = alloc_nhwc(B, H, W, N, dt, dev)
+        layernorm_bwd(dy, dy.stride(3), pre, pre.stride(3), mean, rstd, ln_w.detach(), ln_b.detach(), 1, dpre, dpre.stride(3), M, N,
+                      grad_buffer(ln_w), grad_buffer(ln_b), grad_buffer(b))
+        gw = grad_buffer(w)
+        T = ks * ks
+        if ks == 1:
+            gemm_tn(dpre, 1, 1, M, N, dpre.stride(3), 1, x, C, ld, _epilogue(gw, C, out_f32=True, accumulate=True, tn=(0, C, 1)))
+        else:
+            gemm_tn(dpre, B, H, W, N, dpre.stride(3), ks, x, C, ld,
+                    _epilogue(gw, C, out_f32=True, accumulate=True, tn=(1, C * T, T)))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = alloc_nhwc(B, H, W, C, dt, dev)
+            if ks == 1:
+                wd, n_pad = packed_linear_dgrad(w, dt)
+                gemm_nt(dpre, 1, 1, M, N, dpre.stride(3), 1, wd, n_pad, C, _epilogue(dx, dx.stride(3)))
+            else:
+                wd, n_pad = packed_conv_dgrad([w], dt)
+                gemm_nt(dpre, B, H, W, N, dpre.stride(3), ks, wd, n_pad, C, _epilogue(dx, dx.stride(3)))
+        return dx, None, None, None, None
+
+
+class AvgPoolFn(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d(S) on NHWC (upernext.py:59-65)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, S: int) -> Tensor:
+        B, H, W, C, ld = geom(x)
+        y = alloc_nhwc(B, S, S, C, x.dtype, x.device)
+        L.check(L.LIB.vkocr_avgpool_fwd(_tag(x.dtype), L.ptr(x), ld, H, W, L.ptr(y), y.stride(3), S, B, C, _s()), 'avgpool_fwd')
+        ctx.meta = (B, H, W, C, S)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        B, H, W, C, S = ctx.meta
+        dy = to_nhwc(dy, dy.dtype)
+        dx = alloc_nhwc(B, H, W, C, dy.dtype, dy.device)
+        L.check(L.LIB.vkocr_avgpool_bwd(_tag(dy.dtype), L.ptr(dy), dy.stride(3), S, L.ptr(dx), dx.stride(3), H, W, B, C, 0, _s()),
+                'avgpool_bwd')
+        return dx, None
+
+
+class UpsampleAddFn(torch.autograd.Function):
+    """base + F.interpolate(src, size=base.shape[-2:], mode) — the top-down step (upernext.py:174-182, fpn.py:121-129)."""
+
+    @staticmethod
+    def forward(ctx, base: Tensor, src: Tensor, mode: int) -> Tensor:
+        B, H, W, C, ld = geom(base)
+        out = alloc_nhwc(B, H, W, C, base.dtype, base.device)
+        copy_channels(base, out, C)
+        upsample_fwd(src, out, C, mode, True)
+        ctx.mode = mode
+        ctx.src_shape = tuple(src.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        dout = to_nhwc(dout, dout.dtype)
+        B, C, h, w = ctx.src_shape
+        dsrc = None
+        if ctx.needs_input_grad[1]:
+            dsrc = alloc_nhwc(B, h, w, C, dout.dtype, dout.device)
+            upsample_bwd(dout, dsrc, C, ctx.mode, False)
+        return (dout if ctx.needs_input_grad[0] else None), dsrc, None
+
+
+class UpsampleConcatFn(torch.autograd.Function):
+    """torch.cat([F.interpolate(t, size) or t ...], dim=1): every level is resampled straight into its channel slice of
+    the NHWC concat buffer (upernext.py:76-82,189-197; fpn.py:136-144)."""
+
+    @staticmethod
+    def forward(ctx, mode: int, H: int, W: int, *xs: Tensor) -> Tensor:
+        B = xs[0].shape[0]
+        ctot = sum(int(t.shape[1]) for t in xs)
+        out = alloc_nhwc(B, H, W, ctot, xs[0].dtype, xs[0].device)
+        off = 0
+        for t in xs:
+            C = int(t.shape[1])
+            dst = out[:, off:off + C]
+            if t.shape[2] == H and t.shape[3] == W:
+                copy_channels(t, dst, C)
+            else:
+                upsample_fwd(t, dst, C, mode, False)
+            off += C
+        ctx.mode = mode
+        ctx.shapes = [tuple(t.shape) for t in xs]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        dout = to_nhwc(dout, dout.dtype)
+        H, W = dout.shape[2], dout.shape[3]
+        grads: List[Optional[Tensor]] = []
+        off = 0
+        for i, (B, C, h, w) in enumerate(ctx.shapes):
+            src = dout[:, off:off + C]
+            off += C
+            if not ctx.needs_input_grad[3 + i]:
+                grads.append(None)
+                continue
+            if h == H and w == W:
+                grads.append(src)   # a channel-slice view is a valid NHWC operand (ld = total width)
+            else:
+                d = alloc_nhwc(B, h, w, C, dout.dtype, dout.device)
+                upsample_bwd(src, d, C, ctx.mode, False)
+                grads.append(d)
+        return (None, None, None, *grads)
+
+
+class HeadGroupFn(torch.autograd.Function):
+    """All heads that read one neck tensor, fused: x`factor` up-sample (once) -> one implicit-GEMM conv with the heads'
+    k x k weights concatenated along N -> per-head LayerNorm+GELU+1x1(+Softplus) tail writing NCHW fp32 maps.
+    (UperNextHead.forward upernext.py:233-248, FpnHead.forward fpn.py:193-208, Softplus adaptive_scaling.py:101,140.)
+
+    ``params`` is a flat list of 6 tensors per head: conv_w, conv_b, ln_w, ln_b, lin_w, lin_b.
+    """
+
+    @staticmethod
+    def forward(ctx, x: Tensor, factor: int, mode: int, softplus: Tuple[bool, ...], *params: Tensor):
+        nh = len(softplus)
+        heads = [params[6 * i:6 * i + 6] for i in range(nh)]
+        B, h, w, C, ld = geom(x)
+        dt, dev = x.dtype, x.device
+        H, W = h * factor, w * factor
+        if factor > 1:
+            up = alloc_nhwc(B, H, W, C, dt, dev)
+            upsample_fwd(x, up, C, mode, False)
+        else:
+            up = x
+        inners = [int(hd[0].shape[0]) for hd in heads]
+        ks = int(heads[0][0].shape[2])
+        slot = _ceil_to(max(inners), 16)
+        ntot = slot * nh
+        wp, c_pad, rows = packed_conv_fwd([hd[0] for hd in heads], dt, slot)
+        bias = torch.zeros(ntot, dtype=torch.float32, device=dev)
+        for i, hd in enumerate(heads):
+            bias[i * slot:i * slot + inners[i]].copy_(hd[1].detach())   # tiny staging copy of the conv biases
+        conv = alloc_nhwc(B, H, W, ntot, dt, dev)
+        gemm_nt(up, B, H, W, C, up.stride(3), ks, wp, c_pad, ntot, _epilogue(conv, conv.stride(3), bias=bias))
+        outs = []
+        M = B * H * W
+        for i, hd in enumerate(heads):
+            O = int(hd[4].shape[0])
+            out = torch.empty((B, O, H, W), dtype=torch.float32, device=dev)
+            sl = conv[:, i * slot:(i + 1) * slot]
+            L.check(L.LIB.vkocr_head_tail_fwd(_tag(dt), L.ptr(sl), conv.stride(3), inners[i], slot, L.ptr(hd[2].detach()),
+                                              L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), L.ptr(hd[5].detach()), O,
+                                              int(softplus[i]), L.ptr(out), H * W, M, _s()), 'head_tail_fwd')
+            outs.append(out)
+        if _needs_grad(x, *params):
+            ctx.save_for_backward(x, up, conv, *outs, *params)
+            ctx.meta = (nh, factor, mode, tuple(softplus), slot, ks)
+        else:
+            del conv
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts: Tensor):
+        nh, factor, mode, softplus, slot, ks = ctx.meta
+        saved = ctx.saved_tensors
+        x, up, conv = saved[0], saved[1], saved[2]
+        outs = saved[3:3 + nh]
+        params = saved[3 + nh:]
+        heads = [params[6 * i:6 * i + 6] for i in range(nh)]
+        B, h, w, C, ld = geom(x)
+        H, W = h * factor, w * factor
+        M = B * H * W
+        dt, dev = x.dtype, x.device
+        ntot = slot * nh
+        dconv = alloc_nhwc(B, H, W, ntot, dt, dev)
+        for i, hd in enumerate(heads):
+            inner, O = int(hd[0].shape[0]), int(hd[4].shape[0])
+            dout = douts[i]
+            if dout is None:
+                dout = torch.zeros_like(outs[i])
+            dout = dout.contiguous().float()
+            L.check(L.LIB.vkocr_head_tail_bwd(_tag(dt), L.ptr(conv[:, i * slot:(i + 1) * slot]), conv.stride(3), inner, slot,
+                                              L.ptr(hd[2].detach()), L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), O,
+                                              int(softplus[i]), L.ptr(outs[i]), L.ptr(dout), H * W, M,
+                                              L.ptr(dconv[:, i * slot:(i + 1) * slot]), dconv.stride(3),
+                                              L.ptr(grad_buffer(hd[2])), L.ptr(grad_buffer(hd[3])), L.ptr(grad_buffer(hd[4])),
+                                              L.ptr(grad_buffer(hd[5])), L.ptr(grad_buffer(hd[1])), _s()), 'head_tail_bwd')
+        T = ks * ks
+        # weight gradient of all heads in one pass over (dconv, up): G[n_total, C, T] in OIHW order, then per-head slices
+        gw = _zeros_f32(ntot * C * T, dev)
+        gemm_tn(dconv, B, H, W, ntot, dconv.stride(3), ks, up, C, up.stride(3),
+                _epilogue(gw, C, out_f32=True, accumulate=True, tn=(1, C * T, T)))
+        for i, hd in enumerate(heads):
+            inner = int(hd[0].shape[0])
+            n = inner * C * T
+            L.check(L.LIB.vkocr_accumulate_f32(ctypes.c_void_p(gw.data_ptr() + 4 * i * slot * C * T), L.ptr(grad_buffer(hd[0])), n, _s()),
+                    'accumulate_f32')
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wd, n_pad = packed_conv_dgrad([hd[0] for hd in heads], dt, slot)
+            dup = alloc_nhwc(B, H, W, C, dt, dev)
+            gemm_nt(dconv, B, H, W, ntot, dconv.stride(3), ks, wd, n_pad, C, _epilogue(dup, dup.stride(3)))
+            if factor > 1:
+                dx = alloc_nhwc(B, h, w, C, dt, dev)
+                upsample_bwd(dup, dx, C, mode, False)
+            else:
+                dx = dup
+        return (dx, None, None, None) + (None,) * len(params)
