@@ -1,0 +1,192 @@
+"""GPU parity of the whole adaptive-scaling path (model + losses + backward) against (i) the fixtures written by the
+UNMODIFIED reference (tests/golden, oracle/make_golden.py) and (ii) the oracle run on the same device in fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _util import GRAD_TOL, NEGLIGIBLE, PER_TENSOR_GRAD_TOL, TOL, assert_close, compare_grads, oracle_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ROUGH_KEYS = ('downsampled_mask', 'downsampled_score_map', 'downsampled_shape', 'downsampled_core_box')
+PRECISE_KEYS = ('downsampled_char_prob_score_map', 'downsampled_char_mask', 'downsampled_shape', 'downsampled_core_box',
+                'downsampled_label_point_y', 'downsampled_label_point_x', 'char_up_left_offsets', 'char_corner_angles',
+                'char_corner_distances')
+
+
+@pytest.fixture(scope='module')
+def vk():
+    import vkit_ocr_model_adaptive_scaling_b200 as vk
+    return vk
+
+
+def _to(d, dev):
+    return {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+def _build(vk, neck, size='tiny'):
+    M = vk.model
+    cfg = M.AdaptiveScalingConfig(
+        size=M.AdaptiveScalingSize(size),
+        neck_head_type=M.AdaptiveScalingNeckHeadType.UPERNEXT if neck == 'upernext' else M.AdaptiveScalingNeckHeadType.FPN)
+    return M.AdaptiveScaling(cfg)
+
+
+def _check_norms(names, norms, want, tol, what):
+    """Per-parameter gradient norms against the reference's (tensors below NEGLIGIBLE of the global norm: absolute)."""
+    total = float(np.sqrt(np.sum(np.square(want[want > 0]))))
+    for n, a, b in zip(names, norms, want):
+        if b <= 0:
+            assert a <= 0, f'{n}: unexpected {what} gradient'
+        elif b < NEGLIGIBLE * total:
+            assert abs(max(a, 0.0) - b) <= tol * NEGLIGIBLE * total, f'{what} grad norm of {n}: {a} vs {b}'
+        else:
+            assert abs(a - b) <= tol * b, f'{what} grad norm of {n}: {a} vs {b}'
+
+
+@pytest.mark.parametrize('neck', ['upernext', 'fpn'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_full_model_against_reference_golden(vk, golden_dir, neck, dtype):
+    from oracle import synth
+    g = np.load(os.path.join(golden_dir, f'adaptive_scaling_tiny_{neck}.npz'))
+    batch, height, width, points, inset = (int(v) for v in g['meta'])
+    dev = torch.device('cuda')
+    model = _build(vk, neck)
+    sd = synth.synth_state_dict('tiny', neck, seed=133)
+    assert [str(n) for n in g['param_names']] == list(model.state_dict().keys())
+    model.load_state_dict(sd, strict=True)
+    model.to(dev).eval()
+    rb = _to(synth.synth_rough_batch(batch, height, width, seed=133, inset=inset), dev)
+    pb = _to(synth.synth_precise_batch(batch, height, width, points=points, seed=133, inset=inset), dev)
+    lf = vk.loss_function
+    rough_fn = lf.AdaptiveScalingRoughLossFunction(lf.AdaptiveScalingRoughLossFunctionConifg())
+    precise_fn = lf.AdaptiveScalingPreciseLossFunction(lf.AdaptiveScalingPreciseLossFunctionConifg())
+    tol, gtol = TOL[dtype], PER_TENSOR_GRAD_TOL[dtype]
+    names = [n for n, _ in model.named_parameters()]
+
+    with vk.precision(dtype):
+        mask, hgt = model.forward_rough(rb['image'])
+        assert mask.dtype == torch.float32 and tuple(mask.shape) == (batch, 1, height // 2, width // 2)
+        assert_close(mask.cpu(), torch.from_numpy(g['rough_mask']), tol, 'rough mask')
+        assert_close(hgt.cpu(), torch.from_numpy(g['rough_height']), tol, 'rough height')
+        rl = rough_fn(rough_char_mask_feature=mask, rough_char_height_feature=hgt, **{k: rb[k] for k in ROUGH_KEYS})
+        assert abs(float(rl) - float(g['rough_loss'])) <= tol * abs(float(g['rough_loss'])), (float(rl), float(g['rough_loss']))
+        (rl / 2).backward()
+    norms = np.array([float(p.grad.norm()) if p.grad is not None and float(p.grad.abs().max()) > 0 else -1.0
+                      for _, p in model.named_parameters()])
+    want = g['rough_grad_norm']
+    _check_norms(names, norms, want, gtol, 'rough')
+    model.zero_grad(set_to_none=True)
+
+    with vk.precision(dtype):
+        prob, off, ang, dist = model.forward_precise(pb['image'])
+        for name, t in (('precise_prob', prob), ('precise_offset', off), ('precise_angle', ang), ('precise_distance', dist)):
+            assert_close(t.cpu(), torch.from_numpy(g[name]), tol, name)
+        pl = precise_fn(precise_char_mask_feature=None, precise_char_prob_feature=prob,
+                        precise_char_up_left_corner_offset_feature=off, precise_char_corner_angle_feature=ang,
+                        precise_char_corner_distance_feature=dist, **{k: pb[k] for k in PRECISE_KEYS})
+        assert abs(float(pl) - float(g['precise_loss'])) <= tol * abs(float(g['precise_loss'])), (float(pl), float(g['precise_loss']))
+        (pl / 2).backward()
+    norms = np.array([float(p.grad.norm()) if p.grad is not None and float(p.grad.abs().max()) > 0 else -1.0
+                      for _, p in model.named_parameters()])
+    want = g['precise_grad_norm']
+    _check_norms(names, norms, want, gtol, 'precise')
+    by_name = dict(model.named_parameters())
+    for key in g.files:
+        if key.startswith('precise_grad::'):
+            assert_close(by_name[key.split('::', 1)[1]].grad.cpu(), torch.from_numpy(g[key]), gtol, key)
+
+
+@pytest.mark.parametrize('neck', ['upernext', 'fpn'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_training_step_against_oracle(vk, neck, dtype):
+    """Two-pass step (train.py:397-478) at a size with ragged tiles (160x224 -> 80x112 maps): every parameter gradient
+    after both backward passes against the oracle's autograd on the same device."""
+    from oracle import loss as ol
+    from oracle import model as om
+    from oracle import synth
+    from vkit_ocr_model_adaptive_scaling_b200.training import train_step
+    dev = torch.device('cuda')
+    B, H, W, P = 2, 160, 224, 16
+    model = _build(vk, neck)
+    model.load_state_dict(synth.synth_state_dict('tiny', neck, seed=7), strict=True)
+    model.to(dev).eval()
+    params = oracle_params(model)
+    rb = _to(synth.synth_rough_batch(B, H, W, seed=3, inset=6), dev)
+    pb = _to(synth.synth_precise_batch(B, H, W, points=P, seed=3, inset=6), dev)
+    lf = vk.loss_function
+    rough_fn = lf.AdaptiveScalingRoughLossFunction(lf.AdaptiveScalingRoughLossFunctionConifg())
+    precise_fn = lf.AdaptiveScalingPreciseLossFunction(lf.AdaptiveScalingPreciseLossFunctionConifg())
+    with vk.precision(dtype):
+        rl, pl = train_step(model, rough_fn, precise_fn, rb, pb)
+    rb64 = {k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in rb.items()}
+    pb64 = {k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in pb.items()}
+    rb, pb = rb64, pb64
+    mask, hgt = om.forward_rough(params, rb['image'])
+    rl_ref = ol.rough_loss(mask, hgt, *(rb[k] for k in ROUGH_KEYS))
+    (rl_ref / 2).backward()
+    prob, off, ang, dist = om.forward_precise(params, pb['image'])
+    pl_ref = ol.precise_loss(None, prob, off, ang, dist, *(pb[k] for k in PRECISE_KEYS))
+    (pl_ref / 2).backward()
+    tol = TOL[dtype]
+    assert abs(float(rl) - float(rl_ref)) <= tol * abs(float(rl_ref)), (float(rl), float(rl_ref))
+    assert abs(float(pl) - float(pl_ref)) <= tol * abs(float(pl_ref)), (float(pl), float(pl_ref))
+    compare_grads(model, params, dtype, f'{neck} step')
+
+
+def test_train_mode_stochastic_depth_matches_reference_rng(vk):
+    """train(): the drop masks are drawn with the reference's torch calls in layer order, so the oracle fed the masks
+    re-drawn from the same device seed reproduces the forward pass (convnext.py:41-53)."""
+    from oracle import model as om
+    from oracle import synth
+    dev = torch.device('cuda')
+    model = _build(vk, 'upernext')
+    model.load_state_dict(synth.synth_state_dict('tiny', 'upernext', seed=9), strict=True)
+    model.to(dev).train()
+    x = synth.synth_image(4, 64, 64, seed=2).to(dev)
+    torch.manual_seed(1234)
+    with vk.precision(torch.float32), torch.no_grad():
+        mask, hgt = model.forward_rough(x)
+    torch.manual_seed(1234)
+    probs = om.stochastic_depth_probs((3, 3, 9, 3))
+    masks = {}
+    for s, row in enumerate(probs):
+        for l, p in enumerate(row):
+            if p == 0.0:
+                continue
+            m = torch.empty([4, 1, 1, 1], dtype=torch.float32, device=dev).bernoulli_(1.0 - p).div_(1.0 - p)
+            masks[(s, l)] = m
+    ref_mask, ref_hgt = om.forward_rough(oracle_params(model), x.double(), drop_masks={k: v.double() for k, v in masks.items()})
+    assert_close(mask, ref_mask, 1e-4, 'train-mode rough mask')
+    assert_close(hgt, ref_hgt, 1e-4, 'train-mode rough height')
+
+
+def test_state_dict_round_trip_and_shapes(vk):
+    """Reference shape facts (tests/test_convnext.py:46-50, tests/test_upernext.py:28, tests/test_fpn.py:28,39,47,
+    corrected tests/test_adaptive_scaling.py:51-62 with the 4-channel distance head)."""
+    dev = torch.device('cuda')
+    M = vk.model
+    with torch.no_grad():
+        feats = M.ConvNext.create_tiny().to(dev)(torch.rand(1, 3, 320, 320, device=dev) * 255)
+        assert [tuple(f.shape) for f in feats] == [(1, 96, 80, 80), (1, 192, 40, 40), (1, 384, 20, 20), (1, 768, 10, 10)]
+        feats = M.ConvNext.create_tiny(stem_use_pconv2x2=True).to(dev)(torch.rand(1, 3, 320, 320, device=dev) * 255)
+        assert [tuple(f.shape) for f in feats] == [(1, 96, 160, 160), (1, 192, 80, 80), (1, 384, 40, 40), (1, 768, 20, 20)]
+        fs = [torch.rand(1, c, 80 >> i, 80 >> i, device=dev) for i, c in enumerate((96, 192, 384, 768))]
+        assert tuple(M.UperNextNeck((96, 192, 384, 768), 384).to(dev)(fs).shape) == (1, 384, 80, 80)
+        assert tuple(M.FpnNeck((96, 192, 384, 768), 400).to(dev)(fs).shape) == (1, 400, 80, 80)
+        x = torch.rand(1, 400, 80, 80, device=dev)
+        assert tuple(M.FpnHead(400, 1, upsampling_factor=1).to(dev)(x).shape) == (1, 1, 80, 80)
+        assert tuple(M.FpnHead(400, 1, upsampling_factor=2).to(dev)(x).shape) == (1, 1, 160, 160)
+        model = _build(vk, 'upernext').to(dev)
+        img = torch.rand(1, 3, 320, 320, device=dev) * 255
+        assert [tuple(t.shape) for t in model.forward_rough(img)] == [(1, 1, 160, 160)] * 2
+        assert [tuple(t.shape) for t in model.forward_precise(img)] == [(1, 1, 160, 160), (1, 2, 160, 160), (1, 4, 160, 160),
+                                                                      (1, 4, 160, 160)]
+        with pytest.raises(NotImplementedError):
+            model(img)   # the reference defines no forward() either
+    sd = model.state_dict()
+    clone = _build(vk, 'upernext')
+    clone.load_state_dict(sd, strict=True)
+    assert all(v.dtype == torch.float32 for v in sd.values())

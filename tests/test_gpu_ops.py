@@ -1,0 +1,382 @@
+"""GPU parity of every operator of the hot path against the oracle (unit level), in fp32 mode (rel 1e-4) and bf16 mode
+(rel 2e-2): forward values, input gradients and every parameter gradient.  All calls go through the C ABI."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import GRAD_TOL, PER_TENSOR_GRAD_TOL, TOL, assert_close, compare_grads, oracle_params, randomize, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+@pytest.fixture(scope='module')
+def vk():
+    import vkit_ocr_model_adaptive_scaling_b200 as vk
+    assert torch.cuda.is_available()
+    assert vk._lib.LIB.vkocr_device_check(torch.cuda.current_device()) == 0
+    return vk
+
+
+def _probe(shape, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g).to(device)
+
+
+def _run_pair(vk, dtype, module, module_fn, oracle_fn, x_cpu, seed=0, input_grad=True):
+    """Runs module_fn(module, x) on the GPU product path and oracle_fn(params, x) in fp32 torch on the GPU; compares."""
+    dev = torch.device('cuda')
+    module.to(dev)
+    randomize(module, seed + 100)
+    params = oracle_params(module)
+    x = x_cpu.to(dev).requires_grad_(input_grad)
+    xo = x_cpu.to(dev).double().requires_grad_(input_grad)
+    with vk.precision(dtype):
+        out = module_fn(module, x)
+    ref = oracle_fn(params, xo)
+    outs = out if isinstance(out, (tuple, list)) else [out]
+    refs = ref if isinstance(ref, (tuple, list)) else [ref]
+    total, total_ref = 0.0, 0.0
+    for i, (o, r) in enumerate(zip(outs, refs)):
+        assert_close(o.float(), r, TOL[dtype], f'output {i}')
+        pr = _probe(tuple(r.shape), seed + i, dev)
+        total = total + (o.float() * pr).sum()
+        total_ref = total_ref + (r * pr.double()).sum()
+    with vk.precision(dtype):
+        total.backward()
+    total_ref.backward()
+    torch.cuda.synchronize()
+    if input_grad:
+        assert_close(x.grad.float(), xo.grad, PER_TENSOR_GRAD_TOL[dtype], 'input gradient')
+    compare_grads(module, params, dtype, 'parameters')
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('shape', [(2, 96, 20, 28), (1, 192, 9, 7), (3, 32, 5, 33)])
+def test_convnext_layer(vk, dtype, shape):
+    from oracle import model as om
+    B, C, H, W = shape
+    layer = vk.model.ConvNextBlockLayer(C)
+    layer.eval()
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(1))
+    _run_pair(vk, dtype, layer, lambda m, t: m(t), lambda p, t: om.convnext_layer(p, '', t), x)
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_convnext_layer_stochastic_depth_mask(vk, dtype):
+    """train mode: the drop mask is drawn with the reference's torch calls; with the same device seed the oracle, fed
+    the identical mask, must agree (convnext.py:41-53)."""
+    from oracle import model as om
+    dev = torch.device('cuda')
+    layer = vk.model.ConvNextBlockLayer(64, prob_bypass=0.5).to(dev)
+    randomize(layer, 5)
+    layer.train()
+    x = torch.randn(6, 64, 8, 8, generator=torch.Generator().manual_seed(2)).to(dev)
+    torch.manual_seed(77)
+    with vk.precision(dtype):
+        y = layer(x.clone().requires_grad_(True))
+    torch.manual_seed(77)
+    mask = torch.empty([6, 1, 1, 1], dtype=torch.float32, device=dev).bernoulli_(0.5).div_(0.5)
+    assert 0 < int((mask == 0).sum()) < 6, 'seed should drop some but not all samples'
+    ref = om.convnext_layer(oracle_params(layer), '', x.double(), mask.double())
+    assert_close(y.float(), ref, TOL[dtype], 'stochastic depth output')
+    dropped = (mask.reshape(-1) == 0).nonzero().reshape(-1)
+    assert_close(y.float()[dropped], x[dropped], TOL[dtype], 'dropped samples are the identity')
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('hw', [(64, 96), (36, 44)])
+def test_convnext_backbone(vk, dtype, hw):
+    from oracle import model as om
+    net = vk.model.ConvNext(3, ((32, 2), (64, 1), (96, 2), (128, 1)), False)
+    net.eval()
+    x = torch.randint(0, 256, (2, 3, *hw), generator=torch.Generator().manual_seed(3)).float()
+
+    def scale_stem(module):
+        with torch.no_grad():
+            module.stem[0].weight.mul_(1.0 / 128)   # raw 0..255 pixels come in
+
+    dev = torch.device('cuda')
+    net.to(dev)
+    randomize(net, 11)
+    scale_stem(net)
+    params = oracle_params(net)
+    with vk.precision(dtype):
+        feats = net(x.to(dev))
+    refs = om.convnext_forward(params, x.to(dev).double(), prefix='')
+    assert [tuple(f.shape) for f in feats] == [tuple(r.shape) for r in refs]
+    total, total_ref = 0.0, 0.0
+    for i, (f, r) in enumerate(zip(feats, refs)):
+        assert_close(f.float(), r, TOL[dtype], f'feature {i}')
+        pr = _probe(tuple(r.shape), 20 + i, dev)
+        total = total + (f.float() * pr).sum()
+        total_ref = total_ref + (r * pr.double()).sum()
+    with vk.precision(dtype):
+        total.backward()
+    total_ref.backward()
+    compare_grads(net, params, dtype, 'backbone')
+
+
+def test_convnext_golden_features(vk, golden_dir):
+    """fp32 mode against the fixture produced by the UNMODIFIED reference (oracle/make_golden.py: backbone_features)."""
+    import os
+    from oracle import synth
+    g = np.load(os.path.join(golden_dir, 'convnext_tiny_features.npz'))
+    gen = synth._Gen(7)
+    synth.backbone_state_dict(gen, *synth.SIZES['tiny'], prefix='')
+    net = vk.model.ConvNext.create_tiny()
+    net.load_state_dict(gen.sd, strict=True)
+    net.cuda().eval()
+    x = synth.synth_image(1, 64, 96, seed=5).cuda()
+    for dtype in DTYPES:
+        with vk.precision(dtype), torch.no_grad():
+            feats = net(x)
+        for i, f in enumerate(feats):
+            assert_close(f.float().cpu(), torch.from_numpy(g[f'f{i}']), TOL[dtype], f'{dtype} golden feature {i}')
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('kind', ['upernext', 'fpn'])
+def test_neck(vk, dtype, kind):
+    from oracle import model as om
+    chans = (32, 64, 96, 128)
+    neck = vk.model.UperNextNeck(chans, 64) if kind == 'upernext' else vk.model.FpnNeck(chans, 64)
+    gen = torch.Generator().manual_seed(4)
+    feats_cpu = [torch.randn(2, c, 40 >> i, 56 >> i, generator=gen) for i, c in enumerate(chans)]   # level 3 is 5x7
+    dev = torch.device('cuda')
+    neck.to(dev)
+    randomize(neck, 12)
+    params = oracle_params(neck)
+    feats = [f.to(dev).requires_grad_(True) for f in feats_cpu]
+    feats_o = [f.to(dev).double().requires_grad_(True) for f in feats_cpu]
+    with vk.precision(dtype):
+        out = neck(feats)
+    ref = om.neck_forward(params, '', feats_o, kind)
+    assert_close(out.float(), ref, TOL[dtype], 'neck output')
+    pr = _probe(tuple(ref.shape), 9, dev)
+    with vk.precision(dtype):
+        (out.float() * pr).sum().backward()
+    (ref * pr.double()).sum().backward()
+    for i in range(4):
+        assert_close(feats[i].grad.float(), feats_o[i].grad, PER_TENSOR_GRAD_TOL[dtype], f'feature {i} gradient')
+    compare_grads(neck, params, dtype, 'neck')
+
+
+def test_neck_head_golden_units(vk, golden_dir):
+    """fp32 mode against reference-generated unit fixtures on small odd shapes (non-divisible pooling bins, odd sizes)."""
+    import os
+    from oracle import synth
+    g = np.load(os.path.join(golden_dir, 'neck_head_units.npz'))
+    chans = (8, 16, 24, 32)
+    feats = [torch.from_numpy(g[f'feat{i}']).cuda() for i in range(4)]
+    with vk.precision(torch.float32), torch.no_grad():
+        gen = synth._Gen(21)
+        synth.neck_state_dict(gen, '', 'upernext', chans, 16)
+        neck = vk.model.UperNextNeck(chans, 16)
+        neck.load_state_dict(gen.sd, strict=True)
+        assert_close(neck.cuda()(feats).float().cpu(), torch.from_numpy(g['upernext_neck']), 1e-4, 'upernext neck')
+        gen = synth._Gen(22)
+        synth.neck_state_dict(gen, '', 'fpn', chans, 16)
+        neck = vk.model.FpnNeck(chans, 16)
+        neck.load_state_dict(gen.sd, strict=True)
+        assert_close(neck.cuda()(feats).float().cpu(), torch.from_numpy(g['fpn_neck']), 1e-4, 'fpn neck')
+        x = torch.from_numpy(g['head_in']).cuda()
+        for kind, cls in (('upernext', vk.model.UperNextHead), ('fpn', vk.model.FpnHead)):
+            for factor in (1, 2):
+                gen = synth._Gen(23 + factor)
+                synth.head_state_dict(gen, '', kind, 16, 3, out_bias=0.5)
+                head = cls(16, 3, upsampling_factor=factor)
+                head.load_state_dict(gen.sd, strict=True)
+                assert_close(head.cuda()(x).float().cpu(), torch.from_numpy(g[f'{kind}_head_x{factor}']), 1e-4,
+                             f'{kind} head x{factor}')
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('kind,factor,out_ch', [('upernext', 2, 1), ('upernext', 1, 4), ('fpn', 2, 2), ('fpn', 4, 3)])
+def test_head(vk, dtype, kind, factor, out_ch):
+    from oracle import model as om
+    cls = vk.model.UperNextHead if kind == 'upernext' else vk.model.FpnHead
+    head = cls(64, out_ch, upsampling_factor=factor, init_output_bias=0.3)
+    x = torch.randn(2, 64, 9, 13, generator=torch.Generator().manual_seed(6))
+    _run_pair(vk, dtype, head, lambda m, t: m(t), lambda p, t: om.head_forward(p, '', t, kind, factor), x)
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_softplus_head_and_odd_inner(vk, dtype):
+    """inner = (384 + out)//2 is 193 / 194 for the 2- and 4-channel heads: not a multiple of the vector width."""
+    from oracle import model as om
+    from vkit_ocr_model_adaptive_scaling_b200.model.adaptive_scaling import SoftplusHead
+    head = SoftplusHead(vk.model.UperNextHead(384, 4, upsampling_factor=2))
+    x = torch.randn(1, 384, 6, 10, generator=torch.Generator().manual_seed(8))
+    _run_pair(vk, dtype, head, lambda m, t: m(t), lambda p, t: om.head_forward(p, '0.', t, 'upernext', 2, softplus=True), x)
+
+
+# ------------------------------------------------------------------------------------------------------- losses
+def _loss_inputs(B, H, W, inset, P, seed, dev):
+    from oracle import synth
+    rb = synth.synth_rough_batch(B, 2 * H, 2 * W, seed=seed, inset=inset)
+    pb = synth.synth_precise_batch(B, 2 * H, 2 * W, points=P, seed=seed, inset=inset)
+    to = lambda d: {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    return to(rb), to(pb)
+
+
+@pytest.mark.parametrize('B,H,W,inset', [(2, 48, 64, 4), (1, 33, 29, 0), (3, 40, 40, 10)])
+def test_rough_loss(vk, B, H, W, inset):
+    from oracle import loss as ol
+    dev = torch.device('cuda')
+    rb, _ = _loss_inputs(B, H, W, inset, 8, 50 + B, dev)
+    g = torch.Generator().manual_seed(B)
+    logit = (torch.randn(B, 1, H, W, generator=g) * 2).to(dev)
+    height = (torch.rand(B, 1, H, W, generator=g) * 14).to(dev)   # some below the 1.1 floor
+    a, b = logit.clone().requires_grad_(True), height.clone().requires_grad_(True)
+    ao, bo = logit.clone().requires_grad_(True), height.clone().requires_grad_(True)
+    fn = vk.loss_function.AdaptiveScalingRoughLossFunction(vk.loss_function.AdaptiveScalingRoughLossFunctionConifg())
+    keys = ('downsampled_mask', 'downsampled_score_map', 'downsampled_shape', 'downsampled_core_box')
+    loss = fn(rough_char_mask_feature=a, rough_char_height_feature=b, **{k: rb[k] for k in keys})
+    ref = ol.rough_loss(ao, bo, *(rb[k] for k in keys))
+    assert loss.dim() == 0 and loss.is_cuda
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref)) + 1e-6, (float(loss), float(ref))
+    (loss / 2).backward()
+    (ref / 2).backward()
+    assert_close(a.grad, ao.grad, 1e-4, 'd rough / d mask logits')
+    assert_close(b.grad, bo.grad, 1e-4, 'd rough / d height')
+
+
+@pytest.mark.parametrize('B,H,W,inset,P', [(2, 48, 64, 4, 20), (1, 33, 29, 0, 7), (3, 40, 40, 10, 200)])
+def test_precise_loss(vk, B, H, W, inset, P):
+    from oracle import loss as ol
+    dev = torch.device('cuda')
+    _, pb = _loss_inputs(B, H, W, inset, P, 60 + B, dev)
+    if P >= 2:   # duplicate label points must accumulate in the backward scatter
+        pb['downsampled_label_point_y'][:, 1] = pb['downsampled_label_point_y'][:, 0]
+        pb['downsampled_label_point_x'][:, 1] = pb['downsampled_label_point_x'][:, 0]
+    g = torch.Generator().manual_seed(B)
+    maps = [(torch.randn(B, c, H, W, generator=g) * s).to(dev) for c, s in ((1, 2.0), (2, 8.0), (4, 1.5), (4, 6.0))]
+    maps[3] = maps[3].abs()
+    ours = [m.clone().requires_grad_(True) for m in maps]
+    refs = [m.clone().requires_grad_(True) for m in maps]
+    fn = vk.loss_function.AdaptiveScalingPreciseLossFunction(vk.loss_function.AdaptiveScalingPreciseLossFunctionConifg())
+    keys = ('downsampled_char_prob_score_map', 'downsampled_char_mask', 'downsampled_shape', 'downsampled_core_box',
+            'downsampled_label_point_y', 'downsampled_label_point_x', 'char_up_left_offsets', 'char_corner_angles',
+            'char_corner_distances')
+    loss = fn(precise_char_mask_feature=None, precise_char_prob_feature=ours[0],
+              precise_char_up_left_corner_offset_feature=ours[1], precise_char_corner_angle_feature=ours[2],
+              precise_char_corner_distance_feature=ours[3], **{k: pb[k] for k in keys})
+    ref = ol.precise_loss(None, *refs, *(pb[k] for k in keys))
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref)) + 1e-6, (float(loss), float(ref))
+    (loss / 2).backward()
+    (ref / 2).backward()
+    for i, name in enumerate(('prob', 'offset', 'angle', 'distance')):
+        assert_close(ours[i].grad, refs[i].grad, 1e-4, f'd precise / d {name}')
+
+
+def test_precise_loss_optional_terms(vk):
+    """Off-by-default terms: masked focal on the optional char-mask head, prob smooth-L1, WAHR (reference :272-307)."""
+    from oracle import loss as ol
+    dev = torch.device('cuda')
+    B, H, W, P = 2, 24, 32, 5
+    _, pb = _loss_inputs(B, H, W, 3, P, 71, dev)
+    g = torch.Generator().manual_seed(3)
+    maps = [(torch.randn(B, c, H, W, generator=g)).to(dev) for c in (1, 1, 2, 4, 4)]
+    ours = [m.clone().requires_grad_(True) for m in maps]
+    refs = [m.clone().requires_grad_(True) for m in maps]
+    cfg = vk.loss_function.AdaptiveScalingPreciseLossFunctionConifg(
+        char_mask_focal_factor=1.5, char_prob_l1_factor=0.7, char_prob_wahr_factor=0.9)
+    fn = vk.loss_function.AdaptiveScalingPreciseLossFunction(cfg)
+    keys = ('downsampled_char_prob_score_map', 'downsampled_char_mask', 'downsampled_shape', 'downsampled_core_box',
+            'downsampled_label_point_y', 'downsampled_label_point_x', 'char_up_left_offsets', 'char_corner_angles',
+            'char_corner_distances')
+    loss = fn(ours[0], ours[1], ours[2], ours[3], ours[4], **{k: pb[k] for k in keys})
+    ref = ol.precise_loss(refs[0], refs[1], refs[2], refs[3], refs[4], *(pb[k] for k in keys),
+                          char_mask_focal_factor=1.5, char_prob_l1_factor=0.7, char_prob_wahr_factor=0.9)
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref)) + 1e-6, (float(loss), float(ref))
+    loss.backward()
+    ref.backward()
+    for i in range(5):
+        assert_close(ours[i].grad, refs[i].grad, 2e-4, f'gradient of map {i}')
+
+
+def test_primitive_losses_golden(vk, golden_dir):
+    """Every primitive against the reference-generated fixture values (oracle/make_golden.py: primitive_losses)."""
+    import os
+    g = np.load(os.path.join(golden_dir, 'primitive_losses.npz'))
+    lf = vk.loss_function
+    dev = torch.device('cuda')
+    pred, gt01, gtf, mask = (torch.from_numpy(g[k]).to(dev) for k in ('pred', 'gt01', 'gtf', 'mask'))
+    cases = [
+        ('focal', lf.FocalWithLogitsLossFunction()(pred, gt01)),
+        ('focal_masked', lf.FocalWithLogitsLossFunction()(pred, gt01, mask)),
+        ('dice', lf.DiceLossFunction()(torch.sigmoid(pred), gt01)),
+        ('dice_masked', lf.DiceLossFunction()(torch.sigmoid(pred), gt01, mask)),
+        ('l1', lf.L1LossFunction()(pred, gtf)),
+        ('l1_masked', lf.L1LossFunction()(pred, gtf, mask)),
+        ('smooth_l1', lf.L1LossFunction(smooth=True, smooth_beta=2.5)(pred, gtf)),
+        ('smooth_l1_masked', lf.L1LossFunction(smooth=True)(pred, gtf, mask)),
+        ('l2', lf.L2LossFunction()(pred, gtf)),
+        ('l2_masked', lf.L2LossFunction()(pred, gtf, mask)),
+        ('wahr', lf.WeightAdaptiveHeatmapRegressionLossFunction()(torch.sigmoid(pred), gtf)),
+        ('bce', lf.WeightedBceWithLogitsLossFunction()(pred, gt01)),
+        ('bce_masked', lf.WeightedBceWithLogitsLossFunction()(pred, gt01, mask)),
+        ('ce', lf.CrossEntropyWithLogitsLossFunction()(torch.from_numpy(g['ce_pred']).to(dev), torch.from_numpy(g['ce_gt']).to(dev))),
+    ]
+    for name, value in cases:
+        want = float(g[name])
+        assert abs(float(value) - want) <= 2e-5 * abs(want) + 2e-6, (name, float(value), want)
+
+
+@pytest.mark.parametrize('name', ['focal', 'dice', 'l1', 'smooth_l1', 'l2', 'wahr', 'bce', 'ce'])
+@pytest.mark.parametrize('masked', [False, True])
+def test_primitive_loss_gradients(vk, name, masked):
+    from oracle import loss as ol
+    lf = vk.loss_function
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(13)
+    n = (5, 1000)
+    pred = (torch.randn(n, generator=g) * 2).to(dev)
+    gt01 = (torch.rand(n, generator=g) > 0.7).float().to(dev)
+    gtf = torch.rand(n, generator=g).to(dev)
+    mask = (torch.rand(n, generator=g) > 0.3).float().to(dev) if masked else None
+    a = pred.clone().requires_grad_(True)
+    b = pred.clone().requires_grad_(True)
+    if name == 'ce':
+        if masked:
+            pytest.skip('cross entropy takes no mask')
+        a = torch.randn(6, 4, 50, generator=g).to(dev).requires_grad_(True)
+        b = a.detach().clone().requires_grad_(True)
+        t = torch.softmax(torch.randn(6, 4, 50, generator=g), dim=1).to(dev)
+        ours, ref = lf.CrossEntropyWithLogitsLossFunction()(a, t), ol.cross_entropy_with_logits(b, t)
+    elif name == 'focal':
+        ours, ref = lf.FocalWithLogitsLossFunction()(a, gt01, mask), ol.focal_with_logits(b, gt01, mask)
+    elif name == 'dice':
+        ours = lf.DiceLossFunction()(torch.sigmoid(a), gt01.clone(), mask)
+        ref = ol.dice(torch.sigmoid(b), gt01, mask)
+    elif name == 'l1':
+        ours, ref = lf.L1LossFunction()(a, gtf, mask), ol.l1(b, gtf, mask)
+    elif name == 'smooth_l1':
+        ours, ref = lf.L1LossFunction(smooth=True, smooth_beta=0.8)(a, gtf, mask), ol.l1(b, gtf, mask, True, 0.8)
+    elif name == 'l2':
+        ours, ref = lf.L2LossFunction()(a, gtf, mask), ol.l2(b, gtf, mask)
+    elif name == 'wahr':
+        if masked:
+            pytest.skip('WAHR takes no mask')
+        ours = lf.WeightAdaptiveHeatmapRegressionLossFunction()(torch.sigmoid(a), gtf)
+        ref = ol.weight_adaptive_heatmap_regression(torch.sigmoid(b), gtf)
+    else:
+        ours = lf.WeightedBceWithLogitsLossFunction()(a, gt01.clone(), mask)
+        ref = ol.weighted_bce_with_logits(b, gt01.clone(), mask)
+    assert abs(float(ours) - float(ref)) <= 2e-5 * abs(float(ref)) + 1e-6, (float(ours), float(ref))
+    ours.backward()
+    ref.backward()
+    assert_close(a.grad, b.grad, 1e-4, f'{name} gradient')
+
+
+def test_errors_are_loud(vk):
+    """No CPU fallback: CPU tensors are rejected; unsupported shapes come back as errors from the C ABI."""
+    layer = vk.model.ConvNextBlockLayer(32)
+    with pytest.raises(Exception):
+        layer(torch.randn(1, 32, 8, 8))
+    from vkit_ocr_model_adaptive_scaling_b200 import _lib as L
+    rc = L.LIB.vkocr_dwconv7_fwd(1, None, 8, None, 8, 1, 4, 4, 8, None, None, None, 0, None)
+    assert rc != 0 and b'null' in L.LIB.vkocr_last_error()

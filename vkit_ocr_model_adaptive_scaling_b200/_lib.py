@@ -93,6 +93,15 @@ _SIGNATURES = {
                                  c_void_p, c_void_p],
     'vkocr_accumulate_f32': [c_void_p, c_void_p, c_ll, c_void_p],
     'vkocr_scale_rows': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p],
+    'vkocr_pointwise_loss_fwd': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_void_p, c_void_p, c_void_p],
+    'vkocr_pointwise_loss_bwd': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                 c_void_p],
+    'vkocr_soft_ce_fwd': [c_void_p, c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p, c_void_p],
+    'vkocr_soft_ce_bwd': [c_void_p, c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p],
+    'vkocr_hard_negative_bce_fwd': [c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_void_p],
+    'vkocr_hard_negative_bce_bwd': [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p],
 }
 
 

@@ -89,6 +89,17 @@ template <> struct VkVec<__nv_bfloat16> {
     }
 };
 
+// One-element "vector" with the VkVec interface: the generic path for channel counts / strides / slice offsets that are
+// not 16-byte aligned.
+template <typename T> struct VkScalar {
+    static constexpr int N = 1;
+    T raw;
+    __device__ __forceinline__ void load(const T* p) { raw = *p; }
+    __device__ __forceinline__ void store(T* p) const { *p = raw; }
+    __device__ __forceinline__ void unpack(float* f) const { f[0] = vk_to_f32(raw); }
+    __device__ __forceinline__ void pack(const float* f) { raw = vk_from_f32<T>(f[0]); }
+};
+
 // ---- reductions ---------------------------------------------------------------------------------
 __device__ __forceinline__ float vk_warp_sum(float v) {
 #pragma unroll

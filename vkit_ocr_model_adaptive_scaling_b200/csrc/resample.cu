@@ -33,11 +33,11 @@ __device__ __forceinline__ int nearest_src(int d, int in, int out) {
     return i < in - 1 ? i : in - 1;
 }
 
-template <typename T>
+template <typename T, typename VT>
 __global__ void __launch_bounds__(256)
 upsample_fwd_kernel(const T* __restrict__ src, long long ld_s, int h, int w, T* __restrict__ dst, long long ld_d, int H, int W,
                     int B, int C, int mode, int accumulate) {
-    constexpr int V = VkVec<T>::N;
+    constexpr int V = VT::N;
     const int CV = C / V;
     const long long total = (long long)B * H * W * CV;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,7 +53,7 @@ upsample_fwd_kernel(const T* __restrict__ src, long long ld_s, int h, int w, T* 
     const T* sb = src + (long long)b * h * w * ld_s + c;
     if (mode == 0) {
         const Axis ay = bilinear_axis(Y, h, H), ax = bilinear_axis(X, w, W);
-        VkVec<T> v00, v01, v10, v11;
+        VT v00, v01, v10, v11;
         v00.load(sb + ((long long)ay.i0 * w + ax.i0) * ld_s);
         v01.load(sb + ((long long)ay.i0 * w + ax.i1) * ld_s);
         v10.load(sb + ((long long)ay.i1 * w + ax.i0) * ld_s);
@@ -65,30 +65,30 @@ upsample_fwd_kernel(const T* __restrict__ src, long long ld_s, int h, int w, T* 
             o[i] = ay.w0 * (ax.w0 * f00[i] + ax.w1 * f01[i]) + ay.w1 * (ax.w0 * f10[i] + ax.w1 * f11[i]);
     } else {
         const int sy = nearest_src(Y, h, H), sx = nearest_src(X, w, W);
-        VkVec<T> v;
+        VT v;
         v.load(sb + ((long long)sy * w + sx) * ld_s);
         v.unpack(o);
     }
     T* dp = dst + (((long long)b * H + Y) * W + X) * ld_d + c;
     if (accumulate) {
-        VkVec<T> d;
+        VT d;
         d.load(dp);
         float f[V];
         d.unpack(f);
 #pragma unroll
         for (int i = 0; i < V; ++i) o[i] += f[i];
     }
-    VkVec<T> out;
+    VT out;
     out.pack(o);
     out.store(dp);
 }
 
 // Gather-form adjoint: dsrc[b,i,j,:] (+)= sum over destination pixels that read (i,j) of weight * ddst.
-template <typename T>
+template <typename T, typename VT>
 __global__ void __launch_bounds__(256)
 upsample_bwd_kernel(const T* __restrict__ ddst, long long ld_d, int H, int W, T* __restrict__ dsrc, long long ld_s, int h, int w,
                     int B, int C, int mode, int accumulate) {
-    constexpr int V = VkVec<T>::N;
+    constexpr int V = VT::N;
     const int CV = C / V;
     const long long total = (long long)B * h * w * CV;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,7 +130,7 @@ upsample_bwd_kernel(const T* __restrict__ ddst, long long ld_d, int H, int W, T*
                 wx = nearest_src(X, w, W) == j ? 1.f : 0.f;
             }
             if (wx == 0.f) continue;
-            VkVec<T> v;
+            VT v;
             v.load(db + ((long long)Y * W + X) * ld_d);
             float f[V];
             v.unpack(f);
@@ -141,14 +141,14 @@ upsample_bwd_kernel(const T* __restrict__ ddst, long long ld_d, int H, int W, T*
     }
     T* sp = dsrc + (((long long)b * h + i) * w + j) * ld_s + c;
     if (accumulate) {
-        VkVec<T> d;
+        VT d;
         d.load(sp);
         float f[V];
         d.unpack(f);
 #pragma unroll
         for (int e = 0; e < V; ++e) acc[e] += f[e];
     }
-    VkVec<T> out;
+    VT out;
     out.pack(acc);
     out.store(sp);
 }
@@ -354,6 +354,24 @@ inline bool vec_ok(int dtype, int C, long long a, long long b) {
     const int V = dtype == VKOCR_F32 ? 4 : 8;
     return C % V == 0 && a % V == 0 && b % V == 0;
 }
+inline bool ptr16(const void* a, const void* b) {
+    return (reinterpret_cast<uintptr_t>(a) % 16 == 0) && (reinterpret_cast<uintptr_t>(b) % 16 == 0);
+}
+
+template <typename T, typename VT>
+void launch_upsample_fwd(const void* src, long long ld_s, int h, int w, void* dst, long long ld_d, int H, int W, int B, int C,
+                         int mode, int accumulate, cudaStream_t s) {
+    const long long total = (long long)B * H * W * (C / VT::N);
+    upsample_fwd_kernel<T, VT><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const T*>(src), ld_s, h, w, reinterpret_cast<T*>(dst), ld_d, H, W, B, C, mode, accumulate);
+}
+template <typename T, typename VT>
+void launch_upsample_bwd(const void* ddst, long long ld_d, int H, int W, void* dsrc, long long ld_s, int h, int w, int B, int C,
+                         int mode, int accumulate, cudaStream_t s) {
+    const long long total = (long long)B * h * w * (C / VT::N);
+    upsample_bwd_kernel<T, VT><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const T*>(ddst), ld_d, H, W, reinterpret_cast<T*>(dsrc), ld_s, h, w, B, C, mode, accumulate);
+}
 
 }  // namespace
 
@@ -364,15 +382,12 @@ int vkocr_upsample_fwd(int dtype, const void* src, long long ld_s, int h, int w,
                        int C, int mode, int accumulate, void* stream) {
     VK_REQUIRE(src && dst, VKOCR_BAD_ARGUMENT, "upsample_fwd: null argument");
     VK_REQUIRE(mode == 0 || mode == 1, VKOCR_BAD_ARGUMENT, "upsample_fwd: mode %d", mode);
-    VK_REQUIRE(vec_ok(dtype, C, ld_s, ld_d), VKOCR_BAD_ALIGN, "upsample_fwd: C %d / strides not vector aligned", C);
     VK_REQUIRE(h > 0 && w > 0, VKOCR_BAD_SHAPE, "upsample_fwd: empty source");
-    const int V = dtype == VKOCR_F32 ? 4 : 8;
-    const long long total = (long long)B * H * W * (C / V);
-    if (total == 0) return VKOCR_OK;
+    if ((long long)B * H * W * C == 0) return VKOCR_OK;
+    const bool vec = vec_ok(dtype, C, ld_s, ld_d) && ptr16(src, dst);   // else: scalar path (odd widths / slice offsets)
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    VK_DISPATCH_DTYPE(dtype, T, (upsample_fwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-                                    reinterpret_cast<const T*>(src), ld_s, h, w, reinterpret_cast<T*>(dst), ld_d, H, W, B, C, mode,
-                                    accumulate)));
+    VK_DISPATCH_DTYPE(dtype, T, (vec ? launch_upsample_fwd<T, VkVec<T>>(src, ld_s, h, w, dst, ld_d, H, W, B, C, mode, accumulate, s)
+                                     : launch_upsample_fwd<T, VkScalar<T>>(src, ld_s, h, w, dst, ld_d, H, W, B, C, mode, accumulate, s)));
     VK_CHECK_LAUNCH("upsample_fwd_kernel");
     return VKOCR_OK;
 }
@@ -382,14 +397,11 @@ int vkocr_upsample_bwd(int dtype, const void* ddst, long long ld_d, int H, int W
                        int C, int mode, int accumulate, void* stream) {
     VK_REQUIRE(ddst && dsrc, VKOCR_BAD_ARGUMENT, "upsample_bwd: null argument");
     VK_REQUIRE(mode == 0 || mode == 1, VKOCR_BAD_ARGUMENT, "upsample_bwd: mode %d", mode);
-    VK_REQUIRE(vec_ok(dtype, C, ld_s, ld_d), VKOCR_BAD_ALIGN, "upsample_bwd: C %d / strides not vector aligned", C);
-    const int V = dtype == VKOCR_F32 ? 4 : 8;
-    const long long total = (long long)B * h * w * (C / V);
-    if (total == 0) return VKOCR_OK;
+    if ((long long)B * h * w * C == 0) return VKOCR_OK;
+    const bool vec = vec_ok(dtype, C, ld_s, ld_d) && ptr16(ddst, dsrc);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    VK_DISPATCH_DTYPE(dtype, T, (upsample_bwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-                                    reinterpret_cast<const T*>(ddst), ld_d, H, W, reinterpret_cast<T*>(dsrc), ld_s, h, w, B, C, mode,
-                                    accumulate)));
+    VK_DISPATCH_DTYPE(dtype, T, (vec ? launch_upsample_bwd<T, VkVec<T>>(ddst, ld_d, H, W, dsrc, ld_s, h, w, B, C, mode, accumulate, s)
+                                     : launch_upsample_bwd<T, VkScalar<T>>(ddst, ld_d, H, W, dsrc, ld_s, h, w, B, C, mode, accumulate, s)));
     VK_CHECK_LAUNCH("upsample_bwd_kernel");
     return VKOCR_OK;
 }

@@ -75,6 +75,22 @@ def grad_buffer(p: Tensor) -> Tensor:
     return g
 
 
+# Called with the parameters whose .grad has just been accumulated by a backward node (the kernels write .grad
+# directly, so autograd's own post-accumulate hooks never fire for them).  ``parallel.DataParallel`` installs its
+# bucket bookkeeping here to launch the gradient all-reduce while the rest of backward is still running.
+_GRAD_READY_HOOK = None
+
+
+def set_grad_ready_hook(fn) -> None:
+    global _GRAD_READY_HOOK
+    _GRAD_READY_HOOK = fn
+
+
+def _ready(*params: Tensor) -> None:
+    if _GRAD_READY_HOOK is not None:
+        _GRAD_READY_HOOK(params)
+
+
 def _s() -> ctypes.c_void_p:
     return L.stream_ptr()
 
@@ -277,8 +293,10 @@ def _zeros_f32(n: int, device) -> Tensor:
     return torch.zeros(n, dtype=torch.float32, device=device)
 
 
-def _needs_grad(*ts: Optional[Tensor]) -> bool:
-    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+def _needs_grad(ctx) -> bool:
+    """True when autograd will call this node's backward (grad mode is off inside Function.forward, so the node's own
+    needs_input_grad is the only reliable signal)."""
+    return any(ctx.needs_input_grad)
 
 
 # ----------------------------------------------------------------------------------------------------- autograd nodes
@@ -299,7 +317,7 @@ class StemFn(torch.autograd.Function):
         pre = alloc_nhwc(B, Ho, Wo, N, dtype, image.device)
         gemm_nt(a, 1, 1, M, c_pad, c_pad, 1, wp, c_pad, N, _epilogue(pre, pre.stride(3), bias=b.detach()))
         y = alloc_nhwc(B, Ho, Wo, N, dtype, image.device)
-        train = _needs_grad(w, b, ln_w, ln_b)
+        train = _needs_grad(ctx)
         mean = torch.empty(M, dtype=torch.float32, device=image.device) if train else None
         rstd = torch.empty(M, dtype=torch.float32, device=image.device) if train else None
         layernorm_fwd(pre, pre.stride(3), y, y.stride(3), M, N, ln_w.detach(), ln_b.detach(), 0, mean, rstd)
@@ -321,6 +339,7 @@ class StemFn(torch.autograd.Function):
         gemm_tn(dpre, 1, 1, M, N, dpre.stride(3), 1, a, K, c_pad, _epilogue(g, K, out_f32=True, accumulate=True, tn=(0, K, 1)))
         # GEMM order k = (t, c)  ->  parameter layout (n, c, t)
         L.check(L.LIB.vkocr_unpack_grad(L.ptr(g), N, p * p, Cin, L.ptr(grad_buffer(w)), Cin * p * p, 1, p * p, _s()), 'unpack_grad')
+        _ready(w, b, ln_w, ln_b)
         return None, None, None, None, None, None
 
 
@@ -331,7 +350,7 @@ class LayerNormFn(torch.autograd.Function):
     def forward(ctx, x: Tensor, w: Tensor, b: Tensor, act: int) -> Tensor:
         B, H, W, C, ld = geom(x)
         y = alloc_nhwc(B, H, W, C, x.dtype, x.device)
-        train = _needs_grad(x, w, b)
+        train = _needs_grad(ctx)
         M = B * H * W
         mean = torch.empty(M, dtype=torch.float32, device=x.device) if train else None
         rstd = torch.empty(M, dtype=torch.float32, device=x.device) if train else None
@@ -349,6 +368,7 @@ class LayerNormFn(torch.autograd.Function):
         dx = alloc_nhwc(B, H, W, C, x.dtype, x.device)
         layernorm_bwd(dy, dy.stride(3), x, ld, mean, rstd, w.detach(), b.detach(), ctx.act, dx, dx.stride(3), B * H * W, C,
                       grad_buffer(w), grad_buffer(b), None)
+        _ready(w, b)
         return dx, None, None, None
 
 
@@ -360,7 +380,7 @@ class ConvNextLayerFn(torch.autograd.Function):
         B, H, W, C, ld = geom(x)
         M = B * H * W
         dt, dev = x.dtype, x.device
-        train = _needs_grad(x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale)
+        train = _needs_grad(ctx)
         conv = alloc_nhwc(B, H, W, C, dt, dev)
         dwconv7(x, conv, packed_dwconv(dw_w, False), dw_b.detach(), None)
         lnout = alloc_nhwc(B, H, W, C, dt, dev)
@@ -428,6 +448,7 @@ class ConvNextLayerFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = alloc_nhwc(B, H, W, C, dt, dev)
             dwconv7(dconv, dx, packed_dwconv(dw_w, True), None, dy)   # + residual gradient
+        _ready(dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale)
         return (dx,) + (None,) * 10
 
 
@@ -449,7 +470,7 @@ class PatchConvFn(torch.autograd.Function):
         L.check(L.LIB.vkocr_space_to_depth2(_tag(dt), L.ptr(x), ld, B, H, W, C, L.ptr(a), c_pad, 0, 0, _s()), 'space_to_depth2')
         y = alloc_nhwc(B, Ho, Wo, N, dt, dev)
         gemm_nt(a, 1, 1, M, 4 * C, c_pad, 1, wp, c_pad, N, _epilogue(y, y.stride(3), bias=b.detach()))
-        if _needs_grad(x, w, b):
+        if _needs_grad(ctx):
             ctx.save_for_backward(a, w, b)
             ctx.meta = (B, H, W, C, N, c_pad)
         return y
@@ -474,6 +495,7 @@ class PatchConvFn(torch.autograd.Function):
             dx = alloc_nhwc(B, H, W, C, dt, dev)
             L.check(L.LIB.vkocr_space_to_depth2(_tag(dt), L.ptr(dx), dx.stride(3), B, H, W, C, L.ptr(da), K, 1, 0, _s()),
                     'space_to_depth2(adjoint)')
+        _ready(w, b)
         return dx, None, None
 
 
@@ -497,7 +519,7 @@ class ConvLnGeluFn(torch.autograd.Function):
             gemm_nt(x, 1, 1, M, C, ld, 1, wp, c_pad, N, _epilogue(pre, pre.stride(3), bias=b.detach()))
         else:
             gemm_nt(x, B, H, W, C, ld, ks, wp, c_pad, N, _epilogue(pre, pre.stride(3), bias=b.detach()))
-        train = _needs_grad(x, w, b, ln_w, ln_b)
+        train = _needs_grad(ctx)
         mean = torch.empty(M, dtype=torch.float32, device=dev) if train else None
         rstd = torch.empty(M, dtype=torch.float32, device=dev) if train else None
         y = alloc_nhwc(B, H, W, N, dt, dev)
@@ -535,6 +557,7 @@ class ConvLnGeluFn(torch.autograd.Function):
             else:
                 wd, n_pad = packed_conv_dgrad([w], dt)
                 gemm_nt(dpre, B, H, W, N, dpre.stride(3), ks, wd, n_pad, C, _epilogue(dx, dx.stride(3)))
+        _ready(w, b, ln_w, ln_b)
         return dx, None, None, None, None
 
 
@@ -666,7 +689,7 @@ class HeadGroupFn(torch.autograd.Function):
                                               L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), L.ptr(hd[5].detach()), O,
                                               int(softplus[i]), L.ptr(out), H * W, M, _s()), 'head_tail_fwd')
             outs.append(out)
-        if _needs_grad(x, *params):
+        if _needs_grad(ctx):
             ctx.save_for_backward(x, up, conv, *outs, *params)
             ctx.meta = (nh, factor, mode, tuple(softplus), slot, ks)
         else:
@@ -719,4 +742,217 @@ class HeadGroupFn(torch.autograd.Function):
                 upsample_bwd(dup, dx, C, mode, False)
             else:
                 dx = dup
+        _ready(*params)
         return (dx, None, None, None) + (None,) * len(params)
+
+
+# ----------------------------------------------------------------------------------------------------- fused losses
+def _f32c(t: Tensor) -> Tensor:
+    """Caller-provided loss operand -> contiguous fp32 on its own device (no-op for the usual case)."""
+    L.require_cuda(t)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _i64c(t: Tensor) -> Tensor:
+    L.require_cuda(t)
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t.contiguous()
+
+
+class RoughLossFn(torch.autograd.Function):
+    """focal + dice + masked log-space smooth-L1 of the rough maps inside the core box, one reduction pass
+    (AdaptiveScalingRoughLossFunction.__call__, loss_function/adaptive_scaling.py:53-131)."""
+
+    @staticmethod
+    def forward(ctx, logit: Tensor, height: Tensor, gt_mask: Tensor, gt_score: Tensor, up: int, left: int,
+                height_min: float, score_min: float, focal_factor: float, dice_factor: float, l1_factor: float) -> Tensor:
+        logit_c, height_c = _f32c(logit), _f32c(height)
+        gt_mask, gt_score = _f32c(gt_mask), _f32c(gt_score)
+        B, _, H, W = logit_c.shape
+        _, CH, CW = gt_mask.shape
+        dev = logit_c.device
+        sums = torch.zeros(6, dtype=torch.float64, device=dev)
+        coef = torch.empty(6, dtype=torch.float32, device=dev)
+        L.check(L.LIB.vkocr_rough_loss_fwd(L.ptr(logit_c), L.ptr(height_c), L.ptr(gt_mask), L.ptr(gt_score), B, H, W, up, left, CH, CW,
+                                           height_min, score_min, focal_factor, dice_factor, l1_factor, L.ptr(sums), L.ptr(coef), _s()),
+                'rough_loss_fwd')
+        ctx.save_for_backward(logit_c, height_c, gt_mask, gt_score)
+        ctx.coef = coef
+        ctx.meta = (B, H, W, up, left, CH, CW, height_min, score_min)
+        return coef[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        logit, height, gt_mask, gt_score = ctx.saved_tensors
+        B, H, W, up, left, CH, CW, hmin, smin = ctx.meta
+        gout = gout.contiguous().float()
+        dlogit = torch.empty_like(logit)
+        dheight = torch.empty_like(height)
+        L.check(L.LIB.vkocr_rough_loss_bwd(L.ptr(logit), L.ptr(height), L.ptr(gt_mask), L.ptr(gt_score), B, H, W, up, left, CH, CW,
+                                           hmin, smin, L.ptr(ctx.coef), L.ptr(gout), L.ptr(dlogit), L.ptr(dheight), _s()),
+                'rough_loss_bwd')
+        return (dlogit, dheight) + (None,) * 9
+
+
+_FACTOR_CACHE: Dict[Tuple, Tensor] = {}
+
+
+def _device_factors(values: Tuple[float, ...], device) -> Tensor:
+    key = (values, str(device))
+    t = _FACTOR_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(values, dtype=torch.float32, device=device)
+        _FACTOR_CACHE[key] = t
+    return t
+
+
+class PreciseLossFn(torch.autograd.Function):
+    """Dense pos/neg L2 of sigmoid(prob) inside the core box + label-point gather terms (offset smooth-L1, distance
+    regulation, soft-label CE of the corner angles, corner-distance smooth-L1), x loss_factor
+    (AdaptiveScalingPreciseLossFunction.__call__, loss_function/adaptive_scaling.py:181-346)."""
+
+    @staticmethod
+    def forward(ctx, prob: Tensor, off: Tensor, ang: Tensor, dist: Tensor, gt_score: Tensor, gt_mask: Tensor, up: int, left: int,
+                py: Tensor, px: Tensor, gt_off: Tensor, gt_ang: Tensor, gt_dist: Tensor, beta: float,
+                factors: Tuple[float, ...]) -> Tensor:
+        prob_c, off_c, ang_c, dist_c = _f32c(prob), _f32c(off), _f32c(ang), _f32c(dist)
+        gt_score, gt_mask = _f32c(gt_score), _f32c(gt_mask)
+        py, px, gt_off = _i64c(py), _i64c(px), _i64c(gt_off)
+        gt_ang, gt_dist = _f32c(gt_ang), _f32c(gt_dist)
+        B, _, H, W = prob_c.shape
+        _, CH, CW = gt_mask.shape
+        P = int(py.shape[1])
+        dev = prob_c.device
+        fac = _device_factors(tuple(float(f) for f in factors), dev)
+        sums = torch.zeros(8, dtype=torch.float64, device=dev)
+        coef = torch.empty(3, dtype=torch.float32, device=dev)
+        L.check(L.LIB.vkocr_precise_loss_fwd(L.ptr(prob_c), L.ptr(off_c), L.ptr(ang_c), L.ptr(dist_c), L.ptr(gt_score), L.ptr(gt_mask),
+                                             B, H, W, up, left, CH, CW, L.ptr(py), L.ptr(px), L.ptr(gt_off), L.ptr(gt_ang),
+                                             L.ptr(gt_dist), P, beta, L.ptr(fac), L.ptr(sums), L.ptr(coef), _s()), 'precise_loss_fwd')
+        ctx.save_for_backward(prob_c, off_c, ang_c, dist_c, gt_score, gt_mask, py, px, gt_off, gt_ang, gt_dist)
+        ctx.coef = coef
+        ctx.fac = fac
+        ctx.meta = (B, H, W, up, left, CH, CW, P, beta)
+        return coef[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        prob, off, ang, dist, gt_score, gt_mask, py, px, gt_off, gt_ang, gt_dist = ctx.saved_tensors
+        B, H, W, up, left, CH, CW, P, beta = ctx.meta
+        gout = gout.contiguous().float()
+        dprob = torch.empty_like(prob)
+        doff = torch.zeros_like(off)
+        dang = torch.zeros_like(ang)
+        ddist = torch.zeros_like(dist)
+        L.check(L.LIB.vkocr_precise_loss_bwd(L.ptr(prob), L.ptr(off), L.ptr(ang), L.ptr(dist), L.ptr(gt_score), L.ptr(gt_mask), B, H, W,
+                                             up, left, CH, CW, L.ptr(py), L.ptr(px), L.ptr(gt_off), L.ptr(gt_ang), L.ptr(gt_dist), P,
+                                             beta, L.ptr(ctx.fac), L.ptr(ctx.coef), L.ptr(gout), L.ptr(dprob), L.ptr(doff),
+                                             L.ptr(dang), L.ptr(ddist), _s()), 'precise_loss_bwd')
+        return (dprob, doff, dang, ddist) + (None,) * 11
+
+
+# ----------------------------------------------------------------------------------------------------- primitive losses
+FOCAL, DICE, L1, SMOOTH_L1, L2, WAHR = range(6)
+
+
+class PointwiseLossFn(torch.autograd.Function):
+    """One of the element-wise primitive losses with optional mask, reduced on the device
+    (focal_with_logits.py, dice.py, l1.py, l2.py, weight_adaptive_heatmap_regression.py)."""
+
+    @staticmethod
+    def forward(ctx, pred: Tensor, gt: Tensor, mask: Optional[Tensor], kind: int, p0: float, p1: float,
+                pre_sigmoid: bool = False) -> Tensor:
+        pred_c, gt_c = _f32c(pred), _f32c(gt)
+        if gt_c.shape != pred_c.shape:
+            gt_c = gt_c.expand_as(pred_c).contiguous()
+        mask_c = None
+        if mask is not None:
+            mask_c = _f32c(mask)
+            if mask_c.shape != pred_c.shape:
+                mask_c = mask_c.expand_as(pred_c).contiguous()
+        n = pred_c.numel()
+        dev = pred_c.device
+        sums = torch.zeros(3, dtype=torch.float64, device=dev)
+        coef = torch.empty(3, dtype=torch.float32, device=dev)
+        L.check(L.LIB.vkocr_pointwise_loss_fwd(kind, int(pre_sigmoid), L.ptr(pred_c), L.ptr(gt_c), L.ptr(mask_c), n, p0, p1, L.ptr(sums), L.ptr(coef),
+                                               _s()), 'pointwise_loss_fwd')
+        ctx.save_for_backward(pred_c, gt_c, mask_c if mask_c is not None else torch.empty(0, device=dev))
+        ctx.coef = coef
+        ctx.meta = (kind, p0, p1, mask_c is not None, tuple(pred.shape), int(pre_sigmoid))
+        return coef[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        pred, gt, mask = ctx.saved_tensors
+        kind, p0, p1, has_mask, shape, pre_sigmoid = ctx.meta
+        gout = gout.contiguous().float()
+        dpred = torch.empty_like(pred)
+        L.check(L.LIB.vkocr_pointwise_loss_bwd(kind, pre_sigmoid, L.ptr(pred), L.ptr(gt), L.ptr(mask if has_mask else None), pred.numel(), p0, p1,
+                                               L.ptr(ctx.coef), L.ptr(gout), L.ptr(dpred), _s()), 'pointwise_loss_bwd')
+        return dpred.reshape(shape), None, None, None, None, None, None
+
+
+class SoftCrossEntropyFn(torch.autograd.Function):
+    """F.cross_entropy(pred, gt) with probability targets, class axis 1 (cross_entropy_with_logits.py:16-19)."""
+
+    @staticmethod
+    def forward(ctx, pred: Tensor, gt: Tensor) -> Tensor:
+        pred_c, gt_c = _f32c(pred), _f32c(gt)
+        if pred_c.dim() < 2 or pred_c.shape != gt_c.shape:
+            raise L.VkocrError('soft cross entropy expects pred and gt of equal shape (N, C, ...)')
+        outer, C = int(pred_c.shape[0]), int(pred_c.shape[1])
+        inner = pred_c.numel() // max(outer * C, 1)
+        dev = pred_c.device
+        sums = torch.zeros(1, dtype=torch.float64, device=dev)
+        coef = torch.empty(2, dtype=torch.float32, device=dev)
+        L.check(L.LIB.vkocr_soft_ce_fwd(L.ptr(pred_c), L.ptr(gt_c), outer, C, inner, L.ptr(sums), L.ptr(coef), _s()), 'soft_ce_fwd')
+        ctx.save_for_backward(pred_c, gt_c)
+        ctx.coef = coef
+        ctx.meta = (outer, C, inner)
+        return coef[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        pred, gt = ctx.saved_tensors
+        outer, C, inner = ctx.meta
+        gout = gout.contiguous().float()
+        dpred = torch.empty_like(pred)
+        L.check(L.LIB.vkocr_soft_ce_bwd(L.ptr(pred), L.ptr(gt), outer, C, inner, L.ptr(ctx.coef), L.ptr(gout), L.ptr(dpred), _s()),
+                'soft_ce_bwd')
+        return dpred, None
+
+
+class HardNegativeBceFn(torch.autograd.Function):
+    """BCE-with-logits over all positives plus the k hardest negatives, k = min(round(ratio * #pos), #neg), selected by
+    a device-side radix select (weighted_bce_with_logits.py:18-54; no host synchronisation)."""
+
+    @staticmethod
+    def forward(ctx, pred: Tensor, gt: Tensor, mask: Optional[Tensor], negative_ratio: float, eps: float) -> Tensor:
+        pred_c, gt_c = _f32c(pred), _f32c(gt)
+        mask_c = _f32c(mask) if mask is not None else None
+        n = pred_c.numel()
+        dev = pred_c.device
+        state = torch.zeros(8 + 256, dtype=torch.int64, device=dev)
+        sums = torch.zeros(4, dtype=torch.float64, device=dev)
+        coef = torch.empty(4, dtype=torch.float32, device=dev)
+        L.check(L.LIB.vkocr_hard_negative_bce_fwd(L.ptr(pred_c), L.ptr(gt_c), L.ptr(mask_c), n, negative_ratio, eps, L.ptr(state),
+                                                  L.ptr(sums), L.ptr(coef), _s()), 'hard_negative_bce_fwd')
+        ctx.save_for_backward(pred_c, gt_c, mask_c if mask_c is not None else torch.empty(0, device=dev))
+        ctx.coef, ctx.state = coef, state
+        ctx.meta = (mask_c is not None, tuple(pred.shape))
+        return coef[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        pred, gt, mask = ctx.saved_tensors
+        has_mask, shape = ctx.meta
+        gout = gout.contiguous().float()
+        dpred = torch.empty_like(pred)
+        ties = torch.zeros(1, dtype=torch.int64, device=pred.device)
+        L.check(L.LIB.vkocr_hard_negative_bce_bwd(L.ptr(pred), L.ptr(gt), L.ptr(mask if has_mask else None), pred.numel(),
+                                                  L.ptr(ctx.state), L.ptr(ctx.coef), L.ptr(gout), L.ptr(ties), L.ptr(dpred), _s()),
+                'hard_negative_bce_bwd')
+        return dpred.reshape(shape), None, None, None, None
