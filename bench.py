@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Headline benchmark: training images/sec of the adaptive-scaling model at 640x640 (fwd + bwd + loss [+ gradient
+all-reduce]) on N B200s, beside the reference algorithm's CPU path on the box's own host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--neck upernext|fpn]
+                    [--workload train|backbone|infer] [--batch B] [--size S]
+
+One "step" = the reference's two-pass training step (experiment/adaptive_scaling/train.py:397-478 minus data loading
+and optimizer): forward_rough -> rough loss/2 -> backward, forward_precise -> precise loss/2 -> backward, on B rough +
+B precise synthetic images per GPU; "images/sec" = B * N / step time (image pairs).  For N > 1 launch
+with torchrun (one rank per GPU, NCCL); the gradient all-reduce is bucketed and overlapped (parallel.py).
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event timed, max over ranks.  `e2e`: the same step
+through the public API from pinned HOST buffers (H2D of both batches and D2H of both losses inside the timed region).
+`roofline`: the dominant kernel (the tcgen05 implicit-GEMM 3x3 convolution of the precise head group), algorithmic
+FLOPs / CUDA-event duration measured inside the timed region, against MEASURED_PEAKS.json.  `cpu_baseline`: the oracle
+(port of the reference algorithm, plain fp32 PyTorch) on the host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'train images/sec @640x640 (fwd+bwd+loss)'
+UNIT = 'images/s'
+POINTS = 200          # label points per image (train.py:58)
+INSET = 10            # core-box inset of the reference's integration test (tests/test_adaptive_scaling.py:126-169)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--neck', default='upernext', choices=['upernext', 'fpn'])
+    ap.add_argument('--workload', default='train', choices=['train', 'backbone', 'infer'])
+    ap.add_argument('--batch', type=int, default=None)
+    ap.add_argument('--size', type=int, default=None)
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--profile', action='store_true', help='after timing, run one step with every C-ABI call bracketed '
+                    'by CUDA events and write the per-kernel table to gpurun_out/kernel_table_<workload>.json')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'hbm_gbs': float(p['hbm_gbs']), 'tflops_burst': float(p['bf16_tflops']),
+                'tflops_sustained': float(p.get('bf16_tflops_sustained', p['bf16_tflops'])), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tflops_burst': 1590.0, 'tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int) -> None:
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self) -> None:
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows
+        for _, line in rows:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ synthetic data
+def make_batches(batch: int, size: int, seed: int):
+    """Synthetic batches of the collate schema (dataset/adaptive_scaling.py:282-368), CPU tensors."""
+    from oracle import synth
+    rb = synth.synth_rough_batch(batch, size, size, seed=seed, inset=INSET)
+    pb = synth.synth_precise_batch(batch, size, size, points=POINTS, seed=seed, inset=INSET)
+    return rb, pb
+
+
+def tensor_bytes(d) -> int:
+    import torch
+    return sum(v.numel() * v.element_size() for v in d.values() if isinstance(v, torch.Tensor))
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_step_time(neck: str, batch: int, size: int, steps: int, warmup: int, threads: int):
+    """Oracle (restatement of the reference's algorithm in stock fp32 PyTorch) training step on the host cores."""
+    import torch
+    from oracle import loss as ol
+    from oracle import model as om
+    from oracle import synth
+    torch.set_num_threads(threads)
+    sd = synth.synth_state_dict('tiny', neck, seed=133)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    rb, pb = make_batches(batch, size, 133)
+    rk = ('downsampled_mask', 'downsampled_score_map', 'downsampled_shape', 'downsampled_core_box')
+    pk = ('downsampled_char_prob_score_map', 'downsampled_char_mask', 'downsampled_shape', 'downsampled_core_box',
+          'downsampled_label_point_y', 'downsampled_label_point_x', 'char_up_left_offsets', 'char_corner_angles',
+          'char_corner_distances')
+
+    def step():
+        for p in params.values():
+            p.grad = None
+        rl = ol.rough_loss(*om.forward_rough(params, rb['image']), *(rb[k] for k in rk))
+        (rl / 2).backward()
+        pl = ol.precise_loss(None, *om.forward_precise(params, pb['image']), *(pb[k] for k in pk))
+        (pl / 2).backward()
+        return float(rl), float(pl)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    size = args.size or 640
+    sample_batch = 2
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    sec = cpu_step_time(args.neck, sample_batch, size, steps, warmup, threads)
+    value = sample_batch / sec
+    sample = (f'{sample_batch} image pairs of {size}x{size} per step (the workload\'s per-GPU batch is {args.batch or 32}); '
+              f'{steps} timed step(s), {warmup} warm-up')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
+        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': f'adaptive-scaling TINY/{args.neck.upper()} two-pass training step, {size}x{size}, fp32, host CPU',
+                   'global_batch': sample_batch, 'image_size': size, 'label_points': POINTS},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    import vkit_ocr_model_adaptive_scaling_b200 as vk
+    from vkit_ocr_model_adaptive_scaling_b200 import _lib as L
+    from vkit_ocr_model_adaptive_scaling_b200.parallel import DataParallel
+    from vkit_ocr_model_adaptive_scaling_b200.training import batch_to_device, train_step
+    from oracle import synth  # synthetic weights / batches only (test infrastructure generating inputs, never on the timed path)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert L.LIB.vkocr_device_check(local_rank) == 0, L.LIB.vkocr_last_error()
+    peaks = load_peaks()
+    dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    vk.set_compute_dtype(dtype)
+
+    M, LF = vk.model, vk.loss_function
+    size = args.size or (2048 if args.workload == 'infer' else 640)
+    batch = args.batch or (8 if args.workload == 'infer' else 32)
+    cfg = M.AdaptiveScalingConfig(size=M.AdaptiveScalingSize.TINY, neck_head_type=M.AdaptiveScalingNeckHeadType(args.neck))
+    torch.manual_seed(133)
+    model = M.AdaptiveScaling(cfg)
+    model.load_state_dict(synth.synth_state_dict('tiny', args.neck, seed=133), strict=True)
+    model.to(dev)
+    rough_fn = LF.AdaptiveScalingRoughLossFunction(LF.AdaptiveScalingRoughLossFunctionConifg())
+    precise_fn = LF.AdaptiveScalingPreciseLossFunction(LF.AdaptiveScalingPreciseLossFunctionConifg())
+
+    rb_host, pb_host = make_batches(batch, size, 133 + rank)
+    pin = lambda d: {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    rb_host, pb_host = pin(rb_host), pin(pb_host)
+    rb, pb = batch_to_device(rb_host, dev), batch_to_device(pb_host, dev)
+    h2d = tensor_bytes(rb_host) + tensor_bytes(pb_host)
+
+    dp = None
+    if args.workload == 'train':
+        model.train()   # stochastic depth active, as in the reference loop (train.py:396)
+        # flat gradient buckets also on one GPU: begin_step() zeroes 5 buffers instead of ~300 tensors, and for N > 1 the
+        # bucketed all-reduce overlaps the backward passes
+        dp = DataParallel(model)
+
+        def step(rbatch, pbatch):
+            return train_step(model, rough_fn, precise_fn, rbatch, pbatch, dp)
+        images_per_step = batch
+        workload = (f'adaptive-scaling TINY/{args.neck.upper()} two-pass training step (fwd+bwd+loss'
+                    f'{"+bucketed NCCL grad all-reduce" if world > 1 else ""}), batch {batch}/GPU, {size}x{size}, {POINTS} label points')
+    elif args.workload == 'backbone':
+        model.train()
+        backbone = model.backbone
+
+        def step(rbatch, pbatch):
+            for p in backbone.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+            feats = backbone(rbatch['image'])
+            loss = sum(f.float().square().mean() for f in feats)
+            loss.backward()
+            return loss.detach(), loss.detach()
+        images_per_step = batch
+        workload = f'ConvNeXt-T backbone forward/backward, batch {batch}/GPU, {size}x{size}'
+    else:
+        model.eval()
+
+        def step(rbatch, pbatch):
+            with torch.no_grad():
+                mask, height = model.forward_rough(rbatch['image'])
+            return mask.sum(), height.sum()
+        images_per_step = batch
+        workload = f'forward_rough inference, batch {batch}/GPU, {size}x{size}'
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(rb, pb)
+    barrier()
+
+    # ---- timed region: device-resident inputs, CUDA events on the launching (current) stream, GEMM launches bracketed
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = L.LIB.vkocr_launch_count()
+    L.LIB.start_profile(only={'vkocr_gemm_nt', 'vkocr_gemm_tn'})
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        losses = step(rb, pb)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    prof = L.LIB.stop_profile()
+    launches = (L.LIB.vkocr_launch_count() - launches0) // max(args.steps, 1)
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    value = images_per_step * world / (ms / 1e3)
+    gemm_table = prof.summary()
+
+    # ---- e2e: host (pinned) -> device copies of both batches + device -> host read of both losses, every step
+    e2e = None
+    if not args.no_e2e:
+        loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            a, b = step(batch_to_device(rb_host, dev), batch_to_device(pb_host, dev))
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            rdev = batch_to_device(rb_host, dev)
+            pdev = batch_to_device(pb_host, dev)
+            a, b = step(rdev, pdev)
+            loss_host.copy_(torch.stack([a.float().reshape(()), b.float().reshape(())]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()   # the caller reads the step's losses (train.py:415,453)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        e2e = {'value': images_per_step * world / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
+               'ms_per_step': ms_e2e}
+
+    # ---- optional: full per-kernel table (one extra step, every C-ABI call bracketed)
+    if args.profile and rank == 0:
+        L.LIB.start_profile()
+        step(rb, pb)
+        torch.cuda.synchronize()
+        table = L.LIB.stop_profile().summary()
+        rows = sorted(table.items(), key=lambda kv: -kv[1]['ms'])
+        total = sum(r['ms'] for _, r in rows)
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', f'kernel_table_{args.workload}_{args.neck}.json'), 'w') as f:
+            json.dump({'step_ms_sum_of_calls': total, 'rows': [dict(label=k, **v) for k, v in rows]}, f, indent=1)
+        print(f'# per-call device time, one step: {total:.2f} ms over {sum(r["calls"] for _, r in rows)} C-ABI calls', file=sys.stderr)
+        for k, r in rows[:40]:
+            tf = r['flops'] / (r['ms'] * 1e-3) / 1e12 if r['flops'] else 0.0
+            print(f'#  {r["ms"]:9.3f} ms {100 * r["ms"] / total:5.1f}%  x{r["calls"]:<4d} {tf:7.1f} TF/s  {k}', file=sys.stderr)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: the GEMM label with the largest share of the timed region
+    roofline = None
+    if gemm_table:
+        label, row = max(gemm_table.items(), key=lambda kv: kv[1]['ms'])
+        per_launch_ms = row['ms'] / row['calls']
+        achieved = row['flops'] / row['calls'] / (per_launch_ms * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'kernel': f'vkocr_gemm_tc_kernel [{label}]', 'achieved': achieved,
+                    'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops_sustained'],
+                    'traffic': None, 'peak_source': f'{peaks["source"]} sustained bf16 (kernel timed inside a long step)',
+                    'launch_ms': per_launch_ms, 'share_of_step': row['ms'] / args.steps / ms,
+                    'all_gemm_share_of_step': sum(r['ms'] for r in gemm_table.values()) / args.steps / ms,
+                    'all_gemm_tflops': sum(r['flops'] for r in gemm_table.values()) / sum(r['ms'] for r in gemm_table.values()) / 1e9}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and args.workload == 'train':
+        threads = os.cpu_count() or 1
+        sec = cpu_step_time(args.neck, 2, size, 1, 0, threads)
+        cpu_baseline = {'value': 2 / sec, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                        'sample': f'2 image pairs of {size}x{size}, one fp32 training step of the oracle (reference algorithm) on the host cores'}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if dtype == torch.bfloat16 else 'f32', 'data': 'synthetic',
+        'config': {'workload': workload, 'global_batch': batch * world, 'image_size': size, 'label_points': POINTS,
+                   'parallelism': f'dp{world}', 'l2': f'inputs per step ({h2d / 1e6:.0f} MB) and every activation exceed the 126 MB L2'},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+        'losses': [float(x) for x in losses],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -43,6 +43,7 @@ enum VkocrDtype { VKOCR_F32 = 0, VKOCR_BF16 = 1 };
 int vkocr_abi_version(void);
 const char* vkocr_last_error(void);
 int vkocr_device_check(int device); /* 0 iff `device` is compute capability 10.x */
+long long vkocr_launch_count(void);  /* kernels launched by this library in this process so far */
 
 /* ------------------------------------------------------------------------- GEMM / implicit-GEMM convolution
  * Replaces: helper.conv1x1 = nn.Linear on BHWC (model/helper.py:18-22), helper.conv3x3 / conv5x5 'same' convolutions

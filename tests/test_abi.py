@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_build.LIB)
     for name in symbols:
         assert hasattr(lib, name), f'{name} is declared in include/vkocr_b200.h but not exported by the library'
-    bound = set(_lib._SIGNATURES) | {'vkocr_last_error'}
+    bound = set(_lib._SIGNATURES) | {'vkocr_last_error', 'vkocr_launch_count'}
     assert bound == set(symbols), f'ctypes table and header disagree: {sorted(bound ^ set(symbols))}'
     assert _lib.LIB.vkocr_abi_version() == 1
 

@@ -111,6 +111,8 @@ def _load() -> ctypes.CDLL:
         path = _build.build()
     lib = ctypes.CDLL(path)
     lib.vkocr_last_error.restype = ctypes.c_char_p
+    lib.vkocr_launch_count.restype = ctypes.c_longlong
+    lib.vkocr_launch_count.argtypes = []
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError here == the .so does not export a declared symbol
         fn.argtypes = argtypes
@@ -118,7 +120,80 @@ def _load() -> ctypes.CDLL:
     return lib
 
 
-LIB = _load()
+class _Profile:
+    """Optional CUDA-event bracketing of C-ABI calls on the current stream (bench.py / tools): per-call device time,
+    grouped by a label the operator layer attaches (entry point + shape)."""
+
+    def __init__(self) -> None:
+        self.active = False
+        self.only = None
+        self.records = []     # (entry point, label, flops, bytes, start event, end event)
+        self.pending = None   # (label, flops, bytes) noted by the operator layer for the next call
+
+    def note(self, label: str, flops: float = 0.0, nbytes: float = 0.0) -> None:
+        if self.active:
+            self.pending = (label, flops, nbytes)
+
+    def summary(self):
+        """{label: dict(entry, calls, ms, flops, bytes)} — call after torch.cuda.synchronize()."""
+        out = {}
+        for entry, label, flops, nbytes, e0, e1 in self.records:
+            row = out.setdefault(label, {'entry': entry, 'calls': 0, 'ms': 0.0, 'flops': 0.0, 'bytes': 0.0})
+            row['calls'] += 1
+            row['ms'] += e0.elapsed_time(e1)
+            row['flops'] += flops
+            row['bytes'] += nbytes
+        return out
+
+
+PROFILE = _Profile()
+
+
+class _Library:
+    """The loaded C ABI.  Entry points are plain attributes (raw ctypes functions); while profiling they are swapped for
+    wrappers that bracket the call with CUDA events on the current stream."""
+
+    def __init__(self, cdll: ctypes.CDLL) -> None:
+        self._cdll = cdll
+        self._raw = {name: getattr(cdll, name) for name in list(_SIGNATURES) + ['vkocr_last_error', 'vkocr_launch_count']}
+        self._install(self._raw)
+
+    def _install(self, table) -> None:
+        for name, fn in table.items():
+            setattr(self, name, fn)
+
+    def start_profile(self, only=None) -> None:
+        PROFILE.active, PROFILE.only, PROFILE.records, PROFILE.pending = True, only, [], None
+        wrapped = {}
+        for name, fn in self._raw.items():
+            if name in ('vkocr_last_error', 'vkocr_launch_count', 'vkocr_abi_version', 'vkocr_device_check'):
+                continue
+            if only is not None and name not in only:
+                continue
+            wrapped[name] = self._wrap(name, fn)
+        self._install(wrapped)
+
+    def stop_profile(self):
+        self._install(self._raw)
+        PROFILE.active = False
+        return PROFILE
+
+    @staticmethod
+    def _wrap(name, fn):
+        def call(*args):
+            note, PROFILE.pending = PROFILE.pending, None
+            label, flops, nbytes = note if note is not None else (name, 0.0, 0.0)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            PROFILE.records.append((name, label, flops, nbytes, e0, e1))
+            return rc
+        return call
+
+
+LIB = _Library(_load())
 
 
 class VkocrError(RuntimeError):

@@ -1,6 +1,7 @@
 // C-ABI runtime basics: version, thread-local error text, device check.  See include/vkocr_b200.h.
 #include "common.cuh"
 #include <stdarg.h>
+#include <atomic>
 
 #define VKOCR_ABI_VERSION 1
 
@@ -12,6 +13,9 @@ void vkocr_set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void vkocr_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int vkocr_sm_count() {
     static int sms[64] = {0};
@@ -30,6 +34,9 @@ extern "C" {
 int vkocr_abi_version(void) { return VKOCR_ABI_VERSION; }
 
 const char* vkocr_last_error(void) { return g_err; }
+
+// Number of kernels this library has launched in this process so far (bench.py reports the per-step delta).
+long long vkocr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // 0 when `device` is a compute-capability 10.x GPU (the only target of this library), negative otherwise.
 int vkocr_device_check(int device) {

@@ -22,6 +22,7 @@ enum VkocrDtype { VKOCR_F32 = 0, VKOCR_BF16 = 1 };
 
 void vkocr_set_error(const char* fmt, ...);
 int vkocr_sm_count();
+void vkocr_note_launch();   // bumps the process-wide kernel-launch counter (vkocr_launch_count)
 
 #define VK_FAIL(code, ...)               \
     do {                                 \
@@ -36,6 +37,7 @@ int vkocr_sm_count();
 
 #define VK_CHECK_LAUNCH(name)                                                        \
     do {                                                                             \
+        vkocr_note_launch();                                                         \
         cudaError_t e__ = cudaGetLastError();                                        \
         if (e__ != cudaSuccess)                                                      \
             VK_FAIL(VKOCR_CUDA_ERROR, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \

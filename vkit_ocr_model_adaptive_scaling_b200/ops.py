@@ -9,6 +9,7 @@ Parameter gradients are accumulated by the kernels straight into ``param.grad`` 
 data-parallel bucket views alias (see ``parallel.py``).
 """
 import ctypes
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -104,19 +105,24 @@ class _PackCache:
     """Kernel-layout copies of the fp32 master weights, refreshed when the parameter's version counter moves."""
 
     def __init__(self) -> None:
-        self.entries: Dict[Tuple, Tuple[int, Tensor]] = {}
+        self.entries: Dict[Tuple, Tuple[Tuple, Tensor, Tuple]] = {}
 
     def get(self, key: Tuple, params: Sequence[Tensor], shape: Tuple[int, ...], dtype: torch.dtype, fill) -> Tensor:
         version = tuple(int(p._version) for p in params) + tuple(int(p.data_ptr()) for p in params)
         ent = self.entries.get(key)
-        if ent is not None and ent[0] == version and ent[1].device == params[0].device:
+        # keys carry id(param); a dead parameter's id (and even its storage address) can be reused by a new one, so an
+        # entry is only valid while the very same parameter objects are alive
+        alive = ent is not None and all(r() is p for r, p in zip(ent[2], params))
+        if alive and ent[0] == version and ent[1].device == params[0].device:
             return ent[1]
-        if ent is not None and ent[1].shape == shape and ent[1].dtype == dtype and ent[1].device == params[0].device:
+        if alive and ent[1].shape == shape and ent[1].dtype == dtype and ent[1].device == params[0].device:
             buf = ent[1]
         else:
             buf = torch.zeros(shape, dtype=dtype, device=params[0].device)
         fill(buf)
-        self.entries[key] = (version, buf)
+        if len(self.entries) > 4096:   # entries of parameters that no longer exist
+            self.entries = {k: e for k, e in self.entries.items() if all(r() is not None for r in e[2])}
+        self.entries[key] = (version, buf, tuple(weakref.ref(p) for p in params))
         return buf
 
     def clear(self) -> None:
@@ -229,11 +235,17 @@ SIMT_BACKEND = 0  # tests set this to 1 to route bf16 GEMMs through the SIMT ker
 
 
 def gemm_nt(x: Tensor, B: int, H: int, W: int, C: int, ld_x: int, ks: int, wp: Tensor, c_pad: int, N: int, ep: L.Epilogue) -> None:
+    if L.PROFILE.active:
+        M = B * H * W
+        L.PROFILE.note(f'gemm_nt ks{ks} M{M} K{ks * ks * C} N{N}', 2.0 * M * ks * ks * C * N)
     g = L.ConvGeom(B, H, W, ks, C, ld_x, c_pad)
     L.check(L.LIB.vkocr_gemm_nt(_tag(x.dtype), SIMT_BACKEND, L.ptr(x), ctypes.byref(g), L.ptr(wp), N, ctypes.byref(ep), _s()), 'gemm_nt')
 
 
 def gemm_tn(p: Tensor, B: int, H: int, W: int, I: int, ld_p: int, ks: int, q: Tensor, J: int, ld_q: int, ep: L.Epilogue) -> None:
+    if L.PROFILE.active:
+        M = B * H * W
+        L.PROFILE.note(f'gemm_tn ks{ks} M{M} I{I} J{J}', 2.0 * M * ks * ks * I * J)
     g = L.ConvGeom(B, H, W, ks, I, ld_p, 0)
     L.check(L.LIB.vkocr_gemm_tn(_tag(p.dtype), SIMT_BACKEND, L.ptr(p), ctypes.byref(g), L.ptr(q), J, ld_q, ctypes.byref(ep), _s()), 'gemm_tn')
 
