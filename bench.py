@@ -325,9 +325,10 @@ def run_ours(args) -> None:
         with open(os.path.join(ROOT, 'gpurun_out', f'kernel_table_{args.workload}_{args.neck}.json'), 'w') as f:
             json.dump({'step_ms_sum_of_calls': total, 'rows': [dict(label=k, **v) for k, v in rows]}, f, indent=1)
         print(f'# per-call device time, one step: {total:.2f} ms over {sum(r["calls"] for _, r in rows)} C-ABI calls', file=sys.stderr)
-        for k, r in rows[:40]:
+        for k, r in rows[:70]:
             tf = r['flops'] / (r['ms'] * 1e-3) / 1e12 if r['flops'] else 0.0
-            print(f'#  {r["ms"]:9.3f} ms {100 * r["ms"] / total:5.1f}%  x{r["calls"]:<4d} {tf:7.1f} TF/s  {k}', file=sys.stderr)
+            gb = r['bytes'] / (r['ms'] * 1e-3) / 1e9 if r['bytes'] else 0.0
+            print(f'#  {r["ms"]:9.3f} ms {100 * r["ms"] / total:5.1f}%  x{r["calls"]:<4d} {tf:7.1f} TF/s {gb:7.0f} GB/s  {k}', file=sys.stderr)
 
     if rank != 0:
         if world > 1:

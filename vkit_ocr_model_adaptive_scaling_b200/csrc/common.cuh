@@ -91,6 +91,30 @@ template <> struct VkVec<__nv_bfloat16> {
     }
 };
 
+// 8-byte vector of 4 bf16 (for register-hungry kernels that want 4 channels per thread in either storage type)
+template <typename T> struct VkVec4;
+template <> struct VkVec4<float> : VkVec<float> {};
+template <> struct VkVec4<__nv_bfloat16> {
+    static constexpr int N = 4;
+    uint2 raw;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { raw = *reinterpret_cast<const uint2*>(p); }
+    __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint2*>(p) = raw; }
+    __device__ __forceinline__ void unpack(float* f) const {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float2 v = __bfloat1622float2(h[i]);
+            f[2 * i] = v.x;
+            f[2 * i + 1] = v.y;
+        }
+    }
+    __device__ __forceinline__ void pack(const float* f) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    }
+};
+
 // One-element "vector" with the VkVec interface: the generic path for channel counts / strides / slice offsets that are
 // not 16-byte aligned.
 template <typename T> struct VkScalar {
@@ -127,13 +151,40 @@ __device__ __forceinline__ float vk_block_sum(float v, float* scratch) {
 }
 
 // ---- math ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float vk_gelu(float x) {  // exact erf GELU (reference helper.py:100-101)
-    return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+// Exact (erf) GELU of the reference (helper.py:100-101) and its derivative.  erf is evaluated with Abramowitz & Stegun
+// 7.1.26 (absolute error <= 1.5e-7, below fp32 round-off of the surrounding math): branch-free, one MUFU.RCP, one
+// MUFU.EX2 and five FMAs instead of libdevice erff's ~25-instruction branchy polynomial — these kernels evaluate GELU
+// on billions of elements per step and are instruction-bound on it.  exp(-x^2/2), needed for erf(x/sqrt 2), is also the
+// Gaussian density of the derivative, so gelu and gelu' share all of the work.  The lower tail is computed directly
+// (0.5*(1-erf|u|) = 0.5*poly*e), not as 1 - erf, so it keeps its relative accuracy.
+__device__ __forceinline__ void vk_gelu_parts(float x, float* cdf, float* pdf) {
+    const float u = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.f));
+    const float e = __expf(-u * u);
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float half_tail = 0.5f * poly * t * e;            // 0.5 * erfc(|x| / sqrt 2)
+    *cdf = x >= 0.f ? 1.f - half_tail : half_tail;
+    *pdf = 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float vk_gelu(float x) {
+    float cdf, pdf;
+    vk_gelu_parts(x, &cdf, &pdf);
+    return x * cdf;
 }
 __device__ __forceinline__ float vk_gelu_grad(float x) {
-    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    float cdf, pdf;
+    vk_gelu_parts(x, &cdf, &pdf);
+    return fmaf(x, pdf, cdf);
+}
+// gelu(x) and gelu'(x) together
+__device__ __forceinline__ void vk_gelu_both(float x, float* g, float* dg) {
+    float cdf, pdf;
+    vk_gelu_parts(x, &cdf, &pdf);
+    *g = x * cdf;
+    *dg = fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ float vk_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float vk_softplus(float x) {  // beta 1, threshold 20 (torch.nn.Softplus)

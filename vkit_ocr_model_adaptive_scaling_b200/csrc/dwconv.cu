@@ -87,21 +87,26 @@ dwconv7_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long 
 }
 
 // dW[c][ky*7+kx] += sum_{b,y,x} dy[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]   (the (C,1,7,7) layout of the parameter)
-// block = CV channel-vector lanes x PG pixel groups; grid = (row chunks, 7 ky).
-template <typename T>
-__global__ void __launch_bounds__(256)
+// One thread = one 16-byte channel vector x one kernel row ky (blockIdx.y) x one SEG-pixel segment of an image row: it
+// loads the SEG+6 input vectors of the segment (halo included) and the SEG gradient vectors once and does 7*SEG*V FMAs
+// on them (each x vector is reused by up to 7 taps from registers), keeping acc[7 kx][V] in registers over all rows the
+// block visits.  Partials are merged per block in shared memory, then one atomic per (channel, tap) and block.
+template <typename T, int SEG>
+__global__ void __launch_bounds__(256, 2)
 dwconv7_wgrad_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restrict__ x, long long ld_x, int B, int H, int W,
-                     int C, int cv_per_block, int cv_base_stride, float* __restrict__ dw) {
-    constexpr int V = VkVec<T>::N;
+                     int C, int cv_per_block, float* __restrict__ dw) {
+    using VT = VkVec4<T>;
+    constexpr int V = VT::N;
     extern __shared__ float red[];  // [7][cv_per_block * V]
     const int CV = C / V;
     const int lane_cv = threadIdx.x % cv_per_block;
-    const int pg = threadIdx.x / cv_per_block;
-    const int PG = blockDim.x / cv_per_block;
-    const int cv = blockIdx.z * cv_base_stride + lane_cv;
+    const int sg = threadIdx.x / cv_per_block;
+    const int NSG = blockDim.x / cv_per_block;
+    const int cv = blockIdx.z * cv_per_block + lane_cv;
     const int ky = blockIdx.y;
-    const bool active = cv < CV && pg < PG;
+    const bool active = cv < CV && sg < NSG;
     const int c = cv * V;
+    const int segs = (W + SEG - 1) / SEG;
     float acc[7][V];
 #pragma unroll
     for (int k = 0; k < 7; ++k)
@@ -118,21 +123,38 @@ dwconv7_wgrad_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restr
             if (ys < 0 || ys >= H) continue;
             const T* dyrow = dy + ((long long)b * H + yy) * W * ld_dy + c;
             const T* xrow = x + ((long long)b * H + ys) * W * ld_x + c;
-            for (int xx = pg; xx < W; xx += PG) {
-                VkVec<T> vd;
-                vd.load(dyrow + (long long)xx * ld_dy);
-                float fd[V];
-                vd.unpack(fd);
+            for (int s = sg; s < segs; s += NSG) {
+                const int x0 = s * SEG;
+                VT in[SEG + 6], gd[SEG];
 #pragma unroll
-                for (int kx = 0; kx < 7; ++kx) {
-                    const int xs = xx + kx - 3;
-                    if (xs < 0 || xs >= W) continue;
-                    VkVec<T> vx;
-                    vx.load(xrow + (long long)xs * ld_x);
-                    float fx[V];
-                    vx.unpack(fx);
+                for (int j = 0; j < SEG + 6; ++j) {
+                    const int xx = x0 + j - 3;
+                    if (xx >= 0 && xx < W) in[j].load(xrow + (long long)xx * ld_x);
+                    else {
+                        float z[V] = {};
+                        in[j].pack(z);
+                    }
+                }
 #pragma unroll
-                    for (int i = 0; i < V; ++i) acc[kx][i] = fmaf(fd[i], fx[i], acc[kx][i]);
+                for (int o = 0; o < SEG; ++o) {
+                    const int xx = x0 + o;
+                    if (xx < W) gd[o].load(dyrow + (long long)xx * ld_dy);
+                    else {
+                        float z[V] = {};
+                        gd[o].pack(z);
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < SEG; ++o) {
+                    float fd[V];
+                    gd[o].unpack(fd);
+#pragma unroll
+                    for (int kx = 0; kx < 7; ++kx) {
+                        float fx[V];
+                        in[o + kx].unpack(fx);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) acc[kx][i] = fmaf(fd[i], fx[i], acc[kx][i]);
+                    }
                 }
             }
         }
@@ -145,7 +167,7 @@ dwconv7_wgrad_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restr
     for (int i = threadIdx.x; i < 7 * cv_per_block * V; i += blockDim.x) {
         const int kx = i / (cv_per_block * V);
         const int rem = i % (cv_per_block * V);
-        const int cc = blockIdx.z * cv_base_stride * V + rem;
+        const int cc = blockIdx.z * cv_per_block * V + rem;
         if (cc < C) atomicAdd(dw + (long long)cc * 49 + (ky * 7 + kx), red[i]);
     }
 }
@@ -177,23 +199,27 @@ int vkocr_dwconv7_fwd(int dtype, const void* x, long long ld_x, void* y, long lo
 int vkocr_dwconv7_wgrad(int dtype, const void* dy, long long ld_dy, const void* x, long long ld_x, int B, int H, int W, int C,
                         float* dw, void* stream) {
     VK_REQUIRE(dy && x && dw, VKOCR_BAD_ARGUMENT, "dwconv7_wgrad: null argument");
-    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    const int V = 4;   // 4 channels per thread in either storage type (VkVec4)
     VK_REQUIRE(C % V == 0 && ld_x % V == 0 && ld_dy % V == 0, VKOCR_BAD_ALIGN, "dwconv7_wgrad: C %d / strides must be multiples of %d", C, V);
     if ((long long)B * H * W == 0) return VKOCR_OK;
+    constexpr int SEG = 8;
     const int CV = C / V;
-    int cvb = CV < 32 ? CV : 32;               // channel vectors per block
+    // channel vectors per block: a divisor-friendly width so that (almost) all 256 threads carry a segment
+    int cvb = CV < 32 ? CV : 32;
     const int zblocks = (CV + cvb - 1) / cvb;
-    const int pg = 256 / cvb;
-    const int threads = pg * cvb;
+    const int segs = (W + SEG - 1) / SEG;
+    int nsg = 256 / cvb;
+    if (nsg > segs) nsg = segs;
+    const int threads = nsg * cvb;
     long long rows = (long long)B * H;
-    long long gx = ((long long)vkocr_sm_count() * 8 + 7 * zblocks - 1) / (7 * zblocks);
+    long long gx = ((long long)vkocr_sm_count() * 6 + 7 * zblocks - 1) / (7 * zblocks);
     if (gx > rows) gx = rows;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, 7, (unsigned)zblocks);
     const size_t smem = (size_t)7 * cvb * V * sizeof(float);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    VK_DISPATCH_DTYPE(dtype, T, (dwconv7_wgrad_kernel<T><<<grid, threads, smem, s>>>(
-                                    reinterpret_cast<const T*>(dy), ld_dy, reinterpret_cast<const T*>(x), ld_x, B, H, W, C, cvb, cvb,
+    VK_DISPATCH_DTYPE(dtype, T, (dwconv7_wgrad_kernel<T, SEG><<<grid, threads, smem, s>>>(
+                                    reinterpret_cast<const T*>(dy), ld_dy, reinterpret_cast<const T*>(x), ld_x, B, H, W, C, cvb,
                                     dw)));
     VK_CHECK_LAUNCH("dwconv7_wgrad_kernel");
     return VKOCR_OK;

@@ -8,7 +8,7 @@
 //   warp 1 (1 lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN (16..256), K=16 per instruction,
 //                    accumulators double-buffered in TMEM (2 x 256 columns).
 //   warp 2           TMEM allocator.
-//   warps 4..7       epilogue: tcgen05.ld -> registers -> bias / GELU / layer-scale / residual -> global.
+//   warps 4..11      epilogue: tcgen05.ld -> registers -> bias / GELU / layer-scale / residual -> global.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
 //
 // Modes (see gemm_common.cuh):
@@ -23,7 +23,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements in one 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int MAX_SMEM = 200 * 1024;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 
@@ -160,7 +161,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 128);
+            mbar_init(tempty_bar(a), 32 * EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -294,8 +295,9 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
     } else if (warp >= 4) {
         // ================================================================ epilogue (TMEM -> registers -> global)
-        const int q = warp & 3;                 // TMEM lane quarter owned by this warp
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
         const int r = q * 32 + lane;            // accumulator row
+        const int cpart = (warp - 4) >> 2;      // which interleaved share of the column chunks
         int as = 0;
         uint32_t aph = 0;
         const VkocrEpilogue& ep = p.ep;
@@ -318,7 +320,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
             const bool vec_ok = (p.mode == 0) && (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
                                 (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0);
-            for (int c = 0; c < chunks; ++c) {
+            for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
                 uint32_t acc[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), acc);
                 if (!row_ok) continue;

@@ -91,22 +91,35 @@ head_tail_fwd_kernel(const T* __restrict__ x, long long ld_x, int inner, const f
     }
 }
 
+// Backward.  Per-channel gradient partials (dgamma, dbeta, conv-bias, dW2) live in registers of the lane that owns the
+// channel for all rows the warp visits; the LayerNorm / projection parameters are read from shared memory each row so
+// that the register budget allows two blocks per SM (the kernel is instruction/latency bound, not HBM bound).
 template <typename T, int NVL, int O>
-__global__ void __launch_bounds__(HT_THREADS)
+__global__ void __launch_bounds__(HT_THREADS, (NVL * O <= 4) ? 2 : 1)
 head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int slice_w, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ w2, int softplus, const float* __restrict__ out,
                      const float* __restrict__ dout, long long pixels_per_image, long long rows, T* __restrict__ dx,
                      long long ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw2,
                      float* __restrict__ db2, float* __restrict__ dbias) {
     constexpr int V = VkVec<T>::N;
-    extern __shared__ float sacc[];  // [(3 + O)][32*NVL*V] + [O]
-    const int CW = 32 * NVL * V;
+    constexpr int CW = 32 * NVL * V;
+    extern __shared__ float sm[];
+    float* s_gm = sm;                 // [CW]
+    float* s_bt = sm + CW;            // [CW]
+    float* s_w = sm + 2 * CW;         // [O][CW]
+    float* sacc = sm + (2 + O) * CW;  // [(3 + O)][CW] + [O]
+    for (int i = threadIdx.x; i < CW; i += blockDim.x) {
+        const bool ok = i < inner;
+        s_gm[i] = ok ? gamma[i] : 0.f;
+        s_bt[i] = ok ? beta[i] : 0.f;
+#pragma unroll
+        for (int o = 0; o < O; ++o) s_w[o * CW + i] = ok ? w2[(long long)o * inner + i] : 0.f;
+    }
     for (int i = threadIdx.x; i < (3 + O) * CW + O; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * HT_WARPS + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * HT_WARPS;
-    float gm[NVL][V], bt[NVL][V], w[O][NVL][V];
     float ag[NVL][V], ab[NVL][V], ax[NVL][V], aw[O][NVL][V];
     float adb[O];
 #pragma unroll
@@ -115,16 +128,9 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
     for (int j = 0; j < NVL; ++j)
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c = (lane + 32 * j) * V + i;
-            const bool ok = c < inner;
-            gm[j][i] = ok ? __ldg(gamma + c) : 0.f;
-            bt[j][i] = ok ? __ldg(beta + c) : 0.f;
             ag[j][i] = ab[j][i] = ax[j][i] = 0.f;
 #pragma unroll
-            for (int o = 0; o < O; ++o) {
-                w[o][j][i] = ok ? __ldg(w2 + (long long)o * inner + c) : 0.f;
-                aw[o][j][i] = 0.f;
-            }
+            for (int o = 0; o < O; ++o) aw[o][j][i] = 0.f;
         }
     const float inv = 1.f / inner;
     for (long long r = warp0; r < rows; r += nwarps) {
@@ -145,18 +151,7 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
 #pragma unroll
             for (int i = 0; i < V; ++i) s += (c + i < inner) ? f[j][i] : 0.f;
         }
-        const float mean = vk_warp_sum(s) * inv;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < NVL; ++j)
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const int c = (lane + 32 * j) * V + i;
-                const float d = f[j][i] - mean;
-                q += (c < inner) ? d * d : 0.f;
-            }
-        const float rstd = rsqrtf(vk_warp_sum(q) * inv + LN_EPS);
-        // upstream gradient of the pre-softplus outputs
+        // upstream gradient of the pre-softplus outputs (same value in every lane)
         const long long b = r / pixels_per_image, pix = r % pixels_per_image;
         float dpre[O];
 #pragma unroll
@@ -168,30 +163,51 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
                 d *= (y > 20.f) ? 1.f : (1.f - __expf(-y));   // sigmoid(pre) = 1 - exp(-softplus(pre))
             }
             dpre[o] = d;
-            adb[o] += d;   // every lane holds the same value; lane 0 flushes
+            adb[o] += d;
         }
-        float s1 = 0.f, s2 = 0.f;
-        float xh[NVL][V], dz[NVL][V];
+        const float mean = vk_warp_sum(s) * inv;
+        float q = 0.f;
 #pragma unroll
         for (int j = 0; j < NVL; ++j)
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 const int c = (lane + 32 * j) * V + i;
+                const float d = f[j][i] - mean;
+                q += (c < inner) ? d * d : 0.f;
+            }
+        const float rstd = rsqrtf(vk_warp_sum(q) * inv + LN_EPS);
+        float s1 = 0.f, s2 = 0.f;
+        // after this loop f holds xhat and dz holds d(loss)/d(LN output) per channel
+        float dz[NVL][V];
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) {
+            const int c0 = (lane + 32 * j) * V;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const int c = c0 + i;
+                const float gmv = s_gm[c];
                 const float h = (f[j][i] - mean) * rstd;
-                const float z = h * gm[j][i] + bt[j][i];
-                const float g = vk_gelu(z);
+                const float z = fmaf(h, gmv, s_bt[c]);
+                float g, gp;
+                vk_gelu_both(z, &g, &gp);
                 float dg = 0.f;
 #pragma unroll
                 for (int o = 0; o < O; ++o) {
-                    dg = fmaf(dpre[o], w[o][j][i], dg);
+                    dg = fmaf(dpre[o], s_w[o * CW + c], dg);     // w == 0 on pad channels
                     aw[o][j][i] = fmaf(dpre[o], g, aw[o][j][i]);
                 }
-                const float d = (c < inner) ? dg * vk_gelu_grad(z) : 0.f;
-                xh[j][i] = (c < inner) ? h : 0.f;
+                const bool ok = c < inner;
+                const float d = ok ? dg * gp : 0.f;
+                const float xh = ok ? h : 0.f;
+                f[j][i] = xh;
                 dz[j][i] = d;
-                s1 += d * gm[j][i];
-                s2 += d * gm[j][i] * xh[j][i];
+                const float dxh = d * gmv;
+                s1 += dxh;
+                s2 = fmaf(dxh, xh, s2);
+                ag[j][i] = fmaf(d, xh, ag[j][i]);
+                ab[j][i] += d;
             }
+        }
         s1 = vk_warp_sum(s1) * inv;
         s2 = vk_warp_sum(s2) * inv;
         T* dxr = dx + r * ld_dx;
@@ -202,10 +218,8 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 const int c = c0 + i;
-                const float dxv = (c < inner) ? rstd * (dz[j][i] * gm[j][i] - s1 - xh[j][i] * s2) : 0.f;
+                const float dxv = (c < inner) ? rstd * (dz[j][i] * s_gm[c] - s1 - f[j][i] * s2) : 0.f;
                 fo[i] = dxv;
-                ag[j][i] += dz[j][i] * xh[j][i];
-                ab[j][i] += dz[j][i];
                 ax[j][i] += dxv;
             }
             if (c0 < slice_w) {
@@ -271,7 +285,7 @@ int launch_bwd(int O, const void* x, long long ld_x, int inner, int slice_w, con
     const long long cap = (long long)vkocr_sm_count() * 2;
     if (blocks > cap) blocks = cap;
 #define VK_HT_BWD(OO)                                                                                                       \
-    head_tail_bwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS, ((3 + OO) * 32 * NVL * V + OO) * sizeof(float), s>>>(   \
+    head_tail_bwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS, ((5 + 2 * OO) * 32 * NVL * V + OO) * sizeof(float), s>>>( \
         reinterpret_cast<const T*>(x), ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, ppi, rows,              \
         reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias)
     switch (O) {

@@ -252,6 +252,8 @@ def gemm_tn(p: Tensor, B: int, H: int, W: int, I: int, ld_p: int, ks: int, q: Te
 
 def layernorm_fwd(x: Tensor, ld_x: int, y: Tensor, ld_y: int, rows: int, C: int, gamma: Tensor, beta: Tensor, act: int,
                   mean: Optional[Tensor], rstd: Optional[Tensor]) -> None:
+    if L.PROFILE.active:
+        L.PROFILE.note(f'layernorm_fwd rows{rows} C{C} act{act}', 0.0, 2.0 * rows * C * x.element_size())
     L.check(L.LIB.vkocr_layernorm_fwd(_tag(x.dtype), L.ptr(x), ld_x, L.ptr(y), ld_y, rows, C, L.ptr(gamma), L.ptr(beta), LN_EPS, act,
                                       L.ptr(mean), L.ptr(rstd), _s()), 'layernorm_fwd')
 
@@ -259,23 +261,34 @@ def layernorm_fwd(x: Tensor, ld_x: int, y: Tensor, ld_y: int, rows: int, C: int,
 def layernorm_bwd(dy: Tensor, ld_dy: int, x: Tensor, ld_x: int, mean: Tensor, rstd: Tensor, gamma: Tensor, beta: Tensor, act: int,
                   dx: Tensor, ld_dx: int, rows: int, C: int, dgamma: Optional[Tensor], dbeta: Optional[Tensor],
                   dxsum: Optional[Tensor]) -> None:
+    if L.PROFILE.active:
+        L.PROFILE.note(f'layernorm_bwd rows{rows} C{C} act{act}', 0.0, 3.0 * rows * C * x.element_size())
     L.check(L.LIB.vkocr_layernorm_bwd(_tag(x.dtype), L.ptr(dy), ld_dy, L.ptr(x), ld_x, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
                                       L.ptr(beta), act, L.ptr(dx), ld_dx, rows, C, L.ptr(dgamma), L.ptr(dbeta), L.ptr(dxsum), _s()),
             'layernorm_bwd')
 
 
 def colsum(x: Tensor, ld: int, rows: int, C: int, out: Tensor) -> None:
+    if L.PROFILE.active:
+        L.PROFILE.note(f'colsum rows{rows} C{C}', 0.0, 1.0 * rows * C * x.element_size())
     L.check(L.LIB.vkocr_colsum(_tag(x.dtype), L.ptr(x), ld, rows, C, L.ptr(out), _s()), 'colsum')
 
 
 def dwconv7(x: Tensor, y: Tensor, wt: Tensor, bias: Optional[Tensor], add: Optional[Tensor]) -> None:
     B, H, W, C, ld_x = geom(x)
+    if L.PROFILE.active:
+        n = B * H * W * C
+        L.PROFILE.note(f'dwconv7 {B}x{H}x{W}x{C}{" +add" if add is not None else ""}', 98.0 * n,
+                       (3.0 if add is not None else 2.0) * n * x.element_size())
     L.check(L.LIB.vkocr_dwconv7_fwd(_tag(x.dtype), L.ptr(x), ld_x, L.ptr(y), y.stride(3), B, H, W, C, L.ptr(wt), L.ptr(bias),
                                     L.ptr(add), 0 if add is None else add.stride(3), _s()), 'dwconv7_fwd')
 
 
 def dwconv7_wgrad(dy: Tensor, x: Tensor, dw: Tensor) -> None:
     B, H, W, C, ld_x = geom(x)
+    if L.PROFILE.active:
+        n = B * H * W * C
+        L.PROFILE.note(f'dwconv7_wgrad {B}x{H}x{W}x{C}', 98.0 * n, 2.0 * n * x.element_size())
     L.check(L.LIB.vkocr_dwconv7_wgrad(_tag(x.dtype), L.ptr(dy), dy.stride(3), L.ptr(x), ld_x, B, H, W, C, L.ptr(dw), _s()),
             'dwconv7_wgrad')
 
@@ -284,6 +297,9 @@ def upsample_fwd(src: Tensor, dst: Tensor, C: int, mode: int, accumulate: bool) 
     """dst[:, :C] (=|+=) resample(src[:, :C]); src/dst are NHWC views (possibly channel slices of wider buffers)."""
     B, _, h, w = src.shape
     _, _, H, W = dst.shape
+    if L.PROFILE.active:
+        L.PROFILE.note(f'upsample_fwd {B}x{h}x{w}->{H}x{W} C{C} mode{mode} acc{int(accumulate)}', 0.0,
+                       (B * h * w + (2 if accumulate else 1) * B * H * W) * C * src.element_size())
     L.check(L.LIB.vkocr_upsample_fwd(_tag(src.dtype), L.ptr(src), src.stride(3), h, w, L.ptr(dst), dst.stride(3), H, W, B, C, mode,
                                      int(accumulate), _s()), 'upsample_fwd')
 
@@ -291,6 +307,8 @@ def upsample_fwd(src: Tensor, dst: Tensor, C: int, mode: int, accumulate: bool) 
 def upsample_bwd(ddst: Tensor, dsrc: Tensor, C: int, mode: int, accumulate: bool) -> None:
     B, _, h, w = dsrc.shape
     _, _, H, W = ddst.shape
+    if L.PROFILE.active:
+        L.PROFILE.note(f'upsample_bwd {B}x{H}x{W}->{h}x{w} C{C} mode{mode}', 0.0, (B * h * w + B * H * W) * C * ddst.element_size())
     L.check(L.LIB.vkocr_upsample_bwd(_tag(ddst.dtype), L.ptr(ddst), ddst.stride(3), H, W, L.ptr(dsrc), dsrc.stride(3), h, w, B, C,
                                      mode, int(accumulate), _s()), 'upsample_bwd')
 
@@ -697,6 +715,8 @@ class HeadGroupFn(torch.autograd.Function):
             O = int(hd[4].shape[0])
             out = torch.empty((B, O, H, W), dtype=torch.float32, device=dev)
             sl = conv[:, i * slot:(i + 1) * slot]
+            if L.PROFILE.active:
+                L.PROFILE.note(f'head_tail_fwd rows{M} inner{inners[i]} O{O}', 0.0, M * (slot * conv.element_size() + 4 * O))
             L.check(L.LIB.vkocr_head_tail_fwd(_tag(dt), L.ptr(sl), conv.stride(3), inners[i], slot, L.ptr(hd[2].detach()),
                                               L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), L.ptr(hd[5].detach()), O,
                                               int(softplus[i]), L.ptr(out), H * W, M, _s()), 'head_tail_fwd')
@@ -728,6 +748,8 @@ class HeadGroupFn(torch.autograd.Function):
             if dout is None:
                 dout = torch.zeros_like(outs[i])
             dout = dout.contiguous().float()
+            if L.PROFILE.active:
+                L.PROFILE.note(f'head_tail_bwd rows{M} inner{inner} O{O}', 0.0, M * (2 * slot * conv.element_size() + 8 * O))
             L.check(L.LIB.vkocr_head_tail_bwd(_tag(dt), L.ptr(conv[:, i * slot:(i + 1) * slot]), conv.stride(3), inner, slot,
                                               L.ptr(hd[2].detach()), L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), O,
                                               int(softplus[i]), L.ptr(outs[i]), L.ptr(dout), H * W, M,
