@@ -19,7 +19,8 @@ def pack_w(w_oihw, c_pad, dtype):
     return p.reshape(n, kh * kw * c_pad).contiguous()
 
 
-def gemm_nt(x_nhwc, w_oihw, bias=None, act=0, backend=0, res=None, col_scale=None, want_pre=False):
+def gemm_nt(x_nhwc, w_oihw, bias=None, act=0, backend=0, res=None, col_scale=None, want_pre=False, aux=None, row_scale=None,
+            rows_per_group=1):
     B, H, W, C = x_nhwc.shape
     n, c, ks, _ = w_oihw.shape
     c_pad = (C + 63) // 64 * 64
@@ -29,8 +30,10 @@ def gemm_nt(x_nhwc, w_oihw, bias=None, act=0, backend=0, res=None, col_scale=Non
     g = L.ConvGeom(B, H, W, ks, C, x_nhwc.stride(2), c_pad)
     ep = L.Epilogue(out.data_ptr(), n, 0, 0, pre.data_ptr() if want_pre else None, n,
                     bias.data_ptr() if bias is not None else None, act,
-                    col_scale.data_ptr() if col_scale is not None else None, None, 1,
-                    res.data_ptr() if res is not None else None, n)
+                    col_scale.data_ptr() if col_scale is not None else None,
+                    row_scale.data_ptr() if row_scale is not None else None, rows_per_group,
+                    res.data_ptr() if res is not None else None, n,
+                    aux.data_ptr() if aux is not None else None, n, 0, 0, 0)
     L.check(L.LIB.vkocr_gemm_nt(L.dtype_tag(x_nhwc.dtype), backend, L.ptr(x_nhwc), ctypes.byref(g), L.ptr(wp), n,
                                 ctypes.byref(ep), L.stream_ptr()), 'gemm_nt')
     return out, pre
@@ -41,7 +44,7 @@ def gemm_tn(p_nhwc, q_nhwc, ks, backend=0):
     J = q_nhwc.shape[3]
     out = torch.zeros(ks * ks, I, J, device=dev, dtype=torch.float32)
     g = L.ConvGeom(B, H, W, ks, I, p_nhwc.stride(2), 0)
-    ep = L.Epilogue(out.data_ptr(), J, 1, 1, None, 0, None, 0, None, None, 1, None, 0)
+    ep = L.Epilogue(out.data_ptr(), J, 1, 1, None, 0, None, 0, None, None, 1, None, 0, None, 0, I * J, J, 1)
     L.check(L.LIB.vkocr_gemm_tn(L.dtype_tag(p_nhwc.dtype), backend, L.ptr(p_nhwc), ctypes.byref(g), L.ptr(q_nhwc), J,
                                 q_nhwc.stride(2), ctypes.byref(ep), L.stream_ptr()), 'gemm_tn')
     return out
@@ -69,7 +72,8 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     allok = True
-    cases_plain = [(1000, 96, 384), (4096, 384, 96), (777, 48, 96), (12800, 768, 3072), (513, 192, 193), (300, 1152, 96)]
+    cases_plain = [(1000, 96, 384), (4096, 384, 96), (777, 48, 96), (12800, 768, 3072), (513, 192, 193), (300, 1152, 96),
+                   (70, 96, 1152), (1000, 192, 832), (333, 64, 1200), (5000, 384, 1536)]
     for backend, dt in ((1, torch.float32), (1, torch.bfloat16), (0, torch.bfloat16)):
         tol = 1e-5 if dt == torch.float32 else 6e-3
         tag = f'{"simt" if backend else "tc"}/{str(dt)[6:]}'
@@ -93,8 +97,17 @@ def main():
         cs = torch.rand(N, device=dev)
         out, _ = gemm_nt(x, w, b, backend=backend, res=res, col_scale=cs)
         allok &= report(f'nt scale+res {tag}', out, refpre * cs + res.float(), tol)
+        rsc = torch.rand(M // 256, device=dev)
+        out, _ = gemm_nt(x, w, b, backend=backend, res=res, col_scale=cs, row_scale=rsc, rows_per_group=256)
+        allok &= report(f'nt scale+rowscale+res {tag}', out, refpre * cs * rsc.repeat_interleave(256)[None, None, :, None] + res.float(), tol)
+        aux = torch.randn(1, 1, M, N, device=dev).to(dt)
+        out, _ = gemm_nt(x, w, None, act=2, backend=backend, aux=aux)
+        a32 = aux.float().requires_grad_(True)
+        F.gelu(a32).sum().backward()
+        allok &= report(f'nt gelu-grad {tag}', out, ref_conv(x, w.to(dt), None) * a32.grad, tol)
         # 3x3 conv
-        for (B, H, W, C, N) in [(2, 20, 20, 1152, 96), (2, 40, 40, 96, 96), (1, 64, 48, 384, 193), (2, 33, 17, 64, 32)]:
+        for (B, H, W, C, N) in [(2, 20, 20, 1152, 96), (2, 40, 40, 96, 96), (1, 64, 48, 384, 193), (2, 33, 17, 64, 32),
+                                 (1, 40, 56, 128, 832), (2, 5, 7, 96, 1152), (1, 20, 28, 832, 384)]:
             x = torch.randn(B, H, W, C, device=dev).to(dt)
             w = torch.randn(N, C, 3, 3, device=dev) / (9 * C) ** 0.5
             b = torch.randn(N, device=dev)

@@ -22,7 +22,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements in one 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int MAX_SMEM = 200 * 1024;
+constexpr int MAX_SMEM = 192 * 1024;  // operand stages
+constexpr int EPI_TILE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B staging tile for TMA stores (SWIZZLE_128B)
 constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int TMEM_COLS = 512;
@@ -40,6 +41,8 @@ struct TcParams {
     int splits;              // TN: split of the pixel-tile range
     int num_stages;
     int stage_bytes;
+    int tma_store;           // NT: outputs leave through shared memory + TMA stores (aligned bf16 outputs)
+    int M;                   // NT plain GEMM: number of rows
     long long units;
     VkocrEpilogue ep;
 };
@@ -94,6 +97,40 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void unpack8(uint4 raw, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = __bfloat1622float2(h[i]);
+        f[2 * i] = v.x;
+        f[2 * i + 1] = v.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return raw;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -135,11 +172,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo1
 // ------------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapPre,
                      const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.num_stages;
-    const uint32_t bar_base = smem_base + (uint32_t)S * (uint32_t)p.stage_bytes;
+    const uint32_t epi_base = smem_base + (uint32_t)S * (uint32_t)p.stage_bytes;   // 1024-byte aligned (stage sizes are)
+    const uint32_t bar_base = epi_base + (uint32_t)(EPI_WARPS * EPI_TILE_BYTES);
     // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base address word
     auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
@@ -153,6 +192,10 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        if (p.tma_store) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapOut) : "memory");
+            if (p.ep.out_pre) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapPre) : "memory");
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
@@ -320,6 +363,149 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
             const bool vec_ok = (p.mode == 0) && (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
                                 (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0);
+            if (p.tma_store) {
+                // ---- fast path: each lane finishes its row in registers, the warp's 32 x 64 tile is staged in shared memory
+                // (128-byte swizzle, conflict-free) and leaves as ONE TMA store: full 128-byte lines per row, rows/columns
+                // outside the tensor clipped by the TMA unit.  (Per-lane 16-byte global stores of row-strided data cap
+                // near 1.2 TB/s per chip.)
+                const uint32_t wb = epi_base + (uint32_t)(warp - 4) * (uint32_t)EPI_TILE_BYTES;
+                const uint32_t my_row = wb + (uint32_t)lane * 128u;
+                const uint32_t sw = (uint32_t)(lane & 7);
+                const int r0 = q * 32;
+                const int cx = t.x0 + r0 % p.BW, cy = t.y0 + r0 / p.BW;
+                const int pairs = (BN + 63) / 64;
+                const __nv_bfloat16* esrc = ep.residual ? reinterpret_cast<const __nv_bfloat16*>(ep.residual)
+                                                        : (ep.act == 2 ? reinterpret_cast<const __nv_bfloat16*>(ep.aux) : nullptr);
+                const long long eld = ep.residual ? ep.ld_res : ep.ld_aux;
+                const float rs = (ep.row_scale && row_ok) ? __ldg(ep.row_scale + (row / ep.rows_per_group)) : 1.f;
+                for (int pp = cpart; pp < pairs; pp += EPI_WARPS / 4) {
+                    const int cb = pp * 64;
+                    const int nb = t.n0 + cb;
+                    if (nb >= p.N) break;
+                    // A 64-column store that would run past this tile's BN columns into the NEXT tile's columns (BN not a
+                    // multiple of 64, e.g. 208 or 240) must not go through TMA: it would race with that tile's owner.  The
+                    // few valid columns of such a partial pair leave through per-lane 16-byte stores instead.
+                    const bool use_tma = (cb + 64 <= BN) || (t.n0 + BN >= p.N);
+                    uint4 extra[8];
+                    if (esrc) {
+                        if (p.ks == 1 && p.batch == 1 && p.H == 1) {
+                            // rows of a plain GEMM are consecutive: coalesced 128-byte row reads, transposed through the tile
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int rr = 4 * i + (lane >> 3);
+                                const int seg = lane & 7;
+                                const long long m = (long long)t.x0 + r0 + rr;
+                                const int col = nb + seg * 8;
+                                uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                                if (m < p.M && col < p.N) val = __ldg(reinterpret_cast<const uint4*>(esrc + m * eld + col));
+                                sts128(wb + (uint32_t)rr * 128u + (((uint32_t)seg ^ (uint32_t)(rr & 7)) << 4), val);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) extra[j] = lds128(my_row + (((uint32_t)j ^ sw) << 4));
+                            __syncwarp();
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int col = nb + j * 8;
+                                extra[j] = (row_ok && col < p.N) ? __ldg(reinterpret_cast<const uint4*>(esrc + row * eld + col))
+                                                                : make_uint4(0u, 0u, 0u, 0u);
+                            }
+                        }
+                    }
+                    const int npass = ep.out_pre ? 2 : 1;
+                    for (int pass = 0; pass < npass; ++pass) {
+                        const bool pre = ep.out_pre && pass == 0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c0 = cb + 32 * h;
+                            float v[32];
+                            if (c0 < BN) {
+                                uint32_t acc[32];
+                                tc_ld32(taddr + (uint32_t)c0, acc);
+                                const int nbase = t.n0 + c0;
+                                const bool full = nbase + 32 <= p.N;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                                if (ep.bias) {
+                                    if (full) {
+#pragma unroll
+                                        for (int j = 0; j < 32; j += 4) {
+                                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nbase + j));
+                                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) v[j] += (nbase + j < p.N) ? __ldg(ep.bias + nbase + j) : 0.f;
+                                    }
+                                }
+                                if (!pre) {
+                                    if (ep.act == 1) {
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
+                                    } else if (ep.act == 2) {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            float f[8];
+                                            unpack8(extra[4 * h + j], f);
+#pragma unroll
+                                            for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
+                                        }
+                                    }
+                                    if (ep.col_scale) {
+                                        if (full) {
+#pragma unroll
+                                            for (int j = 0; j < 32; j += 4) {
+                                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nbase + j));
+                                                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+                                            }
+                                        } else {
+#pragma unroll
+                                            for (int j = 0; j < 32; ++j) v[j] *= (nbase + j < p.N) ? __ldg(ep.col_scale + nbase + j) : 0.f;
+                                        }
+                                    }
+                                    if (ep.row_scale) {
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) v[j] *= rs;
+                                    }
+                                    if (ep.residual) {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            float f[8];
+                                            unpack8(extra[4 * h + j], f);
+#pragma unroll
+                                            for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
+                                        }
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                            }
+                            if (use_tma) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)(4 * h + j) ^ sw) << 4), pack8(v + 8 * j));
+                            } else if (row_ok && c0 < BN) {
+                                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(pre ? ep.out_pre : ep.out) +
+                                                   row * (pre ? ep.ld_pre : ep.ldo) + t.n0 + c0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (c0 + 8 * j < BN && t.n0 + c0 + 8 * j < p.N) *reinterpret_cast<uint4*>(o + 8 * j) = pack8(v + 8 * j);
+                            }
+                        }
+                        if (use_tma) {
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_4d(pre ? &mapPre : &mapOut, wb, nb, cx, cy, t.b);
+                                bulk_commit();
+                                bulk_wait_read0();     // the tile may be overwritten once the TMA unit has read it
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            } else
             for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
                 uint32_t acc[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), acc);
@@ -414,6 +600,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
     }
 
+    if (warp >= 4 && lane == 0 && p.tma_store) bulk_wait0();   // all TMA stores of this warp have completed
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -489,9 +676,10 @@ void pick_box(int W, int H, int pixels, int* bw_out, int* bh_out) {
     }
 }
 
-int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapOut, const CUtensorMap& mapPre, TcParams& p,
+           cudaStream_t stream) {
     static bool attr_set = false;
-    const int smem = MAX_SMEM + 1024 + 256;
+    const int smem = MAX_SMEM + 1024 + EPI_WARPS * EPI_TILE_BYTES + 256;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(vkocr_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
@@ -502,7 +690,7 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaSt
     const long long sms = vkocr_sm_count();
     const int grid = (int)(p.units < sms ? p.units : sms);
     if (grid <= 0) return VKOCR_OK;
-    vkocr_gemm_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, p);
+    vkocr_gemm_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, mapOut, mapPre, p);
     VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
     return VKOCR_OK;
 }
@@ -527,6 +715,9 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     // N tile: multiple of 16, <= 256, splitting N as evenly as possible
     const int n_tiles = vk_cdiv(N, 256);
     p.BN = ((vk_cdiv(N, n_tiles) + 15) / 16) * 16;
+    // prefer a multiple of 64 (whole 128-byte TMA store rows) when it does not add padded columns: 1152 -> 6 x 192
+    for (int cand = 256; cand >= 128 && n_tiles > 1; cand -= 64)
+        if ((long long)vk_cdiv(N, cand) * cand <= (long long)vk_cdiv(N, p.BN) * p.BN) { p.BN = cand; break; }
     p.n_tiles = vk_cdiv(N, p.BN);
     p.stage_bytes = A_BYTES + p.BN * 128;
     p.units = (long long)p.batch * p.tiles_y * p.tiles_x * p.n_tiles;
@@ -541,7 +732,24 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     VK_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, VKOCR_BAD_ALIGN, "packed weight not 16-byte aligned");
     rc = encode_map(&mapB, w_packed, 2, dims, str, box);
     if (rc) return rc;
-    return launch(mapA, mapB, p, stream);
+    // outputs through TMA stores when they are plain 16-byte-aligned bf16 matrices (every hot-path call); otherwise the
+    // generic per-element epilogue handles them
+    CUtensorMap mapOut = mapA, mapPre = mapA;
+    p.M = g->W;
+    auto aligned = [](const void* ptr, long long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld & 7) == 0; };
+    p.tma_store = !ep->out_f32 && !ep->accumulate && (N % 8 == 0) && aligned(ep->out, ep->ldo) &&
+                  (!ep->out_pre || aligned(ep->out_pre, ep->ld_pre)) && (!ep->residual || aligned(ep->residual, ep->ld_res)) &&
+                  (ep->act != 2 || aligned(ep->aux, ep->ld_aux));
+    if (p.tma_store) {
+        const int bw2 = p.BW < 32 ? p.BW : 32;
+        rc = encode_nhwc(&mapOut, ep->out, N, g->W, g->H, g->batch, ep->ldo, bw2, 32 / bw2);
+        if (rc) return rc;
+        if (ep->out_pre) {
+            rc = encode_nhwc(&mapPre, ep->out_pre, N, g->W, g->H, g->batch, ep->ld_pre, bw2, 32 / bw2);
+            if (rc) return rc;
+        }
+    }
+    return launch(mapA, mapB, mapOut, mapPre, p, stream);
 }
 
 // TN: G[tap,i,j] += sum_pix P[pix,i] * Q[pix+off(tap), j]   (bf16 in, fp32 out accumulated with red.add)
@@ -578,5 +786,6 @@ int vkocr_gemm_tc_tn(const void* pmat, const VkocrConvGeom* g, const void* qmat,
     if (rc) return rc;
     rc = encode_nhwc(&mapB, qmat, J, g->W, g->H, g->batch, ld_q, p.BW, p.BH);
     if (rc) return rc;
-    return launch(mapA, mapB, p, stream);
+    p.tma_store = 0;
+    return launch(mapA, mapB, mapA, mapA, p, stream);
 }
