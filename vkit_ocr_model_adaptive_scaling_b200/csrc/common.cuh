@@ -152,15 +152,25 @@ __device__ __forceinline__ float vk_block_sum(float v, float* scratch) {
 
 // ---- math ------------------------------------------------------------------------------------------
 // Exact (erf) GELU of the reference (helper.py:100-101) and its derivative.  erf is evaluated with Abramowitz & Stegun
-// 7.1.26 (absolute error <= 1.5e-7, below fp32 round-off of the surrounding math): branch-free, one MUFU.RCP, one
-// MUFU.EX2 and five FMAs instead of libdevice erff's ~25-instruction branchy polynomial — these kernels evaluate GELU
-// on billions of elements per step and are instruction-bound on it.  exp(-x^2/2), needed for erf(x/sqrt 2), is also the
-// Gaussian density of the derivative, so gelu and gelu' share all of the work.  The lower tail is computed directly
-// (0.5*(1-erf|u|) = 0.5*poly*e), not as 1 - erf, so it keeps its relative accuracy.
+// 7.1.26 (absolute error <= 1.5e-7, below fp32 round-off of the surrounding math): straight-line code, one MUFU.RCP
+// (refined by one Newton step -- __frcp_rn / "1.f / x" compile to a MUFU plus a conditional slow-path CALL per element,
+// which serialises these instruction-bound loops), one MUFU.EX2 and a handful of FMAs.  exp(-x^2/2), needed for
+// erf(x/sqrt 2), is also the Gaussian density of the derivative, so gelu and gelu' share all of the work.  The lower
+// tail is computed directly (0.5*(1-erf|u|) = 0.5*poly*e), not as 1 - erf, so it keeps its relative accuracy.
+__device__ __forceinline__ float vk_rcp(float d) {   // d in [1, 2^60]: approx reciprocal + one Newton-Raphson step
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(d));
+    return t * fmaf(-d, t, 2.f);
+}
+__device__ __forceinline__ float vk_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void vk_gelu_parts(float x, float* cdf, float* pdf) {
-    const float u = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.f));
-    const float e = __expf(-u * u);
+    const float u = fminf(fabsf(x) * 0.70710678118654752440f, 12.f);   // erfc(12) == 0 in fp32; keeps inf out of the rcp
+    const float t = vk_rcp(fmaf(0.3275911f, u, 1.f));
+    const float e = vk_ex2(u * u * -1.44269504088896340736f);           // exp(-u^2)
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
@@ -186,7 +196,7 @@ __device__ __forceinline__ void vk_gelu_both(float x, float* g, float* dg) {
     *g = x * cdf;
     *dg = fmaf(x, pdf, cdf);
 }
-__device__ __forceinline__ float vk_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float vk_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }   // per-pixel maps only (IEEE division)
 __device__ __forceinline__ float vk_softplus(float x) {  // beta 1, threshold 20 (torch.nn.Softplus)
     return x > 20.f ? x : log1pf(expf(x));
 }

@@ -16,6 +16,7 @@
 //   TN  G[tap,i,j] = sum_pix P[pix,i] * Q[pix+off(tap), j]               A,B MN-major, split over pixels, fp32 red.add
 #include "gemm_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -41,6 +42,7 @@ struct TcParams {
     int splits;              // TN: split of the pixel-tile range
     int num_stages;
     int stage_bytes;
+    int skip_tma;            // debug: producers arrive without loading (timing experiments)
     int tma_store;           // NT: outputs leave through shared memory + TMA stores (aligned bf16 outputs)
     int M;                   // NT plain GEMM: number of rows
     long long units;
@@ -260,38 +262,86 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         return t;
     };
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 3 && lane == 0 && p.mode == 1) {
+        // ================================================================ second TMA producer (TN): the Q operand boxes.
+        // A cp.async.bulk.tensor costs its issuing thread on the order of 100 cycles; with five boxes per k-block a single
+        // producer thread cannot keep up with the MMAs, so the P and Q operands are issued from two threads.  Both wait on
+        // the stage's empty barrier; warp 0 performs the full barrier's arrival (expect_tx of the whole stage).
+        int s = 0;
+        uint32_t ph = 0;
+        const int nb = (BN + 63) / 64;
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit t = decode(u);
+            const int dy = t.tap / p.ks - half, dx = t.tap % p.ks - half;
+            int kt = t.kt_begin;
+            int tx = kt % p.tiles_x;
+            kt /= p.tiles_x;
+            int ty = kt % p.tiles_y;
+            int b = kt / p.tiles_y;
+            for (int kb = 0; kb < t.num_kb; ++kb) {
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const uint32_t sb = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes + A_BYTES;
+                const int x0 = tx * p.BW + dx, y0 = ty * p.BH + dy;
+                if (!p.skip_tma)
+                    for (int g = 0; g < nb; ++g) tma_load_4d(sb + (uint32_t)g * 8192u, &mapB, full_bar(s), t.n0 + g * 64, x0, y0, b);
+                if (++tx == p.tiles_x) {
+                    tx = 0;
+                    if (++ty == p.tiles_y) { ty = 0; ++b; }
+                }
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 0 && lane == 0) {
         // ================================================================ TMA producer
         int s = 0;
         uint32_t ph = 0;
-        const uint32_t tx_bytes = (p.mode == 0) ? (uint32_t)(A_BYTES + BN * 128) : (uint32_t)(2 * 8192 + (BN / 64) * 8192);
+        const uint32_t tx_bytes = (p.mode == 0) ? (uint32_t)(A_BYTES + BN * 128) : (uint32_t)(2 * 8192 + ((BN + 63) / 64) * 8192);
+        // All per-k-block coordinates are tracked incrementally: integer divisions here sit on the critical path of a
+        // single thread (a handful of dependent divides per k-block costs more than the k-block's MMAs).
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit t = decode(u);
-            for (int kb = 0; kb < t.num_kb; ++kb) {
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
-                const uint32_t sb = sa + A_BYTES;
-                mbar_expect_tx(full_bar(s), tx_bytes);
-                if (p.mode == 0) {
-                    const int tap = kb / p.kb_per_tap;
-                    const int c0 = (kb - tap * p.kb_per_tap) * BK;
-                    const int dy = tap / p.ks - half, dx = tap % p.ks - half;
-                    tma_load_4d(sa, &mapA, full_bar(s), c0, t.x0 + dx, t.y0 + dy, t.b);
-                    tma_load_2d(sb, &mapB, full_bar(s), kb * BK, t.n0);
-                } else {
-                    int kt = t.kt_begin + kb;
-                    const int tx = kt % p.tiles_x;
-                    kt /= p.tiles_x;
-                    const int ty = kt % p.tiles_y;
-                    const int b = kt / p.tiles_y;
-                    const int dy = t.tap / p.ks - half, dx = t.tap % p.ks - half;
-                    const int x0 = tx * p.BW, y0 = ty * p.BH;
-                    tma_load_4d(sa, &mapA, full_bar(s), t.i0, x0, y0, b);
-                    tma_load_4d(sa + 8192, &mapA, full_bar(s), t.i0 + 64, x0, y0, b);
-                    for (int g = 0; g < BN / 64; ++g)
-                        tma_load_4d(sb + (uint32_t)g * 8192u, &mapB, full_bar(s), t.n0 + g * 64, x0 + dx, y0 + dy, b);
+            if (p.mode == 0) {
+                int c0 = 0, dy = -half, dx = -half;
+                for (int kb = 0; kb < t.num_kb; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                    if (p.skip_tma) {
+                        mbar_arrive(full_bar(s));
+                    } else {
+                        mbar_expect_tx(full_bar(s), tx_bytes);
+                        tma_load_4d(sa, &mapA, full_bar(s), c0, t.x0 + dx, t.y0 + dy, t.b);
+                        tma_load_2d(sa + A_BYTES, &mapB, full_bar(s), kb * BK, t.n0);
+                    }
+                    c0 += BK;
+                    if (c0 >= p.kb_per_tap * BK) {
+                        c0 = 0;
+                        if (++dx > half) { dx = -half; ++dy; }
+                    }
+                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
-                if (++s == S) { s = 0; ph ^= 1u; }
+            } else {
+                int kt = t.kt_begin;
+                int tx = kt % p.tiles_x;
+                kt /= p.tiles_x;
+                int ty = kt % p.tiles_y;
+                int b = kt / p.tiles_y;
+                for (int kb = 0; kb < t.num_kb; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                    const int x0 = tx * p.BW, y0 = ty * p.BH;
+                    if (p.skip_tma) {
+                        mbar_arrive(full_bar(s));
+                    } else {
+                        mbar_expect_tx(full_bar(s), tx_bytes);
+                        tma_load_4d(sa, &mapA, full_bar(s), t.i0, x0, y0, b);
+                        tma_load_4d(sa + 8192, &mapA, full_bar(s), t.i0 + 64, x0, y0, b);
+                    }
+                    if (++tx == p.tiles_x) {
+                        tx = 0;
+                        if (++ty == p.tiles_y) { ty = 0; ++b; }
+                    }
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -301,8 +351,11 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         int as = 0;
         uint32_t aph = 0;
         const uint32_t major = (p.mode == 0) ? 0u : 1u;
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (major << 15) | (major << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (major << 15) | (major << 16) |
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const int dbg_major = p.skip_tma >> 1;   // debug (timing only, garbage data): bit0 -> A K-major, bit1 -> B K-major
+        if (dbg_major & 1) idesc &= ~(1u << 15);
+        if (dbg_major & 2) idesc &= ~(1u << 16);
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit t = decode(u);
             if (t.num_kb == 0) continue;
@@ -324,11 +377,12 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 } else {
                     // MN-major SWIZZLE_128B: 64-channel groups 8192 B apart (LBO), 8-pixel atoms 1024 B apart (SBO);
                     // one K=16 slice = 2 atoms = 2048 B.
-                    const uint64_t ad = make_smem_desc(sa, 512, 64);
-                    const uint64_t bd = make_smem_desc(sb, 512, 64);
+                    const uint64_t ad = (dbg_major & 1) ? make_smem_desc(sa, 1, 64) : make_smem_desc(sa, 512, 64);
+                    const uint64_t bd = (dbg_major & 2) ? make_smem_desc(sb, 1, 64) : make_smem_desc(sb, 512, 64);
+                    const uint64_t ka = (dbg_major & 1) ? 2 : 128, kbs = (dbg_major & 2) ? 2 : 128;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        tc_mma(tmem_d, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kb | k) ? 1u : 0u);
+                        tc_mma(tmem_d, ad + ka * (uint64_t)k, bd + kbs * (uint64_t)k, idesc, (kb | k) ? 1u : 0u);
                 }
                 tc_commit(empty_bar(s));
                 if (++s == S) { s = 0; ph ^= 1u; }
@@ -687,6 +741,9 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& 
     }
     p.num_stages = MAX_SMEM / p.stage_bytes;
     if (p.num_stages > 8) p.num_stages = 8;
+    if (p.mode == 1)
+        if (const char* e = getenv("VKOCR_TN_STAGES")) p.num_stages = atoi(e) < p.num_stages ? atoi(e) : p.num_stages;
+    if (const char* e = getenv("VKOCR_DEBUG_SKIP_TMA")) p.skip_tma = atoi(e);
     const long long sms = vkocr_sm_count();
     const int grid = (int)(p.units < sms ? p.units : sms);
     if (grid <= 0) return VKOCR_OK;
@@ -753,36 +810,83 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
 }
 
 // TN: G[tap,i,j] += sum_pix P[pix,i] * Q[pix+off(tap), j]   (bf16 in, fp32 out accumulated with red.add)
-// ep->out must be fp32 [ks*ks*I, ldo] and is accumulated into (caller zeroes it).
+// ep->out must be fp32 and is accumulated into at the tn_s_* strides (caller zeroes it).
+//
+// Either operand may take the M (128-row tile) side of the MMA: G[tap,i,j] = sum_pix Q[pix,j] * P[pix-off(tap),i] is the
+// same contraction with the roles swapped and the tap mirrored.  A tcgen05.mma costs about the same for every N <= ~192,
+// so the orientation with the fewest (tile x instruction) products wins, e.g. I=832, J=384: 7x2 tiles of 128x192 (with
+// 7 % row padding) versus 3x4 tiles of 128x208 (no padding).
+namespace {
+int tn_tile_n(int J, int* n_tiles) {
+    const int nt = vk_cdiv(J, 256);
+    const int bn = ((vk_cdiv(J, nt) + 15) / 16) * 16;
+    *n_tiles = vk_cdiv(J, bn);
+    return bn;
+}
+long long tn_cost(int I, int J) {
+    int nt;
+    const int bn = tn_tile_n(J, &nt);
+    return (long long)vk_cdiv(I, BM) * nt * (bn > 176 ? bn : 176);
+}
+}  // namespace
+
 int vkocr_gemm_tc_tn(const void* pmat, const VkocrConvGeom* g, const void* qmat, int J, long long ld_q,
-                     const VkocrEpilogue* ep, cudaStream_t stream) {
+                     const VkocrEpilogue* ep_in, cudaStream_t stream) {
     VK_REQUIRE(g->ks == 1 || g->ks == 3 || g->ks == 5, VKOCR_BAD_SHAPE, "gemm_tc_tn: kernel size %d", g->ks);
-    VK_REQUIRE(ep->out_f32 && ep->accumulate, VKOCR_BAD_ARGUMENT, "gemm_tc_tn: output must be fp32 accumulate");
+    VK_REQUIRE(ep_in->out_f32 && ep_in->accumulate, VKOCR_BAD_ARGUMENT, "gemm_tc_tn: output must be fp32 accumulate");
     if ((long long)g->batch * g->H * g->W == 0) return VKOCR_OK;
+    int I = g->C;
+    long long ld_p = g->ld_x;
+    VkocrEpilogue ep = *ep_in;
+    // measured on B200 (I=832, J=384, 3x3): both orientations run within 2 % of each other once the split fills whole
+    // waves, so the swap is only taken when it removes at least a fifth of the tile work
+    bool swap = tn_cost(J, I) * 5 < tn_cost(I, J) * 4;
+    if (const char* e = getenv("VKOCR_TN_SWAP")) swap = atoi(e) != 0;
+    if (swap) {
+        const int taps = g->ks * g->ks;
+        ep.out = reinterpret_cast<float*>(ep.out) + (long long)(taps - 1) * ep.tn_s_tap;
+        ep.tn_s_tap = -ep.tn_s_tap;
+        const long long t = ep.tn_s_i;
+        ep.tn_s_i = ep.tn_s_j;
+        ep.tn_s_j = t;
+        const void* tp = pmat; pmat = qmat; qmat = tp;
+        const int ti = I; I = J; J = ti;
+        const long long tl = ld_p; ld_p = ld_q; ld_q = tl;
+    }
     TcParams p{};
     p.mode = 1;
     p.batch = g->batch; p.H = g->H; p.W = g->W; p.ks = g->ks;
     pick_box(g->W, g->H, 64, &p.BW, &p.BH);
     p.tiles_x = vk_cdiv(g->W, p.BW);
     p.tiles_y = vk_cdiv(g->H, p.BH);
-    p.I = g->C;
+    p.I = I;
     p.i_tiles = vk_cdiv(p.I, BM);
     p.N = J;
-    const int n_tiles = vk_cdiv(J, 256);
-    p.BN = ((vk_cdiv(J, n_tiles) + 63) / 64) * 64;
-    p.n_tiles = vk_cdiv(J, p.BN);
-    p.stage_bytes = A_BYTES + p.BN * 128;
+    p.BN = tn_tile_n(J, &p.n_tiles);
+    if (const char* e = getenv("VKOCR_TN_BN")) { p.BN = atoi(e); p.n_tiles = vk_cdiv(J, p.BN); }
+    p.stage_bytes = A_BYTES + vk_cdiv(p.BN, 64) * 8192;   // Q arrives in 64-channel boxes
     const long long out_tiles = (long long)p.ks * p.ks * p.i_tiles * p.n_tiles;
     const long long pix_tiles = (long long)p.batch * p.tiles_y * p.tiles_x;
-    // split the pixel range so that the machine is filled ~2x, keeping >= 8 k-blocks per unit
-    long long splits = (2LL * vkocr_sm_count() + out_tiles - 1) / out_tiles;
-    if (splits > pix_tiles / 8) splits = pix_tiles / 8;
-    if (splits < 1) splits = 1;
+    // Split the pixel range so that the units fill whole waves of the persistent grid: every unit costs the same, so the
+    // kernel time is ceil(units / SMs) unit times -- 378 units on 148 SMs would idle 15 % of the machine in its last wave.
+    // Candidates: 1..8 waves' worth of splits, keeping >= 8 k-blocks per unit; highest wave efficiency wins, ties go to
+    // the fewest splits (fewest fp32 atomics).
+    const long long sms = vkocr_sm_count();
+    long long max_splits = pix_tiles / 8;
+    if (max_splits < 1) max_splits = 1;
+    long long splits = 1;
+    double best_eff = -1.0;
+    for (long long cand = 1; cand <= max_splits && cand * out_tiles <= 8 * sms + out_tiles; ++cand) {
+        const long long units = cand * out_tiles;
+        const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
+        if (eff > best_eff + 1e-9) { best_eff = eff; splits = cand; }
+    }
+    if (const char* e = getenv("VKOCR_TN_SPLITS")) splits = atoi(e);
     p.splits = (int)splits;
     p.units = out_tiles * splits;
-    p.ep = *ep;
+    p.ep = ep;
     CUtensorMap mapA, mapB;
-    int rc = encode_nhwc(&mapA, pmat, g->C, g->W, g->H, g->batch, g->ld_x, p.BW, p.BH);
+    int rc = encode_nhwc(&mapA, pmat, I, g->W, g->H, g->batch, ld_p, p.BW, p.BH);
     if (rc) return rc;
     rc = encode_nhwc(&mapB, qmat, J, g->W, g->H, g->batch, ld_q, p.BW, p.BH);
     if (rc) return rc;
