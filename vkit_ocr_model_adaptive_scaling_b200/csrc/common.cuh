@@ -126,6 +126,18 @@ template <typename T> struct VkScalar {
     __device__ __forceinline__ void pack(const float* f) { raw = vk_from_f32<T>(f[0]); }
 };
 
+// ---- per-thread asynchronous global -> shared copies (LDGSTS) ---------------------------------------------------
+// A thread that streams rows keeps a ring of its next rows' vectors in shared memory: the copies are in flight while it
+// computes, and it reads back only what it copied itself (no cross-thread synchronisation).  One commit group per row.
+__device__ __forceinline__ void vk_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void vk_cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void vk_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void vk_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- reductions ---------------------------------------------------------------------------------
 __device__ __forceinline__ float vk_warp_sum(float v) {
 #pragma unroll
@@ -157,26 +169,27 @@ __device__ __forceinline__ float vk_block_sum(float v, float* scratch) {
 // which serialises these instruction-bound loops), one MUFU.EX2 and a handful of FMAs.  exp(-x^2/2), needed for
 // erf(x/sqrt 2), is also the Gaussian density of the derivative, so gelu and gelu' share all of the work.  The lower
 // tail is computed directly (0.5*(1-erf|u|) = 0.5*poly*e), not as 1 - erf, so it keeps its relative accuracy.
-__device__ __forceinline__ float vk_rcp(float d) {   // d in [1, 2^60]: approx reciprocal + one Newton-Raphson step
+__device__ __forceinline__ float vk_rcp(float d) {   // MUFU.RCP: relative error ~1 ulp, no slow path
     float t;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(d));
-    return t * fmaf(-d, t, 2.f);
+    return t;
 }
 __device__ __forceinline__ float vk_ex2(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// 16 instructions (18 with the density): the 0.5 of Phi = 0.5 erfc(.) and the 1/sqrt(2) of the argument are folded into
+// the constants; +-inf give exactly 0 / 1.
 __device__ __forceinline__ void vk_gelu_parts(float x, float* cdf, float* pdf) {
-    const float u = fminf(fabsf(x) * 0.70710678118654752440f, 12.f);   // erfc(12) == 0 in fp32; keeps inf out of the rcp
-    const float t = vk_rcp(fmaf(0.3275911f, u, 1.f));
-    const float e = vk_ex2(u * u * -1.44269504088896340736f);           // exp(-u^2)
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float half_tail = 0.5f * poly * t * e;            // 0.5 * erfc(|x| / sqrt 2)
-    *cdf = x >= 0.f ? 1.f - half_tail : half_tail;
+    const float t = vk_rcp(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.f));
+    const float e = vk_ex2(x * x * (-0.5f * 1.44269504088896340736f));   // exp(-x^2 / 2)
+    float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    const float half_tail = poly * t * e;                   // 0.5 * erfc(|x| / sqrt 2), in [0, 0.5]
+    *cdf = 0.5f + copysignf(0.5f - half_tail, x);
     *pdf = 0.39894228040143267794f * e;
 }
 __device__ __forceinline__ float vk_gelu(float x) {

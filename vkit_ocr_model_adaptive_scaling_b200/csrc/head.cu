@@ -3,8 +3,13 @@
 // Reference: UperNextHead.forward upernext.py:233-248 / FpnHead.forward fpn.py:193-208 (step1 LN+GELU, step2 1x1),
 // nn.Softplus on the height / distance heads (adaptive_scaling.py:101,140).
 //
-// HBM-bound: one warp per pixel, each lane owns NVL 16-byte channel vectors of the slice (the slice is padded to a
-// multiple of the vector width; pad channels hold zeros and are masked out of the statistics).
+// One warp per pixel row, each lane owns NVL 16-byte channel vectors of the slice; the slice is padded to a multiple of
+// the vector width and pad channels are read as zeros.  The kernels are instruction-bound (about 40 fp32 instructions
+// per element in the backward, half of them the GELU), so everything per-row that is not per-element is kept off the
+// critical path: the per-channel parameters live in registers, the LayerNorm statistics come from ONE shuffle round of
+// shifted sums (sum (x - x0), sum (x - x0)^2: no cancellation, no second sweep), the row -> (image, pixel) split uses a
+// float reciprocal instead of a 64-bit division, and each warp works on two rows at a time for memory- and
+// instruction-level parallelism.
 // Backward recomputes LN/GELU from the saved conv output, writes d(conv output) and accumulates all parameter
 // gradients (LN gamma/beta, 1x1 weight/bias, conv bias) from per-lane register partials.
 #include "common.cuh"
@@ -15,15 +20,94 @@ constexpr int HT_THREADS = 256;
 constexpr int HT_WARPS = HT_THREADS / 32;
 constexpr float LN_EPS = 1e-6f;
 
+__device__ __forceinline__ float2 warp_sum2(float a, float b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    return make_float2(a, b);
+}
+
+// row -> (image, pixel) for row < 2^31 without an integer division
+__device__ __forceinline__ void split_row(unsigned row, unsigned ppi, float inv_ppi, unsigned* b, unsigned* pix) {
+    unsigned q = (unsigned)((float)row * inv_ppi);
+    long long rem = (long long)row - (long long)q * ppi;
+    if (rem < 0) { --q; rem += ppi; }
+    else if (rem >= (long long)ppi) { ++q; rem -= ppi; }
+    *b = q;
+    *pix = (unsigned)rem;
+}
+
+// Row streaming: every thread keeps its vectors of the warp's next RING rows in flight as cp.async copies into a
+// shared-memory ring (one commit group per row) and reads back only what it copied itself.  With one 416-byte row per
+// warp in flight the kernels were latency-bound at ~1 TB/s; the ring keeps RING rows per warp in flight.
+template <int NVL> struct RingDepth { static constexpr int value = NVL == 1 ? 8 : (NVL == 2 ? 4 : 2); };   // 32 KB of vectors per block
+
+template <typename T, int NVL>
+__device__ __forceinline__ void ring_issue(uint4* ring, int slot, const T* __restrict__ xr, int lane, int inner) {
+    constexpr int V = VkVec<T>::N;
+#pragma unroll
+    for (int j = 0; j < NVL; ++j) {
+        const int c = (lane + 32 * j) * V;
+        if (c < inner) vk_cp_async16(ring + (slot * NVL + j) * HT_THREADS + threadIdx.x, xr + c);
+    }
+}
+
+// The lane's channel vectors of the row in `slot` as fp32, zeros beyond `inner`.
+template <typename T, int NVL>
+__device__ __forceinline__ void ring_fetch(const uint4* ring, int slot, int lane, int inner, float (&f)[NVL][VkVec<T>::N]) {
+    constexpr int V = VkVec<T>::N;
+#pragma unroll
+    for (int j = 0; j < NVL; ++j) {
+        const int c = (lane + 32 * j) * V;
+        if (c < inner) {
+            VkVec<T> v;
+            v.raw = *reinterpret_cast<const decltype(v.raw)*>(ring + (slot * NVL + j) * HT_THREADS + threadIdx.x);
+            v.unpack(f[j]);
+            if (c + V > inner) {
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    if (c + i >= inner) f[j][i] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) f[j][i] = 0.f;
+        }
+    }
+}
+
+// mean / rstd of the `inner` real channels of a row held across the warp (pad channels hold zeros).
+template <int NVL, int V>
+__device__ __forceinline__ void row_stats(const float (&f)[NVL][V], int inner, int npad, float inv, float* mean, float* rstd) {
+    const float x0 = __shfl_sync(0xffffffffu, f[0][0], 0);
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NVL; ++j)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float d = f[j][i] - x0;
+            s += d;
+            q = fmaf(d, d, q);
+        }
+    const float2 r = warp_sum2(s, q);
+    // the zero-valued pad channels contributed (0 - x0) and (0 - x0)^2 each
+    const float ss = r.x + (float)npad * x0;
+    const float qq = r.y - (float)npad * x0 * x0;
+    const float m = ss * inv;                         // mean - x0
+    *mean = x0 + m;
+    *rstd = rsqrtf(fmaxf(fmaf(-m, m, qq * inv), 0.f) + LN_EPS);
+}
+
 template <typename T, int NVL, int O>
 __global__ void __launch_bounds__(HT_THREADS)
 head_tail_fwd_kernel(const T* __restrict__ x, long long ld_x, int inner, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ w2, const float* __restrict__ b2, int softplus,
-                     float* __restrict__ out, long long pixels_per_image, long long rows) {
+                     float* __restrict__ out, unsigned ppi, float inv_ppi, unsigned rows) {
     constexpr int V = VkVec<T>::N;
     const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * HT_WARPS + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * HT_WARPS;
+    const unsigned warp0 = blockIdx.x * HT_WARPS + (threadIdx.x >> 5);
+    const unsigned nwarps = gridDim.x * HT_WARPS;
     float gm[NVL][V], bt[NVL][V], w[O][NVL][V];
 #pragma unroll
     for (int j = 0; j < NVL; ++j)
@@ -37,35 +121,30 @@ head_tail_fwd_kernel(const T* __restrict__ x, long long ld_x, int inner, const f
             for (int o = 0; o < O; ++o) w[o][j][i] = ok ? __ldg(w2 + (long long)o * inner + c) : 0.f;
         }
     const float inv = 1.f / inner;
-    for (long long r = warp0; r < rows; r += nwarps) {
-        const T* xr = x + r * ld_x;
+    const int npad = NVL * 32 * V - inner;
+    float bias2 = (lane < O) ? __ldg(b2 + lane) : 0.f;
+    constexpr int RING = RingDepth<NVL>::value;
+    extern __shared__ uint4 ring[];   // [RING][NVL][HT_THREADS]
+#pragma unroll 1
+    for (int d = 0; d < RING; ++d) {
+        const unsigned rr = warp0 + (unsigned)d * nwarps;
+        if (rr < rows) ring_issue<T, NVL>(ring, d, x + (long long)rr * ld_x, lane, inner);
+        vk_cp_async_commit();
+    }
+    int slot = 0;
+    for (unsigned r = warp0; r < rows; r += nwarps) {
         float f[NVL][V];
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < NVL; ++j) {
-            const int c = (lane + 32 * j) * V;
-            if (c < inner) {
-                VkVec<T> v;
-                v.load(xr + c);
-                v.unpack(f[j]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < V; ++i) f[j][i] = 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < V; ++i) s += (c + i < inner) ? f[j][i] : 0.f;
+        vk_cp_async_wait<RING - 1>();
+        ring_fetch<T, NVL>(ring, slot, lane, inner, f);
+        {
+            const unsigned long long rr = (unsigned long long)r + (unsigned long long)RING * nwarps;
+            if (rr < rows) ring_issue<T, NVL>(ring, slot, x + (long long)rr * ld_x, lane, inner);
+            vk_cp_async_commit();
+            slot = (slot + 1) & (RING - 1);
         }
-        const float mean = vk_warp_sum(s) * inv;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < NVL; ++j)
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const int c = (lane + 32 * j) * V + i;
-                const float d = f[j][i] - mean;
-                q += (c < inner) ? d * d : 0.f;
-            }
-        const float rstd = rsqrtf(vk_warp_sum(q) * inv + LN_EPS);
+        float mean, rstd;
+        row_stats<NVL, V>(f, inner, npad, inv, &mean, &rstd);
+        const float shift = -mean * rstd;
         float dot[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) dot[o] = 0.f;
@@ -73,9 +152,10 @@ head_tail_fwd_kernel(const T* __restrict__ x, long long ld_x, int inner, const f
         for (int j = 0; j < NVL; ++j)
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                const float g = vk_gelu((f[j][i] - mean) * rstd * gm[j][i] + bt[j][i]);
+                const float h = fmaf(f[j][i], rstd, shift);
+                const float g = vk_gelu(fmaf(h, gm[j][i], bt[j][i]));      // pad channels: gelu(0) = 0
 #pragma unroll
-                for (int o = 0; o < O; ++o) dot[o] = fmaf(g, w[o][j][i], dot[o]);   // w == 0 on pad channels
+                for (int o = 0; o < O; ++o) dot[o] = fmaf(g, w[o][j][i], dot[o]);
             }
 #pragma unroll
         for (int o = 0; o < O; ++o) dot[o] = vk_warp_sum(dot[o]);
@@ -83,43 +163,36 @@ head_tail_fwd_kernel(const T* __restrict__ x, long long ld_x, int inner, const f
             float v = 0.f;
 #pragma unroll
             for (int o = 0; o < O; ++o) v = (lane == o) ? dot[o] : v;
-            v += __ldg(b2 + lane);
+            v += bias2;
             if (softplus) v = vk_softplus(v);
-            const long long b = r / pixels_per_image, pix = r % pixels_per_image;
-            out[(b * O + lane) * pixels_per_image + pix] = v;
+            unsigned b, pix;
+            split_row(r, ppi, inv_ppi, &b, &pix);
+            out[((long long)b * O + lane) * ppi + pix] = v;
         }
     }
 }
 
 // Backward.  Per-channel gradient partials (dgamma, dbeta, conv-bias, dW2) live in registers of the lane that owns the
-// channel for all rows the warp visits; the LayerNorm / projection parameters are read from shared memory each row so
-// that the register budget allows two blocks per SM (the kernel is instruction/latency bound, not HBM bound).
+// channel for all rows the warp visits.
 template <typename T, int NVL, int O>
 __global__ void __launch_bounds__(HT_THREADS, (NVL * O <= 4) ? 2 : 1)
 head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int slice_w, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ w2, int softplus, const float* __restrict__ out,
-                     const float* __restrict__ dout, long long pixels_per_image, long long rows, T* __restrict__ dx,
+                     const float* __restrict__ dout, unsigned ppi, float inv_ppi, unsigned rows, T* __restrict__ dx,
                      long long ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw2,
                      float* __restrict__ db2, float* __restrict__ dbias) {
     constexpr int V = VkVec<T>::N;
     constexpr int CW = 32 * NVL * V;
-    extern __shared__ float sm[];
-    float* s_gm = sm;                 // [CW]
-    float* s_bt = sm + CW;            // [CW]
-    float* s_w = sm + 2 * CW;         // [O][CW]
-    float* sacc = sm + (2 + O) * CW;  // [(3 + O)][CW] + [O]
-    for (int i = threadIdx.x; i < CW; i += blockDim.x) {
-        const bool ok = i < inner;
-        s_gm[i] = ok ? gamma[i] : 0.f;
-        s_bt[i] = ok ? beta[i] : 0.f;
-#pragma unroll
-        for (int o = 0; o < O; ++o) s_w[o * CW + i] = ok ? w2[(long long)o * inner + i] : 0.f;
-    }
+    constexpr int RING = RingDepth<NVL>::value;
+    extern __shared__ uint4 ring[];   // [RING][NVL][HT_THREADS] vectors, then [RING][HT_WARPS][2 * O] upstream values, then sacc
+    float* dring = reinterpret_cast<float*>(ring + RING * NVL * HT_THREADS);
+    float* sacc = dring + RING * HT_WARPS * 2 * O;   // [(3 + O)][CW] + [O]
     for (int i = threadIdx.x; i < (3 + O) * CW + O; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * HT_WARPS + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * HT_WARPS;
+    const unsigned warp0 = blockIdx.x * HT_WARPS + (threadIdx.x >> 5);
+    const unsigned nwarps = gridDim.x * HT_WARPS;
+    float gm[NVL][V], bt[NVL][V], w[O][NVL][V];
     float ag[NVL][V], ab[NVL][V], ax[NVL][V], aw[O][NVL][V];
     float adb[O];
 #pragma unroll
@@ -128,101 +201,102 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
     for (int j = 0; j < NVL; ++j)
 #pragma unroll
         for (int i = 0; i < V; ++i) {
+            const int c = (lane + 32 * j) * V + i;
+            const bool ok = c < inner;
+            gm[j][i] = ok ? __ldg(gamma + c) : 0.f;
+            bt[j][i] = ok ? __ldg(beta + c) : 0.f;
             ag[j][i] = ab[j][i] = ax[j][i] = 0.f;
 #pragma unroll
-            for (int o = 0; o < O; ++o) aw[o][j][i] = 0.f;
+            for (int o = 0; o < O; ++o) {
+                w[o][j][i] = ok ? __ldg(w2 + (long long)o * inner + c) : 0.f;
+                aw[o][j][i] = 0.f;
+            }
         }
     const float inv = 1.f / inner;
-    for (long long r = warp0; r < rows; r += nwarps) {
-        const T* xr = x + r * ld_x;
-        float f[NVL][V];
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < NVL; ++j) {
-            const int c = (lane + 32 * j) * V;
-            if (c < inner) {
-                VkVec<T> v;
-                v.load(xr + c);
-                v.unpack(f[j]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < V; ++i) f[j][i] = 0.f;
+    const int npad = CW - inner;
+    const int wib = threadIdx.x >> 5;
+    // issue one row: the lane's conv vectors, and (lanes < 2*O) the row's upstream gradient / saved output values
+    auto issue = [&](unsigned long long rr, int sl) {
+        if (rr < rows) {
+            ring_issue<T, NVL>(ring, sl, x + (long long)rr * ld_x, lane, inner);
+            if (lane < 2 * O && (softplus || lane < O)) {
+                unsigned b, pix;
+                split_row((unsigned)rr, ppi, inv_ppi, &b, &pix);
+                const int o = lane < O ? lane : lane - O;
+                const long long oi = ((long long)b * O + o) * ppi + pix;
+                vk_cp_async4(dring + (sl * HT_WARPS + wib) * 2 * O + lane, (lane < O ? dout : out) + oi);
             }
-#pragma unroll
-            for (int i = 0; i < V; ++i) s += (c + i < inner) ? f[j][i] : 0.f;
         }
+        vk_cp_async_commit();
+    };
+#pragma unroll 1
+    for (int d = 0; d < RING; ++d) issue((unsigned long long)warp0 + (unsigned long long)d * nwarps, d);
+    int slot = 0;
+    for (unsigned r = warp0; r < rows; r += nwarps) {
+        float f[NVL][V];
+        vk_cp_async_wait<RING - 1>();
+        __syncwarp();                                   // the upstream values were copied by other lanes
+        ring_fetch<T, NVL>(ring, slot, lane, inner, f);
         // upstream gradient of the pre-softplus outputs (same value in every lane)
-        const long long b = r / pixels_per_image, pix = r % pixels_per_image;
         float dpre[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) {
-            const long long oi = (b * O + o) * pixels_per_image + pix;
-            float d = __ldg(dout + oi);
+            const float* dr = dring + (slot * HT_WARPS + wib) * 2 * O;
+            float d = dr[o];
             if (softplus) {
-                const float y = __ldg(out + oi);
+                const float y = dr[O + o];
                 d *= (y > 20.f) ? 1.f : (1.f - __expf(-y));   // sigmoid(pre) = 1 - exp(-softplus(pre))
             }
             dpre[o] = d;
             adb[o] += d;
         }
-        const float mean = vk_warp_sum(s) * inv;
-        float q = 0.f;
+        __syncwarp();                                   // every lane has read the slot before it is refilled
+        issue((unsigned long long)r + (unsigned long long)RING * nwarps, slot);
+        slot = (slot + 1) & (RING - 1);
+        float mean, rstd;
+        row_stats<NVL, V>(f, inner, npad, inv, &mean, &rstd);
+        const float shift = -mean * rstd;
+        float s1 = 0.f, s2 = 0.f;
+        // after this loop f holds xhat and dz holds d(loss)/d(LN output) * gamma per channel.  Pad channels: gamma = beta =
+        // w = 0 there, so z = 0, dg = 0 and every product below vanishes without a mask.
+        float dz[NVL][V];
 #pragma unroll
         for (int j = 0; j < NVL; ++j)
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                const int c = (lane + 32 * j) * V + i;
-                const float d = f[j][i] - mean;
-                q += (c < inner) ? d * d : 0.f;
-            }
-        const float rstd = rsqrtf(vk_warp_sum(q) * inv + LN_EPS);
-        float s1 = 0.f, s2 = 0.f;
-        // after this loop f holds xhat and dz holds d(loss)/d(LN output) per channel
-        float dz[NVL][V];
-#pragma unroll
-        for (int j = 0; j < NVL; ++j) {
-            const int c0 = (lane + 32 * j) * V;
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const int c = c0 + i;
-                const float gmv = s_gm[c];
-                const float h = (f[j][i] - mean) * rstd;
-                const float z = fmaf(h, gmv, s_bt[c]);
+                const float h = fmaf(f[j][i], rstd, shift);
                 float g, gp;
-                vk_gelu_both(z, &g, &gp);
+                vk_gelu_both(fmaf(h, gm[j][i], bt[j][i]), &g, &gp);
                 float dg = 0.f;
 #pragma unroll
                 for (int o = 0; o < O; ++o) {
-                    dg = fmaf(dpre[o], s_w[o * CW + c], dg);     // w == 0 on pad channels
+                    dg = fmaf(dpre[o], w[o][j][i], dg);
                     aw[o][j][i] = fmaf(dpre[o], g, aw[o][j][i]);
                 }
-                const bool ok = c < inner;
-                const float d = ok ? dg * gp : 0.f;
-                const float xh = ok ? h : 0.f;
-                f[j][i] = xh;
-                dz[j][i] = d;
-                const float dxh = d * gmv;
+                const float d = dg * gp;
+                const float dxh = d * gm[j][i];
+                f[j][i] = h;
+                dz[j][i] = dxh;
                 s1 += dxh;
-                s2 = fmaf(dxh, xh, s2);
-                ag[j][i] = fmaf(d, xh, ag[j][i]);
+                s2 = fmaf(dxh, h, s2);
+                ag[j][i] = fmaf(d, h, ag[j][i]);
                 ab[j][i] += d;
             }
-        }
-        s1 = vk_warp_sum(s1) * inv;
-        s2 = vk_warp_sum(s2) * inv;
-        T* dxr = dx + r * ld_dx;
+        const float2 ss = warp_sum2(s1, s2);
+        const float m1 = ss.x * inv, m2 = ss.y * inv;
+        T* dxr = dx + (long long)r * ld_dx;
 #pragma unroll
         for (int j = 0; j < NVL; ++j) {
             const int c0 = (lane + 32 * j) * V;
-            float fo[V];
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const int c = c0 + i;
-                const float dxv = (c < inner) ? rstd * (dz[j][i] * s_gm[c] - s1 - f[j][i] * s2) : 0.f;
-                fo[i] = dxv;
-                ax[j][i] += dxv;
-            }
             if (c0 < slice_w) {
+                float fo[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    float dxv = rstd * (dz[j][i] - m1 - f[j][i] * m2);
+                    if (c0 + V > inner) dxv = (c0 + i < inner) ? dxv : 0.f;
+                    fo[i] = dxv;
+                    ax[j][i] += dxv;
+                }
                 VkVec<T> vo;
                 vo.pack(fo);
                 vo.store(dxr + c0);
@@ -262,9 +336,12 @@ int launch_fwd(int O, const void* x, long long ld_x, int inner, const float* gam
     long long blocks = (rows + HT_WARPS - 1) / HT_WARPS;
     const long long cap = (long long)vkocr_sm_count() * 8;
     if (blocks > cap) blocks = cap;
+    const float inv_ppi = 1.f / (float)ppi;
+    constexpr int RING = RingDepth<NVL>::value;
 #define VK_HT_FWD(OO)                                                                                            \
-    head_tail_fwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS, 0, s>>>(reinterpret_cast<const T*>(x), ld_x, inner, \
-                                                                             gamma, beta, w2, b2, softplus, out, ppi, rows)
+    head_tail_fwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS, RING * NVL * HT_THREADS * 16, s>>>(reinterpret_cast<const T*>(x), ld_x, inner, \
+                                                                             gamma, beta, w2, b2, softplus, out,  \
+                                                                             (unsigned)ppi, inv_ppi, (unsigned)rows)
     switch (O) {
         case 1: VK_HT_FWD(1); break;
         case 2: VK_HT_FWD(2); break;
@@ -282,12 +359,16 @@ int launch_bwd(int O, const void* x, long long ld_x, int inner, int slice_w, con
                long long ld_dx, float* dgamma, float* dbeta, float* dw2, float* db2, float* dbias, cudaStream_t s) {
     constexpr int V = VkVec<T>::N;
     long long blocks = (rows + HT_WARPS - 1) / HT_WARPS;
-    const long long cap = (long long)vkocr_sm_count() * 2;
+    const long long cap = (long long)vkocr_sm_count() * ((NVL * O <= 4) ? 2 : 1);
     if (blocks > cap) blocks = cap;
+    const float inv_ppi = 1.f / (float)ppi;
+    constexpr int RING = RingDepth<NVL>::value;
 #define VK_HT_BWD(OO)                                                                                                       \
-    head_tail_bwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS, ((5 + 2 * OO) * 32 * NVL * V + OO) * sizeof(float), s>>>( \
-        reinterpret_cast<const T*>(x), ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, ppi, rows,              \
-        reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias)
+    cudaFuncSetAttribute(head_tail_bwd_kernel<T, NVL, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);         \
+    head_tail_bwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS,                                                        \
+        RING * NVL * HT_THREADS * 16 + (RING * HT_WARPS * 2 * OO + (3 + OO) * 32 * NVL * V + OO) * sizeof(float), s>>>(      \
+        reinterpret_cast<const T*>(x), ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, (unsigned)ppi, inv_ppi,  \
+        (unsigned)rows, reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias)
     switch (O) {
         case 1: VK_HT_BWD(1); break;
         case 2: VK_HT_BWD(2); break;
@@ -318,6 +399,8 @@ int vkocr_head_tail_fwd(int dtype, const void* x, long long ld_x, int inner, int
     const int V = dtype == VKOCR_F32 ? 4 : 8;
     VK_REQUIRE(slice_w % V == 0 && ld_x % V == 0 && slice_w >= inner, VKOCR_BAD_ALIGN, "head_tail_fwd: slice %d ld %lld", slice_w, ld_x);
     VK_REQUIRE(O >= 1 && O <= 4, VKOCR_BAD_SHAPE, "head_tail_fwd: out channels %d (1..4 supported)", O);
+    VK_REQUIRE(rows < (1LL << 31) && pixels_per_image >= 1 && pixels_per_image < (1LL << 31), VKOCR_BAD_SHAPE,
+               "head_tail_fwd: %lld rows / %lld pixels per image out of range", rows, pixels_per_image);
     const int nvl = pick_nvl(dtype, slice_w);
     VK_REQUIRE(nvl > 0, VKOCR_BAD_SHAPE, "head_tail_fwd: inner width %d too large", slice_w);
     if (rows == 0) return VKOCR_OK;
@@ -344,6 +427,8 @@ int vkocr_head_tail_bwd(int dtype, const void* x, long long ld_x, int inner, int
     const int V = dtype == VKOCR_F32 ? 4 : 8;
     VK_REQUIRE(slice_w % V == 0 && ld_x % V == 0 && ld_dx % V == 0 && slice_w >= inner, VKOCR_BAD_ALIGN, "head_tail_bwd: slice %d", slice_w);
     VK_REQUIRE(O >= 1 && O <= 4, VKOCR_BAD_SHAPE, "head_tail_bwd: out channels %d (1..4 supported)", O);
+    VK_REQUIRE(rows < (1LL << 31) && pixels_per_image >= 1 && pixels_per_image < (1LL << 31), VKOCR_BAD_SHAPE,
+               "head_tail_bwd: %lld rows / %lld pixels per image out of range", rows, pixels_per_image);
     const int nvl = pick_nvl(dtype, slice_w);
     VK_REQUIRE(nvl > 0, VKOCR_BAD_SHAPE, "head_tail_bwd: inner width %d too large", slice_w);
     if (rows == 0) return VKOCR_OK;
