@@ -60,6 +60,7 @@ _SIGNATURES = {
     'vkocr_layernorm_bwd': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                             c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'vkocr_colsum': [c_int, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p],
+    'vkocr_scale_rows_colsum': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p],
     'vkocr_dwconv7_fwd': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                           c_void_p, c_ll, c_void_p],
     'vkocr_dwconv7_wgrad': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

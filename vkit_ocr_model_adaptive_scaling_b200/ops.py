@@ -444,14 +444,14 @@ class ConvNextLayerFn(torch.autograd.Function):
         dt, dev = x.dtype, x.device
         dy = to_nhwc(dy, dt)
         gamma = scale.detach().reshape(-1)
+        su = _zeros_f32(C, dev)
         if ctx.has_mask:
             u = alloc_nhwc(B, H, W, C, dt, dev)
-            L.check(L.LIB.vkocr_scale_rows(_tag(dt), L.ptr(dy), dy.stride(3), L.ptr(u), u.stride(3), M, C, L.ptr(mask), H * W, _s()),
-                    'scale_rows')
+            L.check(L.LIB.vkocr_scale_rows_colsum(_tag(dt), L.ptr(dy), dy.stride(3), L.ptr(u), u.stride(3), M, C, L.ptr(mask), H * W,
+                                                  L.ptr(su), _s()), 'scale_rows_colsum')
         else:
             u = dy
-        su = _zeros_f32(C, dev)
-        colsum(u, u.stride(3), M, C, su)
+            colsum(u, u.stride(3), M, C, su)
         # dH_pre = (U . (gamma * W2)) * gelu'(H_pre)
         w2d, n2 = packed_linear_dgrad(w2, dt, gamma)
         dh = torch.empty((M, hid), dtype=dt, device=dev)
