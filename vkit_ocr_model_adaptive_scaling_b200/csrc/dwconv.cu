@@ -13,7 +13,7 @@ constexpr int STRIP = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-dwconv7_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int B, int H, int W, int C,
+dwconv7_generic_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int B, int H, int W, int C,
                const float* __restrict__ wt, const float* __restrict__ bias, const T* __restrict__ add, long long ld_add) {
     constexpr int V = VkVec<T>::N;
     const int CV = C / V;
@@ -93,7 +93,7 @@ dwconv7_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long 
 // block visits.  Partials are merged per block in shared memory, then one atomic per (channel, tap) and block.
 template <typename T, int SEG>
 __global__ void __launch_bounds__(256, 2)
-dwconv7_wgrad_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restrict__ x, long long ld_x, int B, int H, int W,
+dwconv7_wgrad_generic_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restrict__ x, long long ld_x, int B, int H, int W,
                      int C, int cv_per_block, float* __restrict__ dw) {
     using VT = VkVec4<T>;
     constexpr int V = VT::N;
@@ -172,6 +172,249 @@ dwconv7_wgrad_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restr
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------- tiled bf16 kernels
+// Shared-memory tiled kernels for bf16 storage with C % 32 == 0 (every hot-path shape).  A block is persistent over the
+// TW x 8 pixel tiles of one 32-channel block: the (TW+6) x (8+6) halo tile is brought in with 16-byte cp.async copies
+// (out-of-image pixels are zero-filled by the copy itself = the conv padding) into one of two buffers while the other is
+// being consumed, and all arithmetic reads shared memory.  The kernels are FMA-bound (49 FMAs per output element against
+// 4 bytes of HBM traffic), so the inner loops are arranged for FMA density: each thread owns 4 channels x a 4 x 2 pixel
+// patch (forward / data gradient) or 4 channels x one kernel row (weight gradient) and converts every bf16 input once
+// per use row.  TW is 40 for the 160/80/40-pixel-wide maps of 640 x 640 training (exact tiling), 20 for 20, 32 otherwise.
+constexpr int TH = 8, CB = 32;
+constexpr int PIX_B = CB * 2;                       // bytes per pixel in the tile
+constexpr int HALO_H = TH + 6;
+// row strides: forward -> rows 2 apart land 64 B apart (mod 128), weight gradient -> consecutive rows do: conflict-free LDS.64
+__host__ __device__ constexpr int rs_fwd(int tw) { return ((tw + 6) * PIX_B) % 128 == 0 ? (tw + 6) * PIX_B + 32 : (tw + 6) * PIX_B + 96; }
+__host__ __device__ constexpr int rs_wg(int tw) { return ((tw + 6) * PIX_B) % 128 == 0 ? (tw + 6) * PIX_B + 64 : (tw + 6) * PIX_B; }
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+__device__ __forceinline__ void unpack4(uint2 raw, float* f) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ uint2 pack4(const float* f) {
+    uint2 raw;
+    *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(f[0], f[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(f[2], f[3]);
+    return raw;
+}
+
+struct TileCoord { int b, y0, x0; };
+template <int TW>
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_x, int tiles_y) {
+    TileCoord tc;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    tc.x0 = tx * TW;
+    tc.y0 = (t % tiles_y) * TH;
+    tc.b = t / tiles_y;
+    return tc;
+}
+
+// halo tile of image b, channels [c0, c0+32), pixels [y0-3, y0+TH+3) x [x0-3, x0+TW+3) -> shared memory (row stride RS)
+template <int TW, int RS>
+__device__ __forceinline__ void load_halo(uint32_t smem, const __nv_bfloat16* __restrict__ x, long long ld_x, TileCoord tc, int H,
+                                          int W, int c0) {
+    constexpr int HW = TW + 6;
+    for (int q = threadIdx.x; q < HALO_H * HW * 4; q += blockDim.x) {
+        const int part = q & 3, pix = q >> 2;
+        const int hy = pix / HW, hx = pix - hy * HW;
+        const int yy = tc.y0 + hy - 3, xx = tc.x0 + hx - 3;
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const __nv_bfloat16* src = ok ? x + (((long long)tc.b * H + yy) * W + xx) * ld_x + c0 + part * 8 : x;
+        cp_async16_zfill(smem + (uint32_t)(hy * RS + hx * PIX_B + part * 16), src, ok);
+    }
+}
+
+template <int TW>
+__global__ void __launch_bounds__(8 * TW, (TW <= 32) ? 3 : 2)
+dwconv7_tile_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bfloat16* __restrict__ y, long long ld_y, int B,
+                    int H, int W, int C, const float* __restrict__ wt, const float* __restrict__ bias,
+                    const __nv_bfloat16* __restrict__ add, long long ld_add, int tiles_x, int tiles_y) {
+    constexpr int RS = rs_fwd(TW);
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    uint8_t* s_in = dw_smem;                                             // [HALO_H][RS]
+    float* s_w = reinterpret_cast<float*>(dw_smem + HALO_H * RS);        // [49][CB]
+    float* s_b = s_w + 49 * CB;                                          // [CB]
+    const int c0 = blockIdx.y * CB;
+    const TileCoord tc = tile_coord<TW>(blockIdx.x, tiles_x, tiles_y);
+    load_halo<TW, RS>((uint32_t)__cvta_generic_to_shared(s_in), x, ld_x, tc, H, W, c0);
+    vk_cp_async_commit();
+    for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) s_w[i] = __ldg(wt + (long long)(i / CB) * C + c0 + (i % CB));
+    if (threadIdx.x < CB) s_b[threadIdx.x] = bias ? __ldg(bias + c0 + threadIdx.x) : 0.f;
+
+    // thread -> 4 channels (cq) x a patch of 4 (x) x 2 (y) pixels; the 4 patches of a warp are stacked in y
+    const int cq = threadIdx.x & 7;
+    const int sidx = threadIdx.x >> 3;          // 0 .. TW - 1
+    const int sy = sidx & 3, sx = sidx >> 2;    // 4 patches in y (8 rows), TW / 4 in x
+    const int px = sx * 4, py = sy * 2;
+    vk_cp_async_wait<0>();
+    __syncthreads();
+    float acc[2][4][4];
+    {
+        const float4 bv = *reinterpret_cast<const float4*>(s_b + cq * 4);
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) { acc[oy][o][0] = bv.x; acc[oy][o][1] = bv.y; acc[oy][o][2] = bv.z; acc[oy][o][3] = bv.w; }
+    }
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {               // halo rows py + r (input rows y0 + py + r - 3)
+        float in[10][4];
+        const uint8_t* rowp = s_in + (py + r) * RS + px * PIX_B + cq * 8;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) unpack4(*reinterpret_cast<const uint2*>(rowp + j * PIX_B), in[j]);
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy) {
+            const int ky = r - oy;
+            if (ky >= 0 && ky < 7) {
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx) {
+                    const float4 w = *reinterpret_cast<const float4*>(s_w + (ky * 7 + kx) * CB + cq * 4);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        acc[oy][o][0] = fmaf(w.x, in[o + kx][0], acc[oy][o][0]);
+                        acc[oy][o][1] = fmaf(w.y, in[o + kx][1], acc[oy][o][1]);
+                        acc[oy][o][2] = fmaf(w.z, in[o + kx][2], acc[oy][o][2]);
+                        acc[oy][o][3] = fmaf(w.w, in[o + kx][3], acc[oy][o][3]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy) {
+        const int yy = tc.y0 + py + oy;
+        if (yy < H) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int xx = tc.x0 + px + o;
+                if (xx < W) {
+                    const long long pix = ((long long)tc.b * H + yy) * W + xx;
+                    if (add) {
+                        float f[4];
+                        unpack4(*reinterpret_cast<const uint2*>(add + pix * ld_add + c0 + cq * 4), f);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[oy][o][i] += f[i];
+                    }
+                    *reinterpret_cast<uint2*>(y + pix * ld_y + c0 + cq * 4) = pack4(acc[oy][o]);
+                }
+            }
+        }
+    }
+}
+
+// Weight gradient.  Thread -> 4 channels (cq) x one kernel row ky x one pair of tile rows; it slides along x keeping the
+// 7 input vectors of its window in registers: acc[kx][4] += dy[y][x][4] * in[y + ky][x + kx][4].
+template <int TW>
+__global__ void __launch_bounds__(224)
+dwconv7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ x,
+                          long long ld_x, int B, int H, int W, int C, int tiles_x, int tiles_y, float* __restrict__ dw) {
+    constexpr int RS = rs_wg(TW);
+    constexpr int BUF = HALO_H * RS + TH * TW * PIX_B;           // halo tile of x, then the dy tile
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    float* s_acc = reinterpret_cast<float*>(dw_smem + BUF);      // [49][CB]
+    const int c0 = blockIdx.x * CB;
+    const int cq = threadIdx.x & 7;
+    const int rest = threadIdx.x >> 3;          // 0..27
+    const int ky = rest % 7, rg = rest / 7;     // kernel row, row pair of the tile
+    float acc[7][4];
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+    for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) s_acc[i] = 0.f;
+    const int ntiles = B * tiles_y * tiles_x;
+    const uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(dw_smem);
+    for (int t = blockIdx.y; t < ntiles; t += gridDim.y) {
+        const TileCoord tc = tile_coord<TW>(t, tiles_x, tiles_y);
+        __syncthreads();                        // previous tile fully consumed
+        load_halo<TW, RS>(smem_a, x, ld_x, tc, H, W, c0);
+        for (int q = threadIdx.x; q < TH * TW * 4; q += blockDim.x) {
+            const int part = q & 3, pix = q >> 2;
+            const int yy = tc.y0 + pix / TW, xx = tc.x0 + pix % TW;
+            const bool ok = yy < H && xx < W;
+            const __nv_bfloat16* src = ok ? dy + (((long long)tc.b * H + yy) * W + xx) * ld_dy + c0 + part * 8 : dy;
+            cp_async16_zfill(smem_a + (uint32_t)(HALO_H * RS + pix * PIX_B + part * 16), src, ok);
+        }
+        vk_cp_async_commit();
+        vk_cp_async_wait<0>();
+        __syncthreads();
+        const uint8_t* s_in = dw_smem;
+        const uint8_t* s_dy = s_in + HALO_H * RS;
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy) {
+            const int row = rg * 2 + oy;                                   // tile row of dy
+            const uint8_t* inrow = s_in + (row + ky) * RS + cq * 8;        // halo row row + ky  (input row y + ky - 3)
+            const uint8_t* dyrow = s_dy + row * TW * PIX_B + cq * 8;
+            float win[7][4];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) unpack4(*reinterpret_cast<const uint2*>(inrow + k * PIX_B), win[k + 1]);
+#pragma unroll 4
+            for (int xx = 0; xx < TW; ++xx) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) win[k][i] = win[k + 1][i];
+                unpack4(*reinterpret_cast<const uint2*>(inrow + (xx + 6) * PIX_B), win[6]);
+                float g[4];
+                unpack4(*reinterpret_cast<const uint2*>(dyrow + xx * PIX_B), g);
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(g[i], win[k][i], acc[k][i]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[(ky * 7 + k) * CB + cq * 4 + i], acc[k][i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) atomicAdd(dw + (long long)(c0 + i % CB) * 49 + i / CB, s_acc[i]);
+}
+
+inline int pick_tw(int W) { return (W % 40 == 0) ? 40 : ((W % 20 == 0 && W < 40) ? 20 : 32); }
+
+template <int TW>
+int launch_dw_tile(const void* x, long long ld_x, void* y, long long ld_y, int B, int H, int W, int C, const float* wt,
+                   const float* bias, const void* add, long long ld_add, cudaStream_t s) {
+    const int tiles_x = vk_cdiv(W, TW), tiles_y = vk_cdiv(H, TH);
+    const long long ntiles = (long long)B * tiles_x * tiles_y;
+    const int cblocks = C / CB;
+    const int smem = HALO_H * rs_fwd(TW) + (49 * CB + CB) * (int)sizeof(float);
+    cudaFuncSetAttribute(dwconv7_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    dwconv7_tile_kernel<TW><<<dim3((unsigned)ntiles, (unsigned)cblocks), 8 * TW, smem, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ld_x, reinterpret_cast<__nv_bfloat16*>(y), ld_y, B, H, W, C, wt, bias,
+        reinterpret_cast<const __nv_bfloat16*>(add), ld_add, tiles_x, tiles_y);
+    return 0;
+}
+
+template <int TW>
+int launch_dw_wgrad_tile(const void* dy, long long ld_dy, const void* x, long long ld_x, int B, int H, int W, int C, float* dw,
+                         cudaStream_t s) {
+    const int tiles_x = vk_cdiv(W, TW), tiles_y = vk_cdiv(H, TH);
+    const long long ntiles = (long long)B * tiles_x * tiles_y;
+    const int cblocks = C / CB;
+    const int smem = HALO_H * rs_wg(TW) + TH * TW * PIX_B + 49 * CB * (int)sizeof(float);
+    const int per_sm = (220 * 1024) / (smem + 1024);
+    long long gy = ((long long)vkocr_sm_count() * per_sm + cblocks - 1) / cblocks;
+    if (gy > ntiles) gy = ntiles;
+    if (gy < 1) gy = 1;
+    cudaFuncSetAttribute(dwconv7_wgrad_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    dwconv7_wgrad_tile_kernel<TW><<<dim3((unsigned)cblocks, (unsigned)gy), 224, smem, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), ld_dy, reinterpret_cast<const __nv_bfloat16*>(x), ld_x, B, H, W, C, tiles_x,
+        tiles_y, dw);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -187,8 +430,16 @@ int vkocr_dwconv7_fwd(int dtype, const void* x, long long ld_x, void* y, long lo
     const long long total = (long long)B * H * ((W + STRIP - 1) / STRIP) * (C / V);
     if (total == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == VKOCR_BF16 && C % CB == 0 && (long long)B * H * W < (1LL << 30)) {
+        const int tw = pick_tw(W);
+        if (tw == 40) launch_dw_tile<40>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        else if (tw == 20) launch_dw_tile<20>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        else launch_dw_tile<32>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        VK_CHECK_LAUNCH("dwconv7_tile_kernel");
+        return VKOCR_OK;
+    }
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    VK_DISPATCH_DTYPE(dtype, T, (dwconv7_kernel<T><<<blocks, 256, 0, s>>>(
+    VK_DISPATCH_DTYPE(dtype, T, (dwconv7_generic_kernel<T><<<blocks, 256, 0, s>>>(
                                     reinterpret_cast<const T*>(x), ld_x, reinterpret_cast<T*>(y), ld_y, B, H, W, C, wt, bias,
                                     reinterpret_cast<const T*>(add), ld_add)));
     VK_CHECK_LAUNCH("dwconv7_kernel");
@@ -202,6 +453,15 @@ int vkocr_dwconv7_wgrad(int dtype, const void* dy, long long ld_dy, const void* 
     const int V = 4;   // 4 channels per thread in either storage type (VkVec4)
     VK_REQUIRE(C % V == 0 && ld_x % V == 0 && ld_dy % V == 0, VKOCR_BAD_ALIGN, "dwconv7_wgrad: C %d / strides must be multiples of %d", C, V);
     if ((long long)B * H * W == 0) return VKOCR_OK;
+    if (dtype == VKOCR_BF16 && C % CB == 0 && (long long)B * H * W < (1LL << 30)) {
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        const int tw = pick_tw(W);
+        if (tw == 40) launch_dw_wgrad_tile<40>(dy, ld_dy, x, ld_x, B, H, W, C, dw, st);
+        else if (tw == 20) launch_dw_wgrad_tile<20>(dy, ld_dy, x, ld_x, B, H, W, C, dw, st);
+        else launch_dw_wgrad_tile<32>(dy, ld_dy, x, ld_x, B, H, W, C, dw, st);
+        VK_CHECK_LAUNCH("dwconv7_wgrad_tile_kernel");
+        return VKOCR_OK;
+    }
     constexpr int SEG = 8;
     const int CV = C / V;
     // channel vectors per block: a divisor-friendly width so that (almost) all 256 threads carry a segment
@@ -218,7 +478,7 @@ int vkocr_dwconv7_wgrad(int dtype, const void* dy, long long ld_dy, const void* 
     dim3 grid((unsigned)gx, 7, (unsigned)zblocks);
     const size_t smem = (size_t)7 * cvb * V * sizeof(float);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    VK_DISPATCH_DTYPE(dtype, T, (dwconv7_wgrad_kernel<T, SEG><<<grid, threads, smem, s>>>(
+    VK_DISPATCH_DTYPE(dtype, T, (dwconv7_wgrad_generic_kernel<T, SEG><<<grid, threads, smem, s>>>(
                                     reinterpret_cast<const T*>(dy), ld_dy, reinterpret_cast<const T*>(x), ld_x, B, H, W, C, cvb,
                                     dw)));
     VK_CHECK_LAUNCH("dwconv7_wgrad_kernel");
