@@ -153,6 +153,143 @@ upsample_bwd_kernel(const T* __restrict__ ddst, long long ld_d, int H, int W, T*
     out.store(sp);
 }
 
+// ------------------------------------------------------------------------------------------------- exact x2 bilinear
+// F.interpolate(scale 2, mode='bilinear', align_corners=False) is the separable 2-tap filter {0.25, 0.75} with the source
+// index clamped at the borders (out[2k] = .25 in[k-1] + .75 in[k], out[2k+1] = .75 in[k] + .25 in[k+1]); its adjoint is
+// the 4-tap filter {.25, .75, .75, .25} over the gradient rows/cols 2i-1 .. 2i+2 with the GRADIENT index clamped.  These
+// carry the 2.5 GB head inputs of the adaptive-scaling heads (upernext.py:237-244) and every top-down step.
+// One thread = one 16-byte channel vector of one source column, sliding down ROWS source rows with the horizontally
+// filtered rows kept in registers: 3 loads per 4 stores (forward), 8 loads per store (backward, served by L1/L2).
+constexpr int UP_ROWS = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const T* __restrict__ src, long long ld_s, int h, int w, T* __restrict__ dst, long long ld_d, int B, int CV,
+                      int accumulate) {
+    constexpr int V = VkVec<T>::N;
+    const int chunks = (h + UP_ROWS - 1) / UP_ROWS;
+    const long long total = (long long)B * chunks * w * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int j = (int)(r % w);
+    r /= w;
+    const int ch = (int)(r % chunks);
+    const int b = (int)(r / chunks);
+    const int c = cv * V;
+    const int jm = j > 0 ? j - 1 : 0, jp = j < w - 1 ? j + 1 : w - 1;
+    const int i0 = ch * UP_ROWS, i1 = (i0 + UP_ROWS < h) ? i0 + UP_ROWS : h;
+    const T* sb = src + (long long)b * h * w * ld_s + c;
+    const int W = 2 * w;
+    T* db = dst + (long long)b * (2 * h) * W * ld_d + c;
+    // he / ho: horizontally filtered source row for the even / odd output column of this source column
+    auto hrow = [&](int i, float* he, float* ho) {
+        const T* row = sb + (long long)i * w * ld_s;
+        VkVec<T> vm, v0, vp;
+        vm.load(row + (long long)jm * ld_s);
+        v0.load(row + (long long)j * ld_s);
+        vp.load(row + (long long)jp * ld_s);
+        float fm[V], f0[V], fp[V];
+        vm.unpack(fm); v0.unpack(f0); vp.unpack(fp);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            he[e] = fmaf(0.25f, fm[e], 0.75f * f0[e]);
+            ho[e] = fmaf(0.25f, fp[e], 0.75f * f0[e]);
+        }
+    };
+    auto emit = [&](int Y, int X, const float* a, const float* bb, float wa, float wb) {
+        T* dp = db + ((long long)Y * W + X) * ld_d;
+        float o[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) o[e] = fmaf(wa, a[e], wb * bb[e]);
+        if (accumulate) {
+            VkVec<T> d;
+            d.load(dp);
+            float f[V];
+            d.unpack(f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) o[e] += f[e];
+        }
+        VkVec<T> out;
+        out.pack(o);
+        out.store(dp);
+    };
+    float pe[V], po[V], ce[V], co[V], ne[V], no[V];
+    hrow(i0 > 0 ? i0 - 1 : 0, pe, po);
+    hrow(i0, ce, co);
+    for (int i = i0; i < i1; ++i) {
+        hrow(i < h - 1 ? i + 1 : h - 1, ne, no);
+        emit(2 * i, 2 * j, pe, ce, 0.25f, 0.75f);
+        emit(2 * i, 2 * j + 1, po, co, 0.25f, 0.75f);
+        emit(2 * i + 1, 2 * j, ce, ne, 0.75f, 0.25f);
+        emit(2 * i + 1, 2 * j + 1, co, no, 0.75f, 0.25f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) { pe[e] = ce[e]; po[e] = co[e]; ce[e] = ne[e]; co[e] = no[e]; }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const T* __restrict__ ddst, long long ld_d, T* __restrict__ dsrc, long long ld_s, int h, int w, int B, int CV,
+                      int accumulate) {
+    constexpr int V = VkVec<T>::N;
+    const int chunks = (h + UP_ROWS - 1) / UP_ROWS;
+    const long long total = (long long)B * chunks * w * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int j = (int)(r % w);
+    r /= w;
+    const int ch = (int)(r % chunks);
+    const int b = (int)(r / chunks);
+    const int c = cv * V;
+    const int H = 2 * h, W = 2 * w;
+    const int x0 = 2 * j > 0 ? 2 * j - 1 : 0, x1 = 2 * j, x2 = 2 * j + 1, x3 = 2 * j + 2 < W ? 2 * j + 2 : W - 1;
+    const int i0 = ch * UP_ROWS, i1 = (i0 + UP_ROWS < h) ? i0 + UP_ROWS : h;
+    const T* db = ddst + (long long)b * H * W * ld_d + c;
+    T* sb = dsrc + (long long)b * h * w * ld_s + c;
+    // g: horizontally filtered gradient row (columns 2j-1 .. 2j+2, clamped)
+    auto grow = [&](int Y, float* g) {
+        Y = Y < 0 ? 0 : (Y > H - 1 ? H - 1 : Y);
+        const T* row = db + (long long)Y * W * ld_d;
+        VkVec<T> v0, v1, v2, v3;
+        v0.load(row + (long long)x0 * ld_d);
+        v1.load(row + (long long)x1 * ld_d);
+        v2.load(row + (long long)x2 * ld_d);
+        v3.load(row + (long long)x3 * ld_d);
+        float f0[V], f1[V], f2[V], f3[V];
+        v0.unpack(f0); v1.unpack(f1); v2.unpack(f2); v3.unpack(f3);
+#pragma unroll
+        for (int e = 0; e < V; ++e) g[e] = fmaf(0.25f, f0[e] + f3[e], 0.75f * (f1[e] + f2[e]));
+    };
+    float ga[V], gb[V], gc[V], gd[V];
+    grow(2 * i0 - 1, ga);
+    grow(2 * i0, gb);
+    for (int i = i0; i < i1; ++i) {
+        grow(2 * i + 1, gc);
+        grow(2 * i + 2, gd);
+        float o[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) o[e] = fmaf(0.25f, ga[e] + gd[e], 0.75f * (gb[e] + gc[e]));
+        T* sp = sb + ((long long)i * w + j) * ld_s;
+        if (accumulate) {
+            VkVec<T> d;
+            d.load(sp);
+            float f[V];
+            d.unpack(f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) o[e] += f[e];
+        }
+        VkVec<T> out;
+        out.pack(o);
+        out.store(sp);
+#pragma unroll
+        for (int e = 0; e < V; ++e) { ga[e] = gc[e]; gb[e] = gd[e]; }
+    }
+}
+
 // AdaptiveAvgPool2d: bin i = [floor(i*in/s), ceil((i+1)*in/s))
 __device__ __forceinline__ int bin_lo(int i, int in, int s) { return (i * in) / s; }
 __device__ __forceinline__ int bin_hi(int i, int in, int s) { return ((i + 1) * in + s - 1) / s; }
@@ -386,6 +523,15 @@ int vkocr_upsample_fwd(int dtype, const void* src, long long ld_s, int h, int w,
     if ((long long)B * H * W * C == 0) return VKOCR_OK;
     const bool vec = vec_ok(dtype, C, ld_s, ld_d) && ptr16(src, dst);   // else: scalar path (odd widths / slice offsets)
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (vec && mode == 0 && H == 2 * h && W == 2 * w) {
+        const int V = dtype == VKOCR_F32 ? 4 : 8;
+        const long long total = (long long)B * ((h + UP_ROWS - 1) / UP_ROWS) * w * (C / V);
+        VK_DISPATCH_DTYPE(dtype, T, (upsample2x_fwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                        reinterpret_cast<const T*>(src), ld_s, h, w, reinterpret_cast<T*>(dst), ld_d, B, C / V,
+                                        accumulate)));
+        VK_CHECK_LAUNCH("upsample2x_fwd_kernel");
+        return VKOCR_OK;
+    }
     VK_DISPATCH_DTYPE(dtype, T, (vec ? launch_upsample_fwd<T, VkVec<T>>(src, ld_s, h, w, dst, ld_d, H, W, B, C, mode, accumulate, s)
                                      : launch_upsample_fwd<T, VkScalar<T>>(src, ld_s, h, w, dst, ld_d, H, W, B, C, mode, accumulate, s)));
     VK_CHECK_LAUNCH("upsample_fwd_kernel");
@@ -400,6 +546,15 @@ int vkocr_upsample_bwd(int dtype, const void* ddst, long long ld_d, int H, int W
     if ((long long)B * h * w * C == 0) return VKOCR_OK;
     const bool vec = vec_ok(dtype, C, ld_s, ld_d) && ptr16(ddst, dsrc);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (vec && mode == 0 && H == 2 * h && W == 2 * w) {
+        const int V = dtype == VKOCR_F32 ? 4 : 8;
+        const long long total = (long long)B * ((h + UP_ROWS - 1) / UP_ROWS) * w * (C / V);
+        VK_DISPATCH_DTYPE(dtype, T, (upsample2x_bwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                        reinterpret_cast<const T*>(ddst), ld_d, reinterpret_cast<T*>(dsrc), ld_s, h, w, B, C / V,
+                                        accumulate)));
+        VK_CHECK_LAUNCH("upsample2x_bwd_kernel");
+        return VKOCR_OK;
+    }
     VK_DISPATCH_DTYPE(dtype, T, (vec ? launch_upsample_bwd<T, VkVec<T>>(ddst, ld_d, H, W, dsrc, ld_s, h, w, B, C, mode, accumulate, s)
                                      : launch_upsample_bwd<T, VkScalar<T>>(ddst, ld_d, H, W, dsrc, ld_s, h, w, B, C, mode, accumulate, s)));
     VK_CHECK_LAUNCH("upsample_bwd_kernel");
