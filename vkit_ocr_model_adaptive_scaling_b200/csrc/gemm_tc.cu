@@ -8,7 +8,8 @@
 //   warp 1 (1 lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN (16..256), K=16 per instruction,
 //                    accumulators double-buffered in TMEM (2 x 256 columns).
 //   warp 2           TMEM allocator.
-//   warps 4..11      epilogue: tcgen05.ld -> registers -> bias / GELU / layer-scale / residual -> global.
+//   warps 4..11      epilogue: tcgen05.ld -> registers -> bias / GELU / layer-scale / residual -> 32 x 64 tile staged in
+//                    shared memory -> coalesced 128-byte-row global stores.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
 //
 // Modes (see gemm_common.cuh):
@@ -24,16 +25,38 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements in one 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int MAX_SMEM = 192 * 1024;  // operand stages
-constexpr int EPI_TILE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B staging tile for TMA stores (SWIZZLE_128B)
+constexpr int EPI_TILE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B staging tile (row-per-lane in, 4 full rows per store out)
 constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 
+// Division of a 31-bit unsigned by a launch-time constant without a divide: q = (mulhi(n, m) + n) >> s.
+// (The unit -> tile decode runs once per tile in every warp; with 64-bit `/` and `%` it cost as many instructions as the
+// epilogue of a K = 96 tile itself.)
+struct FastDiv {
+    uint32_t d, m, s;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    f.s = s;
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) { return (__umulhi(n, f.m) + n) >> f.s; }
+__device__ __forceinline__ void fd_divmod(uint32_t n, const FastDiv& f, uint32_t* q, uint32_t* r) {
+    *q = fd_div(n, f);
+    *r = n - *q * f.d;
+}
+
 struct TcParams {
     int mode;                // 0 NT, 1 TN
     int batch, H, W;
     int BW, BH;              // pixel box (BW*BH == 128 for NT, 64 for TN)
+    int bw_shift;            // log2(BW)
     int tiles_x, tiles_y;
     int ks;
     int kb_per_tap;          // NT: 64-wide K blocks per tap
@@ -43,9 +66,10 @@ struct TcParams {
     int num_stages;
     int stage_bytes;
     int skip_tma;            // debug: producers arrive without loading (timing experiments)
-    int tma_store;           // NT: outputs leave through shared memory + TMA stores (aligned bf16 outputs)
+    int staged_store;        // NT: aligned bf16 outputs leave through the shared-memory staging tiles
     int M;                   // NT plain GEMM: number of rows
     long long units;
+    FastDiv fd_n, fd_x, fd_y, fd_i, fd_taps, fd_rpg;   // n_tiles, tiles_x, tiles_y, i_tiles, ks*ks, rows_per_group
     VkocrEpilogue ep;
 };
 
@@ -99,15 +123,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -174,7 +189,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo1
 // ------------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                     const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapPre,
                      const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -194,10 +208,6 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-        if (p.tma_store) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapOut) : "memory");
-            if (p.ep.out_pre) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapPre) : "memory");
-        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
@@ -231,29 +241,28 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         int tap, i0, kt_begin, kt_end;  // TN
         int num_kb;
     };
-    auto decode = [&](long long u) {
+    auto decode = [&](long long ul) {
         Unit t;
+        const uint32_t u = (uint32_t)ul;          // units < 2^31 (checked on the host)
         if (p.mode == 0) {
-            const int nt = (int)(u % p.n_tiles);
-            long long mt = u / p.n_tiles;
-            const int tx = (int)(mt % p.tiles_x);
-            mt /= p.tiles_x;
-            const int ty = (int)(mt % p.tiles_y);
-            t.b = (int)(mt / p.tiles_y);
-            t.n0 = nt * BN;
-            t.x0 = tx * p.BW;
-            t.y0 = ty * p.BH;
+            uint32_t nt, mt, tx, ty, b;
+            fd_divmod(u, p.fd_n, &mt, &nt);
+            fd_divmod(mt, p.fd_x, &mt, &tx);
+            fd_divmod(mt, p.fd_y, &b, &ty);
+            t.b = (int)b;
+            t.n0 = (int)nt * BN;
+            t.x0 = (int)tx * p.BW;
+            t.y0 = (int)ty * p.BH;
             t.num_kb = p.ks * p.ks * p.kb_per_tap;
             t.tap = 0; t.i0 = 0; t.kt_begin = 0; t.kt_end = 0;
         } else {
-            const int jt = (int)(u % p.n_tiles);
-            long long r = u / p.n_tiles;
-            const int it = (int)(r % p.i_tiles);
-            r /= p.i_tiles;
-            t.tap = (int)(r % (p.ks * p.ks));
-            const int sp = (int)(r / (p.ks * p.ks));
-            t.n0 = jt * BN;
-            t.i0 = it * BM;
+            uint32_t jt, r, it, tap, sp;
+            fd_divmod(u, p.fd_n, &r, &jt);
+            fd_divmod(r, p.fd_i, &r, &it);
+            fd_divmod(r, p.fd_taps, &sp, &tap);
+            t.tap = (int)tap;
+            t.n0 = (int)jt * BN;
+            t.i0 = (int)it * BM;
             t.kt_begin = (int)((long long)pix_tiles * sp / p.splits);
             t.kt_end = (int)((long long)pix_tiles * (sp + 1) / p.splits);
             t.num_kb = t.kt_end - t.kt_begin;
@@ -417,7 +426,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
             const bool vec_ok = (p.mode == 0) && (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
                                 (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0);
-            if (p.tma_store) {
+            if (p.staged_store) {
                 // ---- fast path: each lane finishes its row in registers, the warp's 32 x 64 tile is staged in shared memory
                 // (128-byte swizzle, conflict-free) and leaves as ONE TMA store: full 128-byte lines per row, rows/columns
                 // outside the tensor clipped by the TMA unit.  (Per-lane 16-byte global stores of row-strided data cap
@@ -426,20 +435,27 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 const uint32_t my_row = wb + (uint32_t)lane * 128u;
                 const uint32_t sw = (uint32_t)(lane & 7);
                 const int r0 = q * 32;
-                const int cx = t.x0 + r0 % p.BW, cy = t.y0 + r0 / p.BW;
                 const int pairs = (BN + 63) / 64;
                 const __nv_bfloat16* esrc = ep.residual ? reinterpret_cast<const __nv_bfloat16*>(ep.residual)
                                                         : (ep.act == 2 ? reinterpret_cast<const __nv_bfloat16*>(ep.aux) : nullptr);
                 const long long eld = ep.residual ? ep.ld_res : ep.ld_aux;
-                const float rs = (ep.row_scale && row_ok) ? __ldg(ep.row_scale + (row / ep.rows_per_group)) : 1.f;
+                const float rs = (ep.row_scale && row_ok) ? __ldg(ep.row_scale + fd_div((uint32_t)row, p.fd_rpg)) : 1.f;
+                // global pixel index of the 8 staged rows this lane stores (rows 4*i + lane/8 of the warp's quarter)
+                int pix[8];
+                unsigned okmask = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = r0 + 4 * i + (lane >> 3);
+                    const int yy = t.y0 + (rl >> p.bw_shift), xx = t.x0 + (rl & (p.BW - 1));
+                    pix[i] = (t.b * p.H + yy) * p.W + xx;
+                    if (yy < p.H && xx < p.W) okmask |= 1u << i;
+                }
                 for (int pp = cpart; pp < pairs; pp += EPI_WARPS / 4) {
                     const int cb = pp * 64;
                     const int nb = t.n0 + cb;
                     if (nb >= p.N) break;
-                    // A 64-column store that would run past this tile's BN columns into the NEXT tile's columns (BN not a
-                    // multiple of 64, e.g. 208 or 240) must not go through TMA: it would race with that tile's owner.  The
-                    // few valid columns of such a partial pair leave through per-lane 16-byte stores instead.
-                    const bool use_tma = (cb + 64 <= BN) || (t.n0 + BN >= p.N);
+                    // columns of this pair that belong to the tile and the matrix (8-column groups are all-or-nothing)
+                    const int col_end = (t.n0 + BN < p.N) ? t.n0 + BN : p.N;
                     uint4 extra[8];
                     if (esrc) {
                         if (p.ks == 1 && p.batch == 1 && p.H == 1) {
@@ -536,27 +552,28 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
                             }
-                            if (use_tma) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)(4 * h + j) ^ sw) << 4), pack8(v + 8 * j));
-                            } else if (row_ok && c0 < BN) {
-                                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(pre ? ep.out_pre : ep.out) +
-                                                   row * (pre ? ep.ld_pre : ep.ldo) + t.n0 + c0;
+                            for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)(4 * h + j) ^ sw) << 4), pack8(v + 8 * j));
+                        }
+                        // the staged 32 x 64 tile leaves as full 128-byte rows: 8 lanes per row, 4 rows per store instruction
+                        __syncwarp();
+                        {
+                            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(pre ? ep.out_pre : ep.out);
+                            const long long old_ = pre ? ep.ld_pre : ep.ldo;
+                            const int seg = lane & 7;
+                            const int col = nb + seg * 8;
+                            if (col < col_end) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    if (c0 + 8 * j < BN && t.n0 + c0 + 8 * j < p.N) *reinterpret_cast<uint4*>(o + 8 * j) = pack8(v + 8 * j);
+                                for (int i = 0; i < 8; ++i) {
+                                    const int rr = 4 * i + (lane >> 3);
+                                    if (okmask & (1u << i)) {
+                                        const uint4 val = lds128(wb + (uint32_t)rr * 128u + (((uint32_t)seg ^ (uint32_t)(rr & 7)) << 4));
+                                        *reinterpret_cast<uint4*>(obase + (long long)pix[i] * old_ + col) = val;
+                                    }
+                                }
                             }
                         }
-                        if (use_tma) {
-                            fence_async_smem();
-                            __syncwarp();
-                            if (lane == 0) {
-                                tma_store_4d(pre ? &mapPre : &mapOut, wb, nb, cx, cy, t.b);
-                                bulk_commit();
-                                bulk_wait_read0();     // the tile may be overwritten once the TMA unit has read it
-                            }
-                            __syncwarp();
-                        }
+                        __syncwarp();      // the tile is free again
                     }
                 }
             } else
@@ -654,7 +671,6 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
     }
 
-    if (warp >= 4 && lane == 0 && p.tma_store) bulk_wait0();   // all TMA stores of this warp have completed
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -730,8 +746,7 @@ void pick_box(int W, int H, int pixels, int* bw_out, int* bh_out) {
     }
 }
 
-int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapOut, const CUtensorMap& mapPre, TcParams& p,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaStream_t stream) {
     static bool attr_set = false;
     const int smem = MAX_SMEM + 1024 + EPI_WARPS * EPI_TILE_BYTES + 256;
     if (!attr_set) {
@@ -739,6 +754,13 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& 
         VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
         attr_set = true;
     }
+    VK_REQUIRE(p.units < (1LL << 31), VKOCR_BAD_SHAPE, "gemm_tc: %lld work units", p.units);
+    p.fd_n = make_fastdiv((uint32_t)p.n_tiles);
+    p.fd_x = make_fastdiv((uint32_t)(p.tiles_x > 0 ? p.tiles_x : 1));
+    p.fd_y = make_fastdiv((uint32_t)(p.tiles_y > 0 ? p.tiles_y : 1));
+    p.fd_i = make_fastdiv((uint32_t)(p.i_tiles > 0 ? p.i_tiles : 1));
+    p.fd_taps = make_fastdiv((uint32_t)(p.ks * p.ks));
+    p.fd_rpg = make_fastdiv((uint32_t)(p.ep.rows_per_group > 0 ? p.ep.rows_per_group : 1));
     p.num_stages = MAX_SMEM / p.stage_bytes;
     if (p.num_stages > 8) p.num_stages = 8;
     if (p.mode == 1)
@@ -747,7 +769,7 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& 
     const long long sms = vkocr_sm_count();
     const int grid = (int)(p.units < sms ? p.units : sms);
     if (grid <= 0) return VKOCR_OK;
-    vkocr_gemm_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, mapOut, mapPre, p);
+    vkocr_gemm_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, p);
     VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
     return VKOCR_OK;
 }
@@ -765,6 +787,7 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     p.mode = 0;
     p.batch = g->batch; p.H = g->H; p.W = g->W; p.ks = g->ks;
     pick_box(g->W, g->H, BM, &p.BW, &p.BH);
+    for (p.bw_shift = 0; (1 << p.bw_shift) < p.BW; ++p.bw_shift) {}
     p.tiles_x = vk_cdiv(g->W, p.BW);
     p.tiles_y = vk_cdiv(g->H, p.BH);
     p.kb_per_tap = g->c_pad / BK;
@@ -789,24 +812,13 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     VK_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, VKOCR_BAD_ALIGN, "packed weight not 16-byte aligned");
     rc = encode_map(&mapB, w_packed, 2, dims, str, box);
     if (rc) return rc;
-    // outputs through TMA stores when they are plain 16-byte-aligned bf16 matrices (every hot-path call); otherwise the
-    // generic per-element epilogue handles them
-    CUtensorMap mapOut = mapA, mapPre = mapA;
-    p.M = g->W;
+    // aligned bf16 outputs (every hot-path call) take the staged epilogue; anything else the generic per-element one
     auto aligned = [](const void* ptr, long long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld & 7) == 0; };
-    p.tma_store = !ep->out_f32 && !ep->accumulate && (N % 8 == 0) && aligned(ep->out, ep->ldo) &&
-                  (!ep->out_pre || aligned(ep->out_pre, ep->ld_pre)) && (!ep->residual || aligned(ep->residual, ep->ld_res)) &&
-                  (ep->act != 2 || aligned(ep->aux, ep->ld_aux));
-    if (p.tma_store) {
-        const int bw2 = p.BW < 32 ? p.BW : 32;
-        rc = encode_nhwc(&mapOut, ep->out, N, g->W, g->H, g->batch, ep->ldo, bw2, 32 / bw2);
-        if (rc) return rc;
-        if (ep->out_pre) {
-            rc = encode_nhwc(&mapPre, ep->out_pre, N, g->W, g->H, g->batch, ep->ld_pre, bw2, 32 / bw2);
-            if (rc) return rc;
-        }
-    }
-    return launch(mapA, mapB, mapOut, mapPre, p, stream);
+    p.M = g->W;
+    p.staged_store = !ep->out_f32 && !ep->accumulate && (N % 8 == 0) && aligned(ep->out, ep->ldo) &&
+                     (!ep->out_pre || aligned(ep->out_pre, ep->ld_pre)) && (!ep->residual || aligned(ep->residual, ep->ld_res)) &&
+                     (ep->act != 2 || aligned(ep->aux, ep->ld_aux)) && (long long)g->batch * g->H * g->W < (1LL << 31);
+    return launch(mapA, mapB, p, stream);
 }
 
 // TN: G[tap,i,j] += sum_pix P[pix,i] * Q[pix+off(tap), j]   (bf16 in, fp32 out accumulated with red.add)
@@ -890,6 +902,6 @@ int vkocr_gemm_tc_tn(const void* pmat, const VkocrConvGeom* g, const void* qmat,
     if (rc) return rc;
     rc = encode_nhwc(&mapB, qmat, J, g->W, g->H, g->batch, ld_q, p.BW, p.BH);
     if (rc) return rc;
-    p.tma_store = 0;
-    return launch(mapA, mapB, mapA, mapA, p, stream);
+    p.staged_store = 0;
+    return launch(mapA, mapB, p, stream);
 }
