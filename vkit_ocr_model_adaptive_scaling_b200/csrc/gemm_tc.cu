@@ -8,7 +8,7 @@
 //   warp 1 (1 lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN (16..256), K=16 per instruction,
 //                    accumulators double-buffered in TMEM (2 x 256 columns).
 //   warp 2           TMEM allocator.
-//   warps 4..11      epilogue: tcgen05.ld -> registers -> bias / GELU / layer-scale / residual -> 32 x 64 tile staged in
+//   warps 4..15      epilogue: tcgen05.ld -> registers -> bias / GELU / layer-scale / residual -> 32 x 64 tile staged in
 //                    shared memory -> coalesced 128-byte-row global stores.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
 //
@@ -25,9 +25,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements in one 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int MAX_SMEM = 192 * 1024;  // operand stages
-constexpr int EPI_TILE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B staging tile (row-per-lane in, 4 full rows per store out)
-constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
-constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int EPI_TILE_BYTES = 2048;  // per epilogue warp: 32 rows x 64 B staging tile (row-per-lane in, 8 row segments per store out)
+constexpr int NUM_THREADS = 512;         // warps 0-3: TMA / MMA / TMEM alloc / second TMA producer; warps 4-15: epilogue
+constexpr int EPI_WARPS = 12;            // three warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 
@@ -427,149 +427,124 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const bool vec_ok = (p.mode == 0) && (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
                                 (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0);
             if (p.staged_store) {
-                // ---- fast path: each lane finishes its row in registers, the warp's 32 x 64 tile is staged in shared memory
-                // (128-byte swizzle, conflict-free) and leaves as ONE TMA store: full 128-byte lines per row, rows/columns
-                // outside the tensor clipped by the TMA unit.  (Per-lane 16-byte global stores of row-strided data cap
-                // near 1.2 TB/s per chip.)
+                // ---- fast path, one 32-column chunk at a time: each lane finishes its row in registers (bias, GELU / GELU',
+                // layer scale, drop-path mask, residual), the warp's 32 x 32 tile is staged in shared memory (64-byte rows,
+                // XOR-swizzled: conflict-free both ways) and leaves as coalesced 64-byte row segments, 8 rows per store
+                // instruction.  Residual / GELU' operands come in the same way, transposed through the tile.
                 const uint32_t wb = epi_base + (uint32_t)(warp - 4) * (uint32_t)EPI_TILE_BYTES;
-                const uint32_t my_row = wb + (uint32_t)lane * 128u;
-                const uint32_t sw = (uint32_t)(lane & 7);
+                const uint32_t my_row = wb + (uint32_t)lane * 64u;
+                const uint32_t sw = (uint32_t)((lane >> 1) & 3);
                 const int r0 = q * 32;
-                const int pairs = (BN + 63) / 64;
                 const __nv_bfloat16* esrc = ep.residual ? reinterpret_cast<const __nv_bfloat16*>(ep.residual)
                                                         : (ep.act == 2 ? reinterpret_cast<const __nv_bfloat16*>(ep.aux) : nullptr);
                 const long long eld = ep.residual ? ep.ld_res : ep.ld_aux;
                 const float rs = (ep.row_scale && row_ok) ? __ldg(ep.row_scale + fd_div((uint32_t)row, p.fd_rpg)) : 1.f;
-                // global pixel index of the 8 staged rows this lane stores (rows 4*i + lane/8 of the warp's quarter)
-                int pix[8];
+                // global pixel index of the 4 staged rows this lane moves (rows 8*i + lane/4 of the warp's quarter)
+                int pix[4];
                 unsigned okmask = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rl = r0 + 4 * i + (lane >> 3);
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = r0 + 8 * i + (lane >> 2);
                     const int yy = t.y0 + (rl >> p.bw_shift), xx = t.x0 + (rl & (p.BW - 1));
                     pix[i] = (t.b * p.H + yy) * p.W + xx;
                     if (yy < p.H && xx < p.W) okmask |= 1u << i;
                 }
-                for (int pp = cpart; pp < pairs; pp += EPI_WARPS / 4) {
-                    const int cb = pp * 64;
+                const int seg = lane & 3;
+                const int col_end = (t.n0 + BN < p.N) ? t.n0 + BN : p.N;   // 8-column groups are all-or-nothing
+                for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
+                    const int cb = c * 32;
                     const int nb = t.n0 + cb;
-                    if (nb >= p.N) break;
-                    // columns of this pair that belong to the tile and the matrix (8-column groups are all-or-nothing)
-                    const int col_end = (t.n0 + BN < p.N) ? t.n0 + BN : p.N;
-                    uint4 extra[8];
+                    if (nb >= col_end) break;
+                    const int col = nb + seg * 8;
+                    uint4 extra[4];
                     if (esrc) {
-                        if (p.ks == 1 && p.batch == 1 && p.H == 1) {
-                            // rows of a plain GEMM are consecutive: coalesced 128-byte row reads, transposed through the tile
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int rr = 4 * i + (lane >> 3);
-                                const int seg = lane & 7;
-                                const long long m = (long long)t.x0 + r0 + rr;
-                                const int col = nb + seg * 8;
-                                uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                                if (m < p.M && col < p.N) val = __ldg(reinterpret_cast<const uint4*>(esrc + m * eld + col));
-                                sts128(wb + (uint32_t)rr * 128u + (((uint32_t)seg ^ (uint32_t)(rr & 7)) << 4), val);
-                            }
-                            __syncwarp();
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) extra[j] = lds128(my_row + (((uint32_t)j ^ sw) << 4));
-                            __syncwarp();
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int col = nb + j * 8;
-                                extra[j] = (row_ok && col < p.N) ? __ldg(reinterpret_cast<const uint4*>(esrc + row * eld + col))
-                                                                : make_uint4(0u, 0u, 0u, 0u);
-                            }
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = 8 * i + (lane >> 2);
+                            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                            if ((okmask & (1u << i)) && col < col_end)
+                                val = __ldg(reinterpret_cast<const uint4*>(esrc + (long long)pix[i] * eld + col));
+                            sts128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4), val);
                         }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) extra[j] = lds128(my_row + (((uint32_t)j ^ sw) << 4));
+                        __syncwarp();
                     }
                     const int npass = ep.out_pre ? 2 : 1;
                     for (int pass = 0; pass < npass; ++pass) {
                         const bool pre = ep.out_pre && pass == 0;
+                        float v[32];
+                        {
+                            uint32_t acc[32];
+                            tc_ld32(taddr + (uint32_t)cb, acc);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int c0 = cb + 32 * h;
-                            float v[32];
-                            if (c0 < BN) {
-                                uint32_t acc[32];
-                                tc_ld32(taddr + (uint32_t)c0, acc);
-                                const int nbase = t.n0 + c0;
-                                const bool full = nbase + 32 <= p.N;
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                        }
+                        const bool full = nb + 32 <= p.N;
+                        if (ep.bias) {
+                            if (full) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                                if (ep.bias) {
-                                    if (full) {
-#pragma unroll
-                                        for (int j = 0; j < 32; j += 4) {
-                                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nbase + j));
-                                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                                        }
-                                    } else {
-#pragma unroll
-                                        for (int j = 0; j < 32; ++j) v[j] += (nbase + j < p.N) ? __ldg(ep.bias + nbase + j) : 0.f;
-                                    }
-                                }
-                                if (!pre) {
-                                    if (ep.act == 1) {
-#pragma unroll
-                                        for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
-                                    } else if (ep.act == 2) {
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
-                                            float f[8];
-                                            unpack8(extra[4 * h + j], f);
-#pragma unroll
-                                            for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
-                                        }
-                                    }
-                                    if (ep.col_scale) {
-                                        if (full) {
-#pragma unroll
-                                            for (int j = 0; j < 32; j += 4) {
-                                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nbase + j));
-                                                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-                                            }
-                                        } else {
-#pragma unroll
-                                            for (int j = 0; j < 32; ++j) v[j] *= (nbase + j < p.N) ? __ldg(ep.col_scale + nbase + j) : 0.f;
-                                        }
-                                    }
-                                    if (ep.row_scale) {
-#pragma unroll
-                                        for (int j = 0; j < 32; ++j) v[j] *= rs;
-                                    }
-                                    if (ep.residual) {
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
-                                            float f[8];
-                                            unpack8(extra[4 * h + j], f);
-#pragma unroll
-                                            for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
-                                        }
-                                    }
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+                                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                                 }
                             } else {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                                for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(ep.bias + nb + j) : 0.f;
                             }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)(4 * h + j) ^ sw) << 4), pack8(v + 8 * j));
                         }
-                        // the staged 32 x 64 tile leaves as full 128-byte rows: 8 lanes per row, 4 rows per store instruction
+                        if (!pre) {
+                            if (ep.act == 1) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
+                            } else if (ep.act == 2) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float f[8];
+                                    unpack8(extra[j], f);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
+                                }
+                            }
+                            if (ep.col_scale) {
+                                if (full) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 4) {
+                                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nb + j));
+                                        v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] *= (nb + j < p.N) ? __ldg(ep.col_scale + nb + j) : 0.f;
+                                }
+                            }
+                            if (ep.row_scale) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] *= rs;
+                            }
+                            if (ep.residual) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float f[8];
+                                    unpack8(extra[j], f);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pack8(v + 8 * j));
                         __syncwarp();
-                        {
+                        if (col < col_end) {
                             __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(pre ? ep.out_pre : ep.out);
                             const long long old_ = pre ? ep.ld_pre : ep.ldo;
-                            const int seg = lane & 7;
-                            const int col = nb + seg * 8;
-                            if (col < col_end) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int rr = 4 * i + (lane >> 3);
-                                    if (okmask & (1u << i)) {
-                                        const uint4 val = lds128(wb + (uint32_t)rr * 128u + (((uint32_t)seg ^ (uint32_t)(rr & 7)) << 4));
-                                        *reinterpret_cast<uint4*>(obase + (long long)pix[i] * old_ + col) = val;
-                                    }
+                            for (int i = 0; i < 4; ++i) {
+                                const int rr = 8 * i + (lane >> 2);
+                                if (okmask & (1u << i)) {
+                                    const uint4 val = lds128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4));
+                                    *reinterpret_cast<uint4*>(obase + (long long)pix[i] * old_ + col) = val;
                                 }
                             }
                         }
