@@ -341,9 +341,15 @@ def run_ours(args) -> None:
         label, row = max(gemm_table.items(), key=lambda kv: kv[1]['ms'])
         per_launch_ms = row['ms'] / row['calls']
         achieved = row['flops'] / row['calls'] / (per_launch_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+                traffic = json.load(f).get(label)      # DRAM bytes per launch from the committed ncu --set full capture
+        except OSError:
+            pass
         roofline = {'bound': 'tensor', 'kernel': f'vkocr_gemm_tc_kernel [{label}]', 'achieved': achieved,
                     'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops_sustained'],
-                    'traffic': None, 'peak_source': f'{peaks["source"]} sustained bf16 (kernel timed inside a long step)',
+                    'traffic': traffic, 'peak_source': f'{peaks["source"]} sustained bf16 (kernel timed inside a long step)',
                     'launch_ms': per_launch_ms, 'share_of_step': row['ms'] / args.steps / ms,
                     'all_gemm_share_of_step': sum(r['ms'] for r in gemm_table.values()) / args.steps / ms,
                     'all_gemm_tflops': sum(r['flops'] for r in gemm_table.values()) / sum(r['ms'] for r in gemm_table.values()) / 1e9}

@@ -856,18 +856,21 @@ int vkocr_gemm_tc_tn(const void* pmat, const VkocrConvGeom* g, const void* qmat,
     const long long pix_tiles = (long long)p.batch * p.tiles_y * p.tiles_x;
     // Split the pixel range so that the units fill whole waves of the persistent grid: every unit costs the same, so the
     // kernel time is ceil(units / SMs) unit times -- 378 units on 148 SMs would idle 15 % of the machine in its last wave.
-    // Candidates: 1..8 waves' worth of splits, keeping >= 8 k-blocks per unit; highest wave efficiency wins, ties go to
-    // the fewest splits (fewest fp32 atomics).
+    // Candidates: 1..8 waves' worth of splits, keeping >= 32 k-blocks per unit; the fewest splits (fewest fp32 atomics)
+    // whose wave efficiency is within 5 % of the best candidate's wins.
     const long long sms = vkocr_sm_count();
-    long long max_splits = pix_tiles / 8;
+    long long max_splits = pix_tiles / 32;           // every unit ends with a 128 x BN tile of fp32 atomics: amortise it
     if (max_splits < 1) max_splits = 1;
-    long long splits = 1;
     double best_eff = -1.0;
-    for (long long cand = 1; cand <= max_splits && cand * out_tiles <= 8 * sms + out_tiles; ++cand) {
+    auto wave_eff = [&](long long cand) {
         const long long units = cand * out_tiles;
-        const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
-        if (eff > best_eff + 1e-9) { best_eff = eff; splits = cand; }
-    }
+        return (double)units / (double)(((units + sms - 1) / sms) * sms);
+    };
+    for (long long cand = 1; cand <= max_splits && cand * out_tiles <= 8 * sms + out_tiles; ++cand)
+        if (wave_eff(cand) > best_eff) best_eff = wave_eff(cand);
+    long long splits = 1;
+    for (long long cand = 1; cand <= max_splits && cand * out_tiles <= 8 * sms + out_tiles; ++cand)
+        if (wave_eff(cand) >= 0.95 * best_eff) { splits = cand; break; }   // fewest splits within 5 % of the best fill
     if (const char* e = getenv("VKOCR_TN_SPLITS")) splits = atoi(e);
     p.splits = (int)splits;
     p.units = out_tiles * splits;
