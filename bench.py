@@ -268,7 +268,7 @@ def run_ours(args) -> None:
     # ---- timed region: device-resident inputs, CUDA events on the launching (current) stream, GEMM launches bracketed
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = L.LIB.vkocr_launch_count()
-    L.LIB.start_profile(only={'vkocr_gemm_nt', 'vkocr_gemm_tn'})
+    L.LIB.start_profile(only={'vkocr_gemm_nt', 'vkocr_gemm_nt_heads', 'vkocr_gemm_tn'})
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.time()

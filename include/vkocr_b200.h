@@ -85,6 +85,28 @@ typedef struct VkocrEpilogue {
 
 int vkocr_gemm_nt(int dtype, int backend, const void* x, const VkocrConvGeom* g, const void* w_packed, int N,
                   const VkocrEpilogue* ep, void* stream);
+
+/* Fused head group: the 3x3 (or 1x1 / 5x5) conv of all heads that read one neck tensor with each head's
+ * LayerNorm -> GELU -> Linear(inner -> out <= 4) (-> Softplus) tail applied in the GEMM epilogue from the fp32
+ * accumulators (UperNextHead.forward model/upernext.py:233-248, FpnHead.forward model/fpn.py:193-208, nn.Softplus
+ * model/adaptive_scaling.py:101,140).  N = num_heads * slot; head h owns columns [h*slot, h*slot + inner[h]).
+ * ep->out (the conv output, needed by the backward) may be NULL for inference. bf16 storage only. */
+#define VKOCR_MAX_HEADS 4
+typedef struct VkocrHeadTail {
+    int num_heads;
+    int slot;
+    long long pixels_per_image;
+    const float* gamma[VKOCR_MAX_HEADS];
+    const float* beta[VKOCR_MAX_HEADS];
+    const float* w2[VKOCR_MAX_HEADS];
+    const float* b2[VKOCR_MAX_HEADS];
+    float* out[VKOCR_MAX_HEADS];
+    int inner[VKOCR_MAX_HEADS];
+    int out_channels[VKOCR_MAX_HEADS];
+    int softplus[VKOCR_MAX_HEADS];
+} VkocrHeadTail;
+int vkocr_gemm_nt_heads(int dtype, const void* x, const VkocrConvGeom* g, const void* w_packed, int N, const VkocrEpilogue* ep,
+                        const VkocrHeadTail* heads, void* stream);
 int vkocr_gemm_tn(int dtype, int backend, const void* pmat, const VkocrConvGeom* g, const void* qmat, int J, long long ld_q,
                   const VkocrEpilogue* ep, void* stream);
 

@@ -47,6 +47,18 @@ class Epilogue(ctypes.Structure):
     ]
 
 
+MAX_HEADS = 4
+
+
+class HeadTail(ctypes.Structure):
+    _fields_ = [
+        ('num_heads', c_int), ('slot', c_int), ('pixels_per_image', c_ll),
+        ('gamma', c_void_p * MAX_HEADS), ('beta', c_void_p * MAX_HEADS), ('w2', c_void_p * MAX_HEADS),
+        ('b2', c_void_p * MAX_HEADS), ('out', c_void_p * MAX_HEADS),
+        ('inner', c_int * MAX_HEADS), ('out_channels', c_int * MAX_HEADS), ('softplus', c_int * MAX_HEADS),
+    ]
+
+
 _P = ctypes.POINTER
 
 # name -> argtypes of every compute entry point declared in include/vkocr_b200.h (all return int status)
@@ -54,6 +66,7 @@ _SIGNATURES = {
     'vkocr_abi_version': [],
     'vkocr_device_check': [c_int],
     'vkocr_gemm_nt': [c_int, c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, _P(Epilogue), c_void_p],
+    'vkocr_gemm_nt_heads': [c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, _P(Epilogue), _P(HeadTail), c_void_p],
     'vkocr_gemm_tn': [c_int, c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, c_ll, _P(Epilogue), c_void_p],
     'vkocr_layernorm_fwd': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_float, c_int,
                             c_void_p, c_void_p, c_void_p],

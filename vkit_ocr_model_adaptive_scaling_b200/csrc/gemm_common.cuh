@@ -39,6 +39,26 @@ struct VkocrEpilogue {
     long long tn_s_tap, tn_s_i, tn_s_j;
 };
 
+// Fused head tail (tcgen05 path only): every N tile of `slot` columns is one head; after the conv bias the epilogue applies
+// LayerNorm(inner) -> exact GELU -> Linear(inner -> O <= 4) (-> Softplus) from the fp32 accumulators and writes the NCHW
+// fp32 prediction map (UperNextHead.forward upernext.py:233-248 / FpnHead.forward fpn.py:193-208, adaptive_scaling.py:
+// 101,140).  The conv output itself is still written to ep.out (storage dtype, needed by the backward) unless ep.out is
+// null (inference).
+#define VKOCR_MAX_HEADS 4
+struct VkocrHeadTail {
+    int num_heads;                         // 0: disabled
+    int slot;                              // columns per head (multiple of 16, <= 256) == the GEMM's N tile
+    long long pixels_per_image;
+    const float* gamma[VKOCR_MAX_HEADS];   // LayerNorm weight / bias [inner]
+    const float* beta[VKOCR_MAX_HEADS];
+    const float* w2[VKOCR_MAX_HEADS];      // [O, inner] row-major
+    const float* b2[VKOCR_MAX_HEADS];      // [O]
+    float* out[VKOCR_MAX_HEADS];           // [batch, O, H, W] fp32
+    int inner[VKOCR_MAX_HEADS];
+    int out_channels[VKOCR_MAX_HEADS];
+    int softplus[VKOCR_MAX_HEADS];
+};
+
 // Apply the epilogue to one accumulator value and return the value to store in `out`.
 // Side effect: writes out_pre when requested.
 template <typename T>

@@ -24,10 +24,12 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements in one 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int MAX_SMEM = 192 * 1024;  // operand stages
+constexpr int MAX_SMEM = 176 * 1024;  // operand stages
 constexpr int EPI_TILE_BYTES = 2048;  // per epilogue warp: 32 rows x 64 B staging tile (row-per-lane in, 8 row segments per store out)
 constexpr int NUM_THREADS = 512;         // warps 0-3: TMA / MMA / TMEM alloc / second TMA producer; warps 4-15: epilogue
 constexpr int EPI_WARPS = 12;            // three warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int HEAD_PAR_BYTES = 7 * 256 * 4;                 // fused head tail: gamma, beta, conv bias, w2[4] of the CTA's head
+constexpr int HEAD_XCH_BYTES = EPI_WARPS * 32 * 6 * 4;      // per-warp partial row statistics (2) and projections (4)
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 
@@ -69,8 +71,10 @@ struct TcParams {
     int staged_store;        // NT: aligned bf16 outputs leave through the shared-memory staging tiles
     int M;                   // NT plain GEMM: number of rows
     long long units;
+    int head_mode;           // NT: fused head tail epilogue (ht valid)
     FastDiv fd_n, fd_x, fd_y, fd_i, fd_taps, fd_rpg;   // n_tiles, tiles_x, tiles_y, i_tiles, ks*ks, rows_per_group
     VkocrEpilogue ep;
+    VkocrHeadTail ht;
 };
 
 // ------------------------------------------------------------------------------------------------- PTX wrappers
@@ -194,7 +198,8 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.num_stages;
     const uint32_t epi_base = smem_base + (uint32_t)S * (uint32_t)p.stage_bytes;   // 1024-byte aligned (stage sizes are)
-    const uint32_t bar_base = epi_base + (uint32_t)(EPI_WARPS * EPI_TILE_BYTES);
+    const uint32_t head_off = (uint32_t)S * (uint32_t)p.stage_bytes + (uint32_t)(EPI_WARPS * EPI_TILE_BYTES);   // from smem_base
+    const uint32_t bar_base = smem_base + head_off + (uint32_t)(HEAD_PAR_BYTES + HEAD_XCH_BYTES);
     // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base address word
     auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
@@ -237,7 +242,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
     // unit -> coordinates
     struct Unit {
-        int n0, b, y0, x0;          // NT
+        int n0, nt, b, y0, x0;      // NT
         int tap, i0, kt_begin, kt_end;  // TN
         int num_kb;
     };
@@ -250,6 +255,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             fd_divmod(mt, p.fd_x, &mt, &tx);
             fd_divmod(mt, p.fd_y, &b, &ty);
             t.b = (int)b;
+            t.nt = (int)nt;
             t.n0 = (int)nt * BN;
             t.x0 = (int)tx * p.BW;
             t.y0 = (int)ty * p.BH;
@@ -266,7 +272,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             t.kt_begin = (int)((long long)pix_tiles * sp / p.splits);
             t.kt_end = (int)((long long)pix_tiles * (sp + 1) / p.splits);
             t.num_kb = t.kt_end - t.kt_begin;
-            t.b = 0; t.y0 = 0; t.x0 = 0;
+            t.b = 0; t.y0 = 0; t.x0 = 0; t.nt = 0;
         }
         return t;
     };
@@ -408,6 +414,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         uint32_t aph = 0;
         const VkocrEpilogue& ep = p.ep;
         const int chunks = (BN + 31) / 32;
+        int cur_head = -1;
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit t = decode(u);
             bool row_ok;
@@ -426,7 +433,145 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
             const bool vec_ok = (p.mode == 0) && (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
                                 (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0);
-            if (p.staged_store) {
+            if (p.head_mode) {
+                // ---- fused head tail (one head per N tile): conv bias -> [conv output stored for the backward] ->
+                // LayerNorm over the head's `inner` columns -> exact GELU -> projection to O <= 4 maps (-> Softplus), all
+                // from the fp32 accumulators.  The three warps of a TMEM lane quarter split the columns; partial row
+                // statistics and partial projections are exchanged through shared memory with a 96-thread named barrier.
+                const VkocrHeadTail& ht = p.ht;
+                uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+                float* s_par = reinterpret_cast<float*>(smem_gen + head_off);                       // [7][256]
+                float* s_xs = reinterpret_cast<float*>(smem_gen + head_off + HEAD_PAR_BYTES);       // [EPI_WARPS][32][2]
+                float* s_xd = s_xs + EPI_WARPS * 32 * 2;                                            // [EPI_WARPS][32][4]
+                const int head = t.nt;
+                const int inner = ht.inner[head], O = ht.out_channels[head];
+                if (head != cur_head) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // nobody still reads the old parameters
+                    for (int c = (int)threadIdx.x - 128; c < 256; c += 32 * EPI_WARPS) {
+                        const bool ok = c < inner;
+                        s_par[c] = ok ? __ldg(ht.gamma[head] + c) : 0.f;
+                        s_par[256 + c] = ok ? __ldg(ht.beta[head] + c) : 0.f;
+                        s_par[512 + c] = (ep.bias && c < BN && t.n0 + c < p.N) ? __ldg(ep.bias + t.n0 + c) : 0.f;
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) s_par[(3 + o) * 256 + c] = (ok && o < O) ? __ldg(ht.w2[head] + (long long)o * inner + c) : 0.f;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+                    cur_head = head;
+                }
+                const int wi = warp - 4;
+                const uint32_t wb = epi_base + (uint32_t)wi * (uint32_t)EPI_TILE_BYTES;
+                const uint32_t my_row = wb + (uint32_t)lane * 64u;
+                const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+                const int r0 = q * 32;
+                const int seg = lane & 3;
+                const bool store_conv = ep.out != nullptr;
+                int pix[4];
+                unsigned okmask = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = r0 + 8 * i + (lane >> 2);
+                    const int yy = t.y0 + (rl >> p.bw_shift), xx = t.x0 + (rl & (p.BW - 1));
+                    pix[i] = (t.b * p.H + yy) * p.W + xx;
+                    if (yy < p.H && xx < p.W) okmask |= 1u << i;
+                }
+                const int col_end = (t.n0 + BN < p.N) ? t.n0 + BN : p.N;
+                // phase 1: statistics (+ conv output store)
+                float rsum = 0.f, rsq = 0.f;
+                for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
+                    const int cb = c * 32;
+                    float v[32];
+                    {
+                        uint32_t acc[32];
+                        tc_ld32(taddr + (uint32_t)cb, acc);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_par + 512 + cb + j);
+                            v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
+                            v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x_ = (cb + j < inner) ? v[j] : 0.f;      // pad columns of the slot hold exact zeros anyway
+                        rsum += x_;
+                        rsq = fmaf(x_, x_, rsq);
+                    }
+                    if (store_conv) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pack8(v + 8 * j));
+                        __syncwarp();
+                        const int col = t.n0 + cb + seg * 8;
+                        if (col < col_end) {
+                            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(ep.out);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int rr = 8 * i + (lane >> 2);
+                                if (okmask & (1u << i)) {
+                                    const uint4 val = lds128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4));
+                                    *reinterpret_cast<uint4*>(obase + (long long)pix[i] * ep.ldo + col) = val;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                s_xs[(wi * 32 + lane) * 2] = rsum;
+                s_xs[(wi * 32 + lane) * 2 + 1] = rsq;
+                asm volatile("bar.sync %0, 96;" ::"r"(2 + q) : "memory");
+                float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < EPI_WARPS / 4; ++k) {
+                    S1 += s_xs[((q + 4 * k) * 32 + lane) * 2];
+                    S2 += s_xs[((q + 4 * k) * 32 + lane) * 2 + 1];
+                }
+                const float inv = 1.f / (float)inner;
+                const float mean = S1 * inv;
+                const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, S2 * inv), 0.f) + 1e-6f);
+                const float shift = -mean * rstd;
+                // phase 2: normalise, GELU, project
+                float dot[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
+                    const int cb = c * 32;
+                    if (cb >= inner) break;
+                    uint32_t acc[32];
+                    tc_ld32(taddr + (uint32_t)cb, acc);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_par + 512 + cb + j);
+                        const float4 g4 = *reinterpret_cast<const float4*>(s_par + cb + j);
+                        const float4 e4 = *reinterpret_cast<const float4*>(s_par + 256 + cb + j);
+                        float z[4];
+                        z[0] = fmaf(fmaf(__uint_as_float(acc[j]) + b4.x, rstd, shift), g4.x, e4.x);
+                        z[1] = fmaf(fmaf(__uint_as_float(acc[j + 1]) + b4.y, rstd, shift), g4.y, e4.y);
+                        z[2] = fmaf(fmaf(__uint_as_float(acc[j + 2]) + b4.z, rstd, shift), g4.z, e4.z);
+                        z[3] = fmaf(fmaf(__uint_as_float(acc[j + 3]) + b4.w, rstd, shift), g4.w, e4.w);
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(s_par + (3 + o) * 256 + cb + j);   // zero beyond inner / O
+                            dot[o] = fmaf(vk_gelu(z[0]), w4.x, dot[o]);
+                            dot[o] = fmaf(vk_gelu(z[1]), w4.y, dot[o]);
+                            dot[o] = fmaf(vk_gelu(z[2]), w4.z, dot[o]);
+                            dot[o] = fmaf(vk_gelu(z[3]), w4.w, dot[o]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) s_xd[(wi * 32 + lane) * 4 + o] = dot[o];
+                asm volatile("bar.sync %0, 96;" ::"r"(2 + q) : "memory");
+                if (cpart == 0 && row_ok) {
+                    const int yy = t.y0 + (r >> p.bw_shift), xx = t.x0 + (r & (p.BW - 1));
+                    const long long pin = (long long)yy * p.W + xx;
+                    for (int o = 0; o < O; ++o) {
+                        float val = __ldg(ht.b2[head] + o);
+#pragma unroll
+                        for (int k = 0; k < EPI_WARPS / 4; ++k) val += s_xd[((q + 4 * k) * 32 + lane) * 4 + o];
+                        if (ht.softplus[head]) val = vk_softplus(val);
+                        ht.out[head][((long long)t.b * O + o) * ht.pixels_per_image + pin] = val;
+                    }
+                }
+                // the exchange buffers are rewritten only after the next tile's phase 1, which every warp of the quarter
+                // reaches after this point; the cpart-0 reader above is ordered by the next tile's first named barrier
+            } else if (p.staged_store) {
                 // ---- fast path, one 32-column chunk at a time: each lane finishes its row in registers (bias, GELU / GELU',
                 // layer scale, drop-path mask, residual), the warp's 32 x 32 tile is staged in shared memory (64-byte rows,
                 // XOR-swizzled: conflict-free both ways) and leaves as coalesced 64-byte row segments, 8 rows per store
@@ -723,7 +868,7 @@ void pick_box(int W, int H, int pixels, int* bw_out, int* bh_out) {
 
 int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaStream_t stream) {
     static bool attr_set = false;
-    const int smem = MAX_SMEM + 1024 + EPI_WARPS * EPI_TILE_BYTES + 256;
+    const int smem = MAX_SMEM + 1024 + EPI_WARPS * EPI_TILE_BYTES + HEAD_PAR_BYTES + HEAD_XCH_BYTES + 256;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(vkocr_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
@@ -753,7 +898,7 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaSt
 
 // NT: D[m,n] = sum_{tap,c} X[pix(m)+off(tap), c] * Wp[n, tap*c_pad + c]   (bf16 in, fp32 accumulate)
 int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed, int N, const VkocrEpilogue* ep,
-                     cudaStream_t stream) {
+                     const VkocrHeadTail* heads, cudaStream_t stream) {
     VK_REQUIRE(g->ks == 1 || g->ks == 3 || g->ks == 5, VKOCR_BAD_SHAPE, "gemm_tc_nt: kernel size %d", g->ks);
     VK_REQUIRE(g->c_pad % BK == 0 && g->c_pad >= g->C, VKOCR_BAD_SHAPE, "gemm_tc_nt: c_pad %d (C %d)", g->c_pad, g->C);
     VK_REQUIRE(N >= 1, VKOCR_BAD_SHAPE, "gemm_tc_nt: N %d", N);
@@ -773,6 +918,11 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     // prefer a multiple of 64 (whole 128-byte TMA store rows) when it does not add padded columns: 1152 -> 6 x 192
     for (int cand = 256; cand >= 128 && n_tiles > 1; cand -= 64)
         if ((long long)vk_cdiv(N, cand) * cand <= (long long)vk_cdiv(N, p.BN) * p.BN) { p.BN = cand; break; }
+    if (heads) {
+        p.BN = heads->slot;          // one head per N tile
+        p.head_mode = 1;
+        p.ht = *heads;
+    }
     p.n_tiles = vk_cdiv(N, p.BN);
     p.stage_bytes = A_BYTES + p.BN * 128;
     p.units = (long long)p.batch * p.tiles_y * p.tiles_x * p.n_tiles;

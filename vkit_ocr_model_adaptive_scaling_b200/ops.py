@@ -707,21 +707,40 @@ class HeadGroupFn(torch.autograd.Function):
         bias = torch.zeros(ntot, dtype=torch.float32, device=dev)
         for i, hd in enumerate(heads):
             bias[i * slot:i * slot + inners[i]].copy_(hd[1].detach())   # tiny staging copy of the conv biases
-        conv = alloc_nhwc(B, H, W, ntot, dt, dev)
-        gemm_nt(up, B, H, W, C, up.stride(3), ks, wp, c_pad, ntot, _epilogue(conv, conv.stride(3), bias=bias))
-        outs = []
+        train = _needs_grad(ctx)
         M = B * H * W
-        for i, hd in enumerate(heads):
-            O = int(hd[4].shape[0])
-            out = torch.empty((B, O, H, W), dtype=torch.float32, device=dev)
-            sl = conv[:, i * slot:(i + 1) * slot]
+        outs = [torch.empty((B, int(hd[4].shape[0]), H, W), dtype=torch.float32, device=dev) for hd in heads]
+        fused = dt == torch.bfloat16 and SIMT_BACKEND == 0 and nh <= L.MAX_HEADS and slot <= 256
+        if fused:
+            # conv + every head's LayerNorm/GELU/projection(/Softplus) in ONE tcgen05 GEMM: the tails run in the epilogue on
+            # the fp32 accumulators; the bf16 conv output is only written when the backward will need it
+            conv = alloc_nhwc(B, H, W, ntot, dt, dev) if train else None
+            ht = L.HeadTail()
+            ht.num_heads, ht.slot, ht.pixels_per_image = nh, slot, H * W
+            for i, hd in enumerate(heads):
+                ht.gamma[i], ht.beta[i] = hd[2].detach().data_ptr(), hd[3].detach().data_ptr()
+                ht.w2[i], ht.b2[i] = hd[4].detach().data_ptr(), hd[5].detach().data_ptr()
+                ht.out[i] = outs[i].data_ptr()
+                ht.inner[i], ht.out_channels[i], ht.softplus[i] = inners[i], int(hd[4].shape[0]), int(softplus[i])
             if L.PROFILE.active:
-                L.PROFILE.note(f'head_tail_fwd rows{M} inner{inners[i]} O{O}', 0.0, M * (slot * conv.element_size() + 4 * O))
-            L.check(L.LIB.vkocr_head_tail_fwd(_tag(dt), L.ptr(sl), conv.stride(3), inners[i], slot, L.ptr(hd[2].detach()),
-                                              L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), L.ptr(hd[5].detach()), O,
-                                              int(softplus[i]), L.ptr(out), H * W, M, _s()), 'head_tail_fwd')
-            outs.append(out)
-        if _needs_grad(ctx):
+                L.PROFILE.note(f'gemm_nt_heads ks{ks} M{M} K{ks * ks * C} N{ntot}', 2.0 * M * ks * ks * C * ntot)
+            g = L.ConvGeom(B, H, W, ks, C, up.stride(3), c_pad)
+            ep = L.Epilogue(None if conv is None else conv.data_ptr(), ntot if conv is None else conv.stride(3), 0, 0, None, 0,
+                            bias.data_ptr(), 0, None, None, 1, None, 0, None, 0, 0, 0, 0)
+            L.check(L.LIB.vkocr_gemm_nt_heads(_tag(dt), L.ptr(up), ctypes.byref(g), L.ptr(wp), ntot, ctypes.byref(ep), ctypes.byref(ht),
+                                              _s()), 'gemm_nt_heads')
+        else:
+            conv = alloc_nhwc(B, H, W, ntot, dt, dev)
+            gemm_nt(up, B, H, W, C, up.stride(3), ks, wp, c_pad, ntot, _epilogue(conv, conv.stride(3), bias=bias))
+            for i, hd in enumerate(heads):
+                O = int(hd[4].shape[0])
+                sl = conv[:, i * slot:(i + 1) * slot]
+                if L.PROFILE.active:
+                    L.PROFILE.note(f'head_tail_fwd rows{M} inner{inners[i]} O{O}', 0.0, M * (slot * conv.element_size() + 4 * O))
+                L.check(L.LIB.vkocr_head_tail_fwd(_tag(dt), L.ptr(sl), conv.stride(3), inners[i], slot, L.ptr(hd[2].detach()),
+                                                  L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), L.ptr(hd[5].detach()), O,
+                                                  int(softplus[i]), L.ptr(outs[i]), H * W, M, _s()), 'head_tail_fwd')
+        if train:
             ctx.save_for_backward(x, up, conv, *outs, *params)
             ctx.meta = (nh, factor, mode, tuple(softplus), slot, ks)
         else:
