@@ -11,7 +11,8 @@ B precise synthetic images per GPU; "images/sec" = B * N / step time (image pair
 with torchrun (one rank per GPU, NCCL); the gradient all-reduce is bucketed and overlapped (parallel.py).
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event timed, max over ranks.  `e2e`: the same step
-through the public API from pinned HOST buffers (H2D of both batches and D2H of both losses inside the timed region).
+through the public API from pinned HOST buffers (per step one H2D copy of both batches, issued on a copy stream one step
+ahead like a training input pipeline, and a D2H read of both losses; all inside the timed region).
 `roofline`: the dominant kernel (the tcgen05 implicit-GEMM 3x3 convolution of the precise head group), algorithmic
 FLOPs / CUDA-event duration measured inside the timed region, against MEASURED_PEAKS.json.  `cpu_baseline`: the oracle
 (port of the reference algorithm, plain fp32 PyTorch) on the host cores over a bounded sample.
@@ -293,16 +294,37 @@ def run_ours(args) -> None:
     e2e = None
     if not args.no_e2e:
         loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+
+        def stage():
+            """H2D copy of one step's rough + precise batch on the copy stream (the input pipeline of a training loop:
+            the next step's batch is in flight while the current step computes)."""
+            with torch.cuda.stream(copy_stream):
+                r, p_ = batch_to_device(rb_host, dev), batch_to_device(pb_host, dev)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            for d in (r, p_):
+                for v in d.values():
+                    if isinstance(v, torch.Tensor):
+                        v.record_stream(main_stream)
+            return r, p_, ev
+
         for _ in range(2):
-            a, b = step(batch_to_device(rb_host, dev), batch_to_device(pb_host, dev))
+            r, p_, ev = stage()
+            main_stream.wait_event(ev)
+            a, b = step(r, p_)
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            rdev = batch_to_device(rb_host, dev)
-            pdev = batch_to_device(pb_host, dev)
+        nxt = stage()                                       # step 0's copy is exposed; every later copy overlaps a step
+        for i in range(args.steps):
+            rdev, pdev, ev = nxt
+            main_stream.wait_event(ev)
+            if i + 1 < args.steps:
+                nxt = stage()
             a, b = step(rdev, pdev)
             loss_host.copy_(torch.stack([a.float().reshape(()), b.float().reshape(())]), non_blocking=True)
-            torch.cuda.current_stream().synchronize()   # the caller reads the step's losses (train.py:415,453)
+            main_stream.synchronize()                       # the caller reads the step's losses (train.py:415,453)
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1) / args.steps

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     """ctypes mirrors of VkocrConvGeom / VkocrEpilogue have the field order of the header."""
     from vkit_ocr_model_adaptive_scaling_b200 import _lib
     text = open(os.path.join(ROOT, 'include', 'vkocr_b200.h')).read()
-    for cname, cls in (('VkocrConvGeom', _lib.ConvGeom), ('VkocrEpilogue', _lib.Epilogue)):
+    for cname, cls in (('VkocrConvGeom', _lib.ConvGeom), ('VkocrEpilogue', _lib.Epilogue), ('VkocrHeadTail', _lib.HeadTail)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), text, flags=re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
         fields = []
@@ -44,8 +44,8 @@ def test_struct_layouts_match_header():
                 continue
             names = decl.split(',')
             first = names[0].split()[-1]
-            fields.append(first.lstrip('*'))
-            fields.extend(n.strip().lstrip('*') for n in names[1:])
+            fields.append(re.sub(r'\[.*?\]', '', first.lstrip('*')))
+            fields.extend(re.sub(r'\[.*?\]', '', n.strip().lstrip('*')) for n in names[1:])
         assert fields == [f[0] for f in cls._fields_], (cname, fields)
 
 
