@@ -210,3 +210,39 @@ def test_state_dict_round_trip_and_shapes(vk):
     clone = _build(vk, 'upernext')
     clone.load_state_dict(sd, strict=True)
     assert all(v.dtype == torch.float32 for v in sd.values())
+
+
+@pytest.mark.parametrize('size,neck', [('base', 'fpn'), ('small', 'upernext')])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_larger_configs_against_oracle(vk, size, neck, dtype):
+    """The other `create_*` sizes of the reference (convnext.py:188-225): BASE has 128..1024 channels, so the heads'
+    inner width (256 + out)/2 no longer fits one 256-column tile and the head group takes the unfused tail; SMALL has a
+    27-layer stage.  Forward outputs, both losses and every gradient against the oracle at a small image."""
+    from oracle import loss as ol
+    from oracle import model as om
+    from oracle import synth
+    from vkit_ocr_model_adaptive_scaling_b200.training import train_step
+    dev = torch.device('cuda')
+    B, H, W, P = 1, 64, 96, 8
+    model = _build(vk, neck, size)
+    model.load_state_dict(synth.synth_state_dict(size, neck, seed=11), strict=True)
+    model.to(dev).eval()
+    params = oracle_params(model)
+    rb = _to(synth.synth_rough_batch(B, H, W, seed=5, inset=2), dev)
+    pb = _to(synth.synth_precise_batch(B, H, W, points=P, seed=5, inset=2), dev)
+    lf = vk.loss_function
+    rough_fn = lf.AdaptiveScalingRoughLossFunction(lf.AdaptiveScalingRoughLossFunctionConifg())
+    precise_fn = lf.AdaptiveScalingPreciseLossFunction(lf.AdaptiveScalingPreciseLossFunctionConifg())
+    with vk.precision(dtype):
+        rl, pl = train_step(model, rough_fn, precise_fn, rb, pb)
+    f64 = lambda d: {k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in d.items()}
+    rb, pb = f64(rb), f64(pb)
+    rl_ref = ol.rough_loss(*om.forward_rough(params, rb['image']), *(rb[k] for k in ROUGH_KEYS))
+    (rl_ref / 2).backward()
+    pl_ref = ol.precise_loss(None, *om.forward_precise(params, pb['image']), *(pb[k] for k in PRECISE_KEYS))
+    (pl_ref / 2).backward()
+    tol = TOL[dtype]
+    assert abs(float(rl) - float(rl_ref)) <= tol * abs(float(rl_ref)), (float(rl), float(rl_ref))
+    assert abs(float(pl) - float(pl_ref)) <= tol * abs(float(pl_ref)), (float(pl), float(pl_ref))
+    # bf16: the 40-layer SMALL / 1024-channel BASE chains are deeper than TINY's; same yardstick rule as the step test
+    compare_grads(model, params, dtype, f'{size}/{neck} step', yardstick=4e-2 if dtype == torch.bfloat16 else None)
