@@ -402,6 +402,40 @@ patchify_image_kernel(const float* __restrict__ img, int B, int Cin, int H, int 
     out[idx] = vk_from_f32<T>(v);
 }
 
+// The stem's case (3 channels, 4 x 4 patches, convnext.py:106-123): one thread = one patch row (ky) of one patch: three
+// coalesced float4 loads (one per colour plane), 12 bf16 values (24 B) written to k = (ky*4 + kx)*3 + ch.
+__global__ void __launch_bounds__(256)
+patchify_rgb4_kernel(const float* __restrict__ img, int B, int H, int W, __nv_bfloat16* __restrict__ out, int c_pad) {
+    const int Ho = H / 4, Wo = W / 4;
+    const long long total = (long long)B * Ho * Wo * 4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    // thread order: xo fastest (coalesced image reads), then ky, then yo, then b
+    const int xo = (int)(idx % Wo);
+    long long r = idx / Wo;
+    const int ky = (int)(r & 3);
+    r >>= 2;
+    const int yo = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const long long plane = (long long)H * W;
+    const float* src = img + (long long)b * 3 * plane + (long long)(yo * 4 + ky) * W + xo * 4;
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(src + plane));
+    const float4 c2 = __ldg(reinterpret_cast<const float4*>(src + 2 * plane));
+    const float v[12] = {c0.x, c1.x, c2.x, c0.y, c1.y, c2.y, c0.z, c1.z, c2.z, c0.w, c1.w, c2.w};
+    __nv_bfloat16* dst = out + (((long long)b * Ho + yo) * Wo + xo) * c_pad + ky * 12;
+    uint2* d2 = reinterpret_cast<uint2*>(dst);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        uint2 raw;
+        *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(v[4 * i], v[4 * i + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(v[4 * i + 2], v[4 * i + 3]);
+        d2[i] = raw;
+    }
+    if (ky == 0)
+        for (int k = 48; k < c_pad; k += 4) *reinterpret_cast<uint2*>(dst + k) = make_uint2(0u, 0u);   // K padding
+}
+
 // NHWC (B,H,W,C) -> (B,H/2,W/2,4C) with k = (ky*2+kx)*C + c  (dir 0), or the adjoint scatter (dir 1; pixels of an odd
 // trailing row/column get zero).  accumulate only applies to dir 1.
 template <typename T>
@@ -596,6 +630,13 @@ int vkocr_patchify_image(int dtype, const float* img, int B, int Cin, int H, int
     const long long total = (long long)B * (H / p) * (W / p) * c_pad;
     if (total == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == VKOCR_BF16 && Cin == 3 && p == 4 && W % 4 == 0 && c_pad % 4 == 0 && c_pad >= 48 &&
+        (reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+        const long long threads = (long long)B * (H / 4) * (W / 4) * 4;
+        patchify_rgb4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(img, B, H, W, reinterpret_cast<__nv_bfloat16*>(out), c_pad);
+        VK_CHECK_LAUNCH("patchify_rgb4_kernel");
+        return VKOCR_OK;
+    }
     VK_DISPATCH_DTYPE(dtype, T, (patchify_image_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
                                     img, B, Cin, H, W, p, reinterpret_cast<T*>(out), c_pad)));
     VK_CHECK_LAUNCH("patchify_image_kernel");
