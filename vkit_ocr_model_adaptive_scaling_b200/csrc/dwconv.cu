@@ -233,7 +233,7 @@ __device__ __forceinline__ void load_halo(uint32_t smem, const __nv_bfloat16* __
 }
 
 template <int TW>
-__global__ void __launch_bounds__(8 * TW, (TW <= 32) ? 3 : 2)
+__global__ void __launch_bounds__(8 * TW, 2)
 dwconv7_tile_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bfloat16* __restrict__ y, long long ld_y, int B,
                     int H, int W, int C, const float* __restrict__ wt, const float* __restrict__ bias,
                     const __nv_bfloat16* __restrict__ add, long long ld_add, int tiles_x, int tiles_y) {
@@ -264,7 +264,8 @@ dwconv7_tile_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bf
 #pragma unroll
             for (int o = 0; o < 4; ++o) { acc[oy][o][0] = bv.x; acc[oy][o][1] = bv.y; acc[oy][o][2] = bv.z; acc[oy][o][3] = bv.w; }
     }
-#pragma unroll 1
+    // fully unrolled: every shared-memory address below is base + immediate and the (r, oy) -> ky validity is static
+#pragma unroll
     for (int r = 0; r < 8; ++r) {               // halo rows py + r (input rows y0 + py + r - 3)
         float in[10][4];
         const uint8_t* rowp = s_in + (py + r) * RS + px * PIX_B + cq * 8;
@@ -356,7 +357,7 @@ dwconv7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy,
             float win[7][4];
 #pragma unroll
             for (int k = 0; k < 6; ++k) unpack4(*reinterpret_cast<const uint2*>(inrow + k * PIX_B), win[k + 1]);
-#pragma unroll 4
+#pragma unroll 8
             for (int xx = 0; xx < TW; ++xx) {
 #pragma unroll
                 for (int k = 0; k < 6; ++k)
