@@ -415,6 +415,18 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const VkocrEpilogue& ep = p.ep;
         const int chunks = (BN + 31) / 32;
         int cur_head = -1;
+        // bias / layer-scale vectors of the staged NT path live in shared memory (one global read per CTA instead of one
+        // L2 round trip per 32-column chunk and pass): [0, 896) bias, [896, 1792) column scale, when N fits
+        uint8_t* smem_gen0 = smem_raw + (smem_base - smem_u32(smem_raw));
+        float* s_vec = reinterpret_cast<float*>(smem_gen0 + head_off);
+        const bool vec_in_smem = p.mode == 0 && p.staged_store && !p.head_mode && p.N <= 896;
+        if (vec_in_smem) {
+            for (int i = (int)threadIdx.x - 128; i < p.N; i += 32 * EPI_WARPS) {
+                s_vec[i] = ep.bias ? __ldg(ep.bias + i) : 0.f;
+                s_vec[896 + i] = ep.col_scale ? __ldg(ep.col_scale + i) : 1.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        }
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit t = decode(u);
             bool row_ok;
@@ -616,85 +628,95 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         for (int j = 0; j < 4; ++j) extra[j] = lds128(my_row + (((uint32_t)j ^ sw) << 4));
                         __syncwarp();
                     }
-                    const int npass = ep.out_pre ? 2 : 1;
-                    for (int pass = 0; pass < npass; ++pass) {
-                        const bool pre = ep.out_pre && pass == 0;
-                        float v[32];
-                        {
-                            uint32_t acc[32];
-                            tc_ld32(taddr + (uint32_t)cb, acc);
+                    // stage the lane's 32 finished values and write the warp's tile out as coalesced row segments
+                    auto store_tile = [&](const float* vals, void* base, long long ld) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                        }
-                        const bool full = nb + 32 <= p.N;
-                        if (ep.bias) {
-                            if (full) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
-                                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(ep.bias + nb + j) : 0.f;
-                            }
-                        }
-                        if (!pre) {
-                            if (ep.act == 1) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
-                            } else if (ep.act == 2) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float f[8];
-                                    unpack8(extra[j], f);
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
-                                }
-                            }
-                            if (ep.col_scale) {
-                                if (full) {
-#pragma unroll
-                                    for (int j = 0; j < 32; j += 4) {
-                                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nb + j));
-                                        v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) v[j] *= (nb + j < p.N) ? __ldg(ep.col_scale + nb + j) : 0.f;
-                                }
-                            }
-                            if (ep.row_scale) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] *= rs;
-                            }
-                            if (ep.residual) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float f[8];
-                                    unpack8(extra[j], f);
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pack8(v + 8 * j));
+                        for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pack8(vals + 8 * j));
                         __syncwarp();
                         if (col < col_end) {
-                            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(pre ? ep.out_pre : ep.out);
-                            const long long old_ = pre ? ep.ld_pre : ep.ldo;
+                            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(base);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int rr = 8 * i + (lane >> 2);
                                 if (okmask & (1u << i)) {
                                     const uint4 val = lds128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4));
-                                    *reinterpret_cast<uint4*>(obase + (long long)pix[i] * old_ + col) = val;
+                                    *reinterpret_cast<uint4*>(obase + (long long)pix[i] * ld + col) = val;
                                 }
                             }
                         }
                         __syncwarp();      // the tile is free again
+                    };
+                    float v[32];
+                    {
+                        uint32_t acc[32];
+                        tc_ld32(taddr + (uint32_t)cb, acc);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
                     }
+                    const bool full = nb + 32 <= p.N;
+                    if (ep.bias && vec_in_smem && full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_vec + nb + j);
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else if (ep.bias) {
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(ep.bias + nb + j) : 0.f;
+                        }
+                    }
+                    if (ep.out_pre) store_tile(v, ep.out_pre, ep.ld_pre);      // pre-activation copy (acc + bias)
+                    if (ep.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
+                    } else if (ep.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float f[8];
+                            unpack8(extra[j], f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
+                        }
+                    }
+                    if (ep.col_scale && vec_in_smem && full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(s_vec + 896 + nb + j);
+                            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+                        }
+                    } else if (ep.col_scale) {
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nb + j));
+                                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= (nb + j < p.N) ? __ldg(ep.col_scale + nb + j) : 0.f;
+                        }
+                    }
+                    if (ep.row_scale) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= rs;
+                    }
+                    if (ep.residual) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float f[8];
+                            unpack8(extra[j], f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
+                        }
+                    }
+                    store_tile(v, ep.out, ep.ldo);
                 }
             } else
             for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
