@@ -228,6 +228,17 @@ int vkocr_accumulate_f32(const float* a, float* y, long long n, void* stream);
 int vkocr_scale_rows(int dtype, const void* x, long long ld_x, void* y, long long ld_y, long long rows, int C,
                      const float* scale, int rows_per_group, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ optimizer tail
+ * Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step over ~300 tensors
+ * (experiment/adaptive_scaling/train.py:73-80,287-298,468-478) by two passes over the flat fp32 buckets.
+ * vkocr_sumsq_f32: out[0] += sum x^2 (fp64).  vkocr_adamw_step: AdamW with decoupled weight decay on a flat range; the
+ * gradient is scaled by grad_scale and clipped by min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)) when sumsq is
+ * given; bias_corr1/2 = 1 - beta1^t / 1 - beta2^t. */
+int vkocr_sumsq_f32(const float* x, long long n, double* out, void* stream);
+int vkocr_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2, const double* sumsq,
+                     float max_norm, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

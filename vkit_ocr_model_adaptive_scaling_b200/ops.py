@@ -106,9 +106,13 @@ class _PackCache:
 
     def __init__(self) -> None:
         self.entries: Dict[Tuple, Tuple[Tuple, Tensor, Tuple]] = {}
+        self.epoch = 0   # bumped by writers that update parameters outside torch (training.FusedAdamW): invalidates everything
+
+    def bump(self) -> None:
+        self.epoch += 1
 
     def get(self, key: Tuple, params: Sequence[Tensor], shape: Tuple[int, ...], dtype: torch.dtype, fill) -> Tensor:
-        version = tuple(int(p._version) for p in params) + tuple(int(p.data_ptr()) for p in params)
+        version = (self.epoch,) + tuple(int(p._version) for p in params) + tuple(int(p.data_ptr()) for p in params)
         ent = self.entries.get(key)
         # keys carry id(param); a dead parameter's id (and even its storage address) can be reused by a new one, so an
         # entry is only valid while the very same parameter objects are alive

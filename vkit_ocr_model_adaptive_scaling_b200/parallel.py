@@ -61,24 +61,35 @@ def bucket_plan(model: nn.Module) -> List[Tuple[str, List[str]]]:
 class GradientBuckets:
     """Flat fp32 gradient storage; ``param.grad`` of every parameter aliases a slice of its bucket."""
 
-    def __init__(self, model: nn.Module, plan: Optional[Sequence[Tuple[str, Sequence[str]]]] = None) -> None:
+    def __init__(self, model: nn.Module, plan: Optional[Sequence[Tuple[str, Sequence[str]]]] = None,
+                 flatten_params: bool = False) -> None:
         plan = bucket_plan(model) if plan is None else plan
         params = dict(model.named_parameters())
         self.names: List[str] = []
         self.flat: List[Tensor] = []
+        self.flat_params: List[Tensor] = []     # only with flatten_params: param.data of every member aliases a slice
         self.members: List[List[nn.Parameter]] = []
         self.bucket_of: Dict[int, int] = {}
         for idx, (bucket, names) in enumerate(plan):
             members = [params[n] for n in names]
             total = sum(p.numel() for p in members)
             flat = torch.zeros(total, dtype=torch.float32, device=members[0].device)
+            flat_p = torch.empty(total, dtype=torch.float32, device=members[0].device) if flatten_params else None
             offset = 0
             for p in members:
                 p.grad = flat[offset:offset + p.numel()].view(p.shape)
+                if flat_p is not None:
+                    # the fused optimizer (training.FusedAdamW) updates whole buckets: parameters move into flat storage
+                    # (same values, same shapes; state_dict() is unchanged)
+                    view = flat_p[offset:offset + p.numel()].view(p.shape)
+                    view.copy_(p.data)
+                    p.data = view
                 offset += p.numel()
                 self.bucket_of[id(p)] = idx
             self.names.append(bucket)
             self.flat.append(flat)
+            if flat_p is not None:
+                self.flat_params.append(flat_p)
             self.members.append(members)
 
     def zero(self) -> None:
@@ -108,11 +119,12 @@ class DataParallel:
         dp.finish_step()                      # current stream waits for all reductions
     """
 
-    def __init__(self, model: nn.Module, process_group=None, broadcast_parameters: bool = True) -> None:
+    def __init__(self, model: nn.Module, process_group=None, broadcast_parameters: bool = True,
+                 flatten_params: bool = False) -> None:
         self.model = model
         self.group = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self.buckets = GradientBuckets(model)
+        self.buckets = GradientBuckets(model, flatten_params=flatten_params)
         self.loss_scale = 1.0 / self.world_size
         self._pending: Dict[int, int] = {}
         self._works: List = []

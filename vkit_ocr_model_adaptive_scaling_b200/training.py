@@ -51,3 +51,50 @@ def train_step(model, rough_loss_function: AdaptiveScalingRoughLossFunction,
     if dp is not None:
         dp.finish_step()
     return rough_loss.detach(), precise_loss.detach()
+
+
+class FusedAdamW:
+    """Global gradient-norm clipping + AdamW over the flat buckets of ``parallel.GradientBuckets(model, flatten_params=True)``:
+    the optimizer tail of the reference loop (``clip_grad_norm_`` + ``torch.optim.AdamW.step``,
+    experiment/adaptive_scaling/train.py:73-80,287-298,468-478) as one sum-of-squares pass and one update kernel per bucket,
+    with the clip coefficient computed on the device (no host synchronisation).  ``step(lr=...)`` takes the learning rate of
+    the caller's schedule (the reference uses CosineAnnealingWarmRestarts)."""
+
+    def __init__(self, buckets, lr: float = 8e-4, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, max_grad_norm: Optional[float] = None) -> None:
+        if not buckets.flat_params:
+            raise ValueError('FusedAdamW needs GradientBuckets(model, flatten_params=True)')
+        self.buckets = buckets
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.exp_avg = [torch.zeros_like(t) for t in buckets.flat_params]
+        self.exp_avg_sq = [torch.zeros_like(t) for t in buckets.flat_params]
+        self.steps = 0
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=buckets.flat_params[0].device)
+
+    def zero_grad(self) -> None:
+        self.buckets.reattach()
+        self.buckets.zero()
+
+    def grad_norm(self) -> Tensor:
+        """Global L2 norm of the gradients as seen by the last ``step`` (device tensor)."""
+        return self._sumsq.sqrt().float()
+
+    def step(self, lr: Optional[float] = None, grad_scale: float = 1.0) -> None:
+        from . import _lib as L
+        from . import ops
+        lr = self.lr if lr is None else lr
+        self.steps += 1
+        b1, b2 = self.betas
+        bc1, bc2 = 1.0 - b1 ** self.steps, 1.0 - b2 ** self.steps
+        clip = self.max_grad_norm is not None and self.max_grad_norm > 0
+        stream = L.stream_ptr()
+        self._sumsq.zero_()
+        if clip:
+            for g in self.buckets.flat:
+                L.check(L.LIB.vkocr_sumsq_f32(L.ptr(g), g.numel(), L.ptr(self._sumsq), stream), 'sumsq_f32')
+        for p, g, m, v in zip(self.buckets.flat_params, self.buckets.flat, self.exp_avg, self.exp_avg_sq):
+            L.check(L.LIB.vkocr_adamw_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, b1, b2, self.eps, self.weight_decay,
+                                           bc1, bc2, L.ptr(self._sumsq) if clip else None, float(self.max_grad_norm or 0.0),
+                                           grad_scale, stream), 'adamw_step')
+        ops.PACK.bump()   # the parameters changed behind torch's version counters: re-pack the kernel-layout weights
