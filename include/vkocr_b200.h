@@ -239,6 +239,15 @@ int vkocr_adamw_step(float* param, const float* grad, float* exp_avg, float* exp
                      float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2, const double* sumsq,
                      float max_norm, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------- rough inference pre/post ops
+ * vkocr_ingest_image_u8: uint8 HWC page image(s) -> zero-padded fp32 NCHW network input (inferencing/opt.py:16-41
+ * pad_mat_to_make_divisible + the transpose/astype of inferencing/adaptive_scaling.py:116-121).
+ * vkocr_rough_postprocess: sigmoid >= thr mask (uint8) and the height map with padding and too-small heights zeroed
+ * (inferencing/adaptive_scaling.py:145-169). */
+int vkocr_ingest_image_u8(const void* img, int B, int H, int W, float* out, int Hp, int Wp, void* stream);
+int vkocr_rough_postprocess(const float* logit, const float* height, int B, int h, int w, int valid_h, int valid_w, float thr,
+                            float height_min, void* mask_out, float* height_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,84 @@
+"""Tensor-side rough inference ops on the device against the oracle restatement of the reference lines
+(inferencing/opt.py:16-41, inferencing/adaptive_scaling.py:109-180)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def vk():
+    import vkit_ocr_model_adaptive_scaling_b200 as vk
+    return vk
+
+
+@pytest.mark.parametrize('hw', [(64, 96), (70, 101), (33, 32), (1, 1)])
+def test_ingest_matches_reference_padding(vk, hw):
+    from oracle import infer as oi
+    H, W = hw
+    rng = np.random.default_rng(H * 1000 + W)
+    img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    want = oi.network_input(img, 32)
+    got = vk.inferencing.ingest_images(torch.from_numpy(img).cuda(), 32)
+    assert tuple(got.shape) == tuple(want.shape)
+    assert torch.equal(got.cpu(), want)                       # bit-exact: integers 0..255 and zeros
+
+
+def test_rough_infer_tensors_against_oracle(vk):
+    from oracle import infer as oi
+    from oracle import model as om
+    from oracle import synth
+    dev = torch.device('cuda')
+    M = vk.model
+    model = M.AdaptiveScaling(M.AdaptiveScalingConfig(size=M.AdaptiveScalingSize.TINY,
+                                                      neck_head_type=M.AdaptiveScalingNeckHeadType.UPERNEXT))
+    sd = synth.synth_state_dict('tiny', 'upernext', seed=21, rough_height_bias=3.0)   # heights straddle the 3.0 cut
+    model.load_state_dict(sd, strict=True)
+    model.to(dev).eval()
+    H, W = 90, 141                                            # pads to 96 x 160
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    with vk.precision(torch.float32):
+        mask, hmap, shape = vk.inferencing.rough_infer_tensors(model, torch.from_numpy(img).cuda())
+    x = oi.network_input(img, 32).double().to(dev)
+    params = {k: v.detach().double().to(dev) for k, v in sd.items()}
+    with torch.no_grad():
+        logit, height = om.forward_rough(params, x)
+    want_mask, want_h, want_shape = oi.rough_postprocess(logit[0, 0].float().cpu(), height[0, 0].float().cpu(), H, W,
+                                                         x.shape[2], x.shape[3])
+    assert shape == want_shape
+    assert tuple(mask.shape) == (1,) + want_mask.shape and mask.dtype == torch.uint8
+    got_mask, got_h = mask[0].cpu().numpy(), hmap[0].cpu().numpy()
+    # outside a 1e-4 band around the two thresholds (fp32 kernels vs the fp64 oracle) the maps must agree exactly
+    lo = logit[0, 0].float().cpu().numpy()
+    hh = height[0, 0].float().cpu().numpy()
+    sure_m = np.abs(lo) > 1e-4
+    sure_h = np.abs(hh - 3.0) > 1e-3
+    assert np.array_equal(got_mask[sure_m], want_mask[sure_m])
+    zero_w, zero_g = want_h == 0.0, got_h == 0.0
+    assert np.array_equal(zero_w[sure_h], zero_g[sure_h])
+    assert (zero_w.sum() > 0) and (~zero_w).sum() > 0
+    keep = sure_h & ~zero_w
+    assert np.allclose(got_h[keep], want_h[keep], rtol=1e-4, atol=1e-4)
+    assert got_mask[shape[0]:].sum() == 0 and got_mask[:, shape[1]:].sum() == 0     # padding forced negative
+
+
+def test_rough_postprocess_kernel_on_synthetic_maps(vk):
+    """The post-op kernel alone on random logits / heights (both mask classes, heights on both sides of the cut)."""
+    import ctypes
+    from oracle import infer as oi
+    from vkit_ocr_model_adaptive_scaling_b200 import _lib as L
+    g = torch.Generator().manual_seed(4)
+    h, w, H, W = 48, 80, 90, 141
+    logit = torch.randn(1, 1, h, w, generator=g) * 3
+    height = torch.rand(1, 1, h, w, generator=g) * 8
+    mask = torch.empty((1, h, w), dtype=torch.uint8, device='cuda')
+    hmap = torch.empty((1, h, w), dtype=torch.float32, device='cuda')
+    ld, hd = logit.cuda(), height.cuda()
+    L.check(L.LIB.vkocr_rough_postprocess(L.ptr(ld), L.ptr(hd), 1, h, w, 45, 71, 0.5, 3.0, L.ptr(mask), L.ptr(hmap), L.stream_ptr()),
+            'rough_postprocess')
+    want_mask, want_h, shape = oi.rough_postprocess(logit[0, 0], height[0, 0], H, W, 96, 160)
+    assert shape == (45, 71)
+    assert np.array_equal(mask[0].cpu().numpy(), want_mask) and 0.2 < want_mask.mean() < 0.8
+    assert np.array_equal(hmap[0].cpu().numpy(), want_h) and 0.1 < (want_h == 0).mean() < 0.9
