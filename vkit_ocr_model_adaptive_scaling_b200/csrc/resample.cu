@@ -102,8 +102,11 @@ upsample_bwd_kernel(const T* __restrict__ ddst, long long ld_d, int H, int W, T*
     const int c = cv * V;
     // conservative candidate ranges of destination rows/cols touching source row i / col j
     const float ry = (float)H / (float)h, rx = (float)W / (float)w;
-    int Ylo = (int)floorf((i - 1) * ry) - 2, Yhi = (int)ceilf((i + 2) * ry) + 2;
-    int Xlo = (int)floorf((j - 1) * rx) - 2, Xhi = (int)ceilf((j + 2) * rx) + 2;
+    // a destination row Y reads source rows floor(s), floor(s)+1 with s = (Y + .5) / ry - .5, so source row i is read by
+    // the Y with s in (i - 1, i + 1): Y + .5 in ((i - .5) ry, (i + 1.5) ry); one extra row each side absorbs rounding
+    // (nearest: the Y with floor(Y / ry) == i lie inside the same range)
+    int Ylo = (int)floorf((i - 0.5f) * ry - 0.5f) - 1, Yhi = (int)ceilf((i + 1.5f) * ry - 0.5f) + 1;
+    int Xlo = (int)floorf((j - 0.5f) * rx - 0.5f) - 1, Xhi = (int)ceilf((j + 1.5f) * rx - 0.5f) + 1;
     if (Ylo < 0) Ylo = 0;
     if (Xlo < 0) Xlo = 0;
     if (Yhi > H - 1) Yhi = H - 1;

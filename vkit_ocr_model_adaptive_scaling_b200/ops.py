@@ -157,9 +157,12 @@ def packed_linear_dgrad(w: Tensor, dtype: torch.dtype, col_scale: Optional[Tenso
     """Linear weight (N, K) -> [K, n_pad] operand of dX = dY . W (optionally with W rows scaled by col_scale[n])."""
     N, K = w.shape
     n_pad = _ceil_to(N, 64)
+    # `col_scale` is the layer-scale PARAMETER itself (any shape with N elements): the cache entry lives as long as the
+    # parameter objects do, so a per-call detached view would force a re-pack on every call
     params = [w] if col_scale is None else [w, col_scale]
     buf = PACK.get(('lin_dgrad', id(w), dtype, col_scale is not None), params, (K, n_pad), dtype,
-                   lambda b: _pack(w.detach(), 1, 0, K, K, 1, N, 0, None if col_scale is None else col_scale.detach(), b, 0, n_pad, 0))
+                   lambda b: _pack(w.detach(), 1, 0, K, K, 1, N, 0,
+                                   None if col_scale is None else col_scale.detach().reshape(-1), b, 0, n_pad, 0))
     return buf, n_pad
 
 
@@ -457,7 +460,7 @@ class ConvNextLayerFn(torch.autograd.Function):
             u = dy
             colsum(u, u.stride(3), M, C, su)
         # dH_pre = (U . (gamma * W2)) * gelu'(H_pre)
-        w2d, n2 = packed_linear_dgrad(w2, dt, gamma)
+        w2d, n2 = packed_linear_dgrad(w2, dt, scale)
         dh = torch.empty((M, hid), dtype=dt, device=dev)
         gemm_nt(u, 1, 1, M, C, u.stride(3), 1, w2d, n2, hid, _epilogue(dh, hid, act=2, aux=hpre, ld_aux=hid))
         # S[c,k] = sum_p U[p,c] G[p,k]  -> dW2, dscale, db2
