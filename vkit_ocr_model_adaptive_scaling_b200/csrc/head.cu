@@ -187,12 +187,20 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
     extern __shared__ uint4 ring[];   // [RING][NVL][HT_THREADS] vectors, then [RING][HT_WARPS][2 * O] upstream values, then sacc
     float* dring = reinterpret_cast<float*>(ring + RING * NVL * HT_THREADS);
     float* sacc = dring + RING * HT_WARPS * 2 * O;   // [(3 + O)][CW] + [O]
+    // O >= 3: the projection weights stay in shared memory (32 registers of them would spill the accumulators)
+    constexpr bool W_SMEM = O >= 3;
+    float* s_w = sacc + (3 + O) * CW + O;            // [O][CW], only when W_SMEM
     for (int i = threadIdx.x; i < (3 + O) * CW + O; i += blockDim.x) sacc[i] = 0.f;
+    if (W_SMEM)
+        for (int i = threadIdx.x; i < O * CW; i += blockDim.x) {
+            const int o = i / CW, c = i % CW;
+            s_w[i] = c < inner ? __ldg(w2 + (long long)o * inner + c) : 0.f;
+        }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const unsigned warp0 = blockIdx.x * HT_WARPS + (threadIdx.x >> 5);
     const unsigned nwarps = gridDim.x * HT_WARPS;
-    float gm[NVL][V], bt[NVL][V], w[O][NVL][V];
+    float gm[NVL][V], bt[NVL][V], w[W_SMEM ? 1 : O][NVL][V];
     float ag[NVL][V], ab[NVL][V], ax[NVL][V], aw[O][NVL][V];
     float adb[O];
 #pragma unroll
@@ -208,7 +216,7 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
             ag[j][i] = ab[j][i] = ax[j][i] = 0.f;
 #pragma unroll
             for (int o = 0; o < O; ++o) {
-                w[o][j][i] = ok ? __ldg(w2 + (long long)o * inner + c) : 0.f;
+                if (!W_SMEM) w[o][j][i] = ok ? __ldg(w2 + (long long)o * inner + c) : 0.f;
                 aw[o][j][i] = 0.f;
             }
         }
@@ -270,7 +278,8 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
                 float dg = 0.f;
 #pragma unroll
                 for (int o = 0; o < O; ++o) {
-                    dg = fmaf(dpre[o], w[o][j][i], dg);
+                    const float wv = W_SMEM ? s_w[o * CW + (lane + 32 * j) * V + i] : w[o][j][i];
+                    dg = fmaf(dpre[o], wv, dg);
                     aw[o][j][i] = fmaf(dpre[o], g, aw[o][j][i]);
                 }
                 const float d = dg * gp;
@@ -366,7 +375,7 @@ int launch_bwd(int O, const void* x, long long ld_x, int inner, int slice_w, con
 #define VK_HT_BWD(OO)                                                                                                       \
     cudaFuncSetAttribute(head_tail_bwd_kernel<T, NVL, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);         \
     head_tail_bwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS,                                                        \
-        RING * NVL * HT_THREADS * 16 + (RING * HT_WARPS * 2 * OO + (3 + OO) * 32 * NVL * V + OO) * sizeof(float), s>>>(      \
+        RING * NVL * HT_THREADS * 16 + (RING * HT_WARPS * 2 * OO + (3 + OO + (OO >= 3 ? OO : 0)) * 32 * NVL * V + OO) * sizeof(float), s>>>(      \
         reinterpret_cast<const T*>(x), ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, (unsigned)ppi, inv_ppi,  \
         (unsigned)rows, reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias)
     switch (O) {
