@@ -380,3 +380,35 @@ def test_errors_are_loud(vk):
     from vkit_ocr_model_adaptive_scaling_b200 import _lib as L
     rc = L.LIB.vkocr_dwconv7_fwd(1, None, 8, None, 8, 1, 4, 4, 8, None, None, None, 0, None)
     assert rc != 0 and b'null' in L.LIB.vkocr_last_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(2, 32, 16, 40), (1, 64, 19, 80), (2, 32, 20, 20), (1, 96, 13, 35), (3, 32, 8, 120)])
+def test_dwconv7_tiled_kernels_against_conv2d(vk, shape):
+    """The bf16 tiled depthwise kernels (helper.dconv7x7, model/helper.py:61-73) at every tile width (40 / 20 / 32), with
+    partial tiles and the fused residual operand: forward and weight gradient against torch's own convolution of the
+    same bf16-rounded operands in fp64 (only the final bf16 rounding / fp32 summation order may differ)."""
+    from vkit_ocr_model_adaptive_scaling_b200 import ops
+    B, C, H, W = shape
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = ops.alloc_nhwc(B, H, W, C, torch.bfloat16, dev)
+    x.copy_(torch.randn(B, C, H, W, generator=g))
+    add = ops.alloc_nhwc(B, H, W, C, torch.bfloat16, dev)
+    add.copy_(torch.randn(B, C, H, W, generator=g))
+    y = ops.alloc_nhwc(B, H, W, C, torch.bfloat16, dev)
+    w = torch.randn(C, 1, 7, 7, generator=g).to(dev)
+    bias = torch.randn(C, generator=g).to(dev)
+    wt = w.reshape(C, 49).t().contiguous()                      # [49][C] tap table
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), padding=3, groups=C)
+    ops.dwconv7(x, y, wt, bias, None)
+    assert_close(y.float(), ref, 4e-3, 'dwconv7 forward')
+    ops.dwconv7(x, y, wt, None, add)
+    ref2 = torch.nn.functional.conv2d(x.double(), w.double(), None, padding=3, groups=C) + add.double()
+    assert_close(y.float(), ref2, 4e-3, 'dwconv7 + add')
+    dw = torch.zeros(C, 1, 7, 7, device=dev)
+    ops.dwconv7_wgrad(add, x, dw)
+    xd = x.double().requires_grad_(False)
+    wd = w.double().requires_grad_(True)
+    (torch.nn.functional.conv2d(xd, wd, None, padding=3, groups=C) * add.double()).sum().backward()
+    assert_close(dw, wd.grad, 1e-5, 'dwconv7 weight gradient')

@@ -232,19 +232,61 @@ __device__ __forceinline__ void load_halo(uint32_t smem, const __nv_bfloat16* __
     }
 }
 
+// Packed fp32 FMA (sm_100 FFMA2): d = a * b + d on two lanes.  Same FMA-pipe throughput as two FFMAs but ONE issue slot,
+// which is what these kernels are short of (conversions, LDS and address arithmetic share the scheduler with the FMAs).
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(dd)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+// two bf16 channels in one 32-bit word -> an fp32 pair (one shift, one mask)
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t raw) {
+    return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+}
+
+// Column-wise halo loader: thread -> one 16-byte quarter of one halo column, walking down the HALO_H rows with a
+// constant address increment (no per-copy index arithmetic).  Threads beyond (TW + 6) * 4 idle.
+template <int TW, int RS>
+__device__ __forceinline__ void load_halo_cols(uint32_t smem, const __nv_bfloat16* __restrict__ x, long long ld_x, TileCoord tc,
+                                               int H, int W, int c0) {
+    constexpr int HW = TW + 6;
+    if (threadIdx.x < HW * 4) {
+        const int part = threadIdx.x & 3, hx = threadIdx.x >> 2;
+        const int xx = tc.x0 + hx - 3;
+        const bool col_ok = xx >= 0 && xx < W;
+        const long long row_step = (long long)W * ld_x;
+        const __nv_bfloat16* src = x + (((long long)tc.b * H + (tc.y0 - 3)) * W + (col_ok ? xx : 0)) * ld_x + c0 + part * 8;
+        uint32_t dst = smem + (uint32_t)(hx * PIX_B + part * 16);
+#pragma unroll
+        for (int hy = 0; hy < HALO_H; ++hy) {
+            const int yy = tc.y0 + hy - 3;
+            const bool ok = col_ok && yy >= 0 && yy < H;
+            cp_async16_zfill(dst, ok ? src : x, ok);
+            src += row_step;
+            dst += RS;
+        }
+    }
+}
+
+// Forward / data gradient.  A block is persistent over the TW x 8 tiles of one 32-channel block and double-buffers the
+// halo tile: the cp.async copies of tile t+1 are in flight while tile t is computed from shared memory.
 template <int TW>
 __global__ void __launch_bounds__(8 * TW, 2)
 dwconv7_tile_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bfloat16* __restrict__ y, long long ld_y, int B,
                     int H, int W, int C, const float* __restrict__ wt, const float* __restrict__ bias,
-                    const __nv_bfloat16* __restrict__ add, long long ld_add, int tiles_x, int tiles_y) {
+                    const __nv_bfloat16* __restrict__ add, long long ld_add, int tiles_x, int tiles_y, int ntiles) {
     constexpr int RS = rs_fwd(TW);
+    constexpr int BUF = HALO_H * RS;
     extern __shared__ __align__(128) uint8_t dw_smem[];
-    uint8_t* s_in = dw_smem;                                             // [HALO_H][RS]
-    float* s_w = reinterpret_cast<float*>(dw_smem + HALO_H * RS);        // [49][CB]
+    uint8_t* s_in = dw_smem;                                             // [2][HALO_H][RS]
+    float* s_w = reinterpret_cast<float*>(dw_smem + 2 * BUF);            // [49][CB]
     float* s_b = s_w + 49 * CB;                                          // [CB]
     const int c0 = blockIdx.y * CB;
-    const TileCoord tc = tile_coord<TW>(blockIdx.x, tiles_x, tiles_y);
-    load_halo<TW, RS>((uint32_t)__cvta_generic_to_shared(s_in), x, ld_x, tc, H, W, c0);
+    const uint32_t s_in_a = (uint32_t)__cvta_generic_to_shared(s_in);
+    int t = blockIdx.x;
+    if (t < ntiles) load_halo_cols<TW, RS>(s_in_a, x, ld_x, tile_coord<TW>(t, tiles_x, tiles_y), H, W, c0);
     vk_cp_async_commit();
     for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) s_w[i] = __ldg(wt + (long long)(i / CB) * C + c0 + (i % CB));
     if (threadIdx.x < CB) s_b[threadIdx.x] = bias ? __ldg(bias + c0 + threadIdx.x) : 0.f;
@@ -254,57 +296,92 @@ dwconv7_tile_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bf
     const int sidx = threadIdx.x >> 3;          // 0 .. TW - 1
     const int sy = sidx & 3, sx = sidx >> 2;    // 4 patches in y (8 rows), TW / 4 in x
     const int px = sx * 4, py = sy * 2;
-    vk_cp_async_wait<0>();
-    __syncthreads();
-    float acc[2][4][4];
-    {
-        const float4 bv = *reinterpret_cast<const float4*>(s_b + cq * 4);
+    int buf = 0;
+    for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+        const TileCoord tc = tile_coord<TW>(t, tiles_x, tiles_y);
+        vk_cp_async_wait<0>();
+        __syncthreads();                        // tile t has landed; everybody is done with the other buffer
+        if (t + (int)gridDim.x < ntiles)
+            load_halo_cols<TW, RS>(s_in_a + (uint32_t)((buf ^ 1) * BUF), x, ld_x, tile_coord<TW>(t + gridDim.x, tiles_x, tiles_y), H, W, c0);
+        vk_cp_async_commit();
+        float2 acc[2][4][2];
+        {
+            const float4 bv = *reinterpret_cast<const float4*>(s_b + cq * 4);
 #pragma unroll
-        for (int oy = 0; oy < 2; ++oy)
+            for (int oy = 0; oy < 2; ++oy)
 #pragma unroll
-            for (int o = 0; o < 4; ++o) { acc[oy][o][0] = bv.x; acc[oy][o][1] = bv.y; acc[oy][o][2] = bv.z; acc[oy][o][3] = bv.w; }
-    }
-    // fully unrolled: every shared-memory address below is base + immediate and the (r, oy) -> ky validity is static
+                for (int o = 0; o < 4; ++o) { acc[oy][o][0] = make_float2(bv.x, bv.y); acc[oy][o][1] = make_float2(bv.z, bv.w); }
+        }
+        // Halo row py + r feeds output row oy with kernel row ky = r - oy: rows 1..6 feed both output rows, row 0 only
+        // the upper and row 7 only the lower one.  The middle rows run as a ROLLED loop: the fully unrolled body (2500
+        // instructions, 40 KB) streamed through the instruction cache and left the schedulers half idle.
+        const uint8_t* tile = s_in + buf * BUF + py * RS + px * PIX_B + cq * 8;
+        const float* wrow = s_w + cq * 4;
+        auto load_row = [&](const uint8_t* rowp, float2 (&in)[10][2]) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {               // halo rows py + r (input rows y0 + py + r - 3)
-        float in[10][4];
-        const uint8_t* rowp = s_in + (py + r) * RS + px * PIX_B + cq * 8;
+            for (int j = 0; j < 10; ++j) {
+                const uint2 raw = *reinterpret_cast<const uint2*>(rowp + j * PIX_B);
+                in[j][0] = bf2_to_f2(raw.x);
+                in[j][1] = bf2_to_f2(raw.y);
+            }
+        };
+        auto taps = [&](const float* wk, const float2 (&in)[10][2], float2 (&a)[4][2]) {
 #pragma unroll
-        for (int j = 0; j < 10; ++j) unpack4(*reinterpret_cast<const uint2*>(rowp + j * PIX_B), in[j]);
+            for (int kx = 0; kx < 7; ++kx) {
+                const float4 w = *reinterpret_cast<const float4*>(wk + kx * CB);
+                const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
 #pragma unroll
-        for (int oy = 0; oy < 2; ++oy) {
-            const int ky = r - oy;
-            if (ky >= 0 && ky < 7) {
-#pragma unroll
-                for (int kx = 0; kx < 7; ++kx) {
-                    const float4 w = *reinterpret_cast<const float4*>(s_w + (ky * 7 + kx) * CB + cq * 4);
-#pragma unroll
-                    for (int o = 0; o < 4; ++o) {
-                        acc[oy][o][0] = fmaf(w.x, in[o + kx][0], acc[oy][o][0]);
-                        acc[oy][o][1] = fmaf(w.y, in[o + kx][1], acc[oy][o][1]);
-                        acc[oy][o][2] = fmaf(w.z, in[o + kx][2], acc[oy][o][2]);
-                        acc[oy][o][3] = fmaf(w.w, in[o + kx][3], acc[oy][o][3]);
-                    }
+                for (int o = 0; o < 4; ++o) {
+                    ffma2(a[o][0], w0, in[o + kx][0]);
+                    ffma2(a[o][1], w1, in[o + kx][1]);
                 }
             }
+        };
+        {
+            float2 in[10][2];
+            load_row(tile, in);
+            taps(wrow, in, acc[0]);                                   // r = 0: ky = 0 of the upper row
         }
-    }
+#pragma unroll 1
+        for (int r = 1; r < 7; ++r) {
+            float2 in[10][2];
+            load_row(tile + r * RS, in);
+            taps(wrow + r * 7 * CB, in, acc[0]);                      // ky = r
+            taps(wrow + (r - 1) * 7 * CB, in, acc[1]);                // ky = r - 1
+        }
+        {
+            float2 in[10][2];
+            load_row(tile + 7 * RS, in);
+            taps(wrow + 6 * 7 * CB, in, acc[1]);                      // r = 7: ky = 6 of the lower row
+        }
+        uint2 av[2][4];
+        if (add) {
 #pragma unroll
-    for (int oy = 0; oy < 2; ++oy) {
-        const int yy = tc.y0 + py + oy;
-        if (yy < H) {
+            for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int yy = tc.y0 + py + oy, xx = tc.x0 + px + o;
+                    av[oy][o] = make_uint2(0u, 0u);
+                    if (yy < H && xx < W)
+                        av[oy][o] = __ldg(reinterpret_cast<const uint2*>(add + (((long long)tc.b * H + yy) * W + xx) * ld_add + c0 + cq * 4));
+                }
+        }
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy) {
+            const int yy = tc.y0 + py + oy;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
                 const int xx = tc.x0 + px + o;
-                if (xx < W) {
-                    const long long pix = ((long long)tc.b * H + yy) * W + xx;
+                if (yy < H && xx < W) {
+                    float2 a0 = acc[oy][o][0], a1 = acc[oy][o][1];
                     if (add) {
-                        float f[4];
-                        unpack4(*reinterpret_cast<const uint2*>(add + pix * ld_add + c0 + cq * 4), f);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[oy][o][i] += f[i];
+                        const float2 f0 = bf2_to_f2(av[oy][o].x), f1 = bf2_to_f2(av[oy][o].y);
+                        a0.x += f0.x; a0.y += f0.y; a1.x += f1.x; a1.y += f1.y;
                     }
-                    *reinterpret_cast<uint2*>(y + pix * ld_y + c0 + cq * 4) = pack4(acc[oy][o]);
+                    uint2 raw;
+                    *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(a0.x, a0.y);
+                    *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(a1.x, a1.y);
+                    *reinterpret_cast<uint2*>(y + (((long long)tc.b * H + yy) * W + xx) * ld_y + c0 + cq * 4) = raw;
                 }
             }
         }
@@ -325,11 +402,9 @@ dwconv7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy,
     const int cq = threadIdx.x & 7;
     const int rest = threadIdx.x >> 3;          // 0..27
     const int ky = rest % 7, rg = rest / 7;     // kernel row, row pair of the tile
-    float acc[7][4];
+    float2 acc[7][2];
 #pragma unroll
-    for (int k = 0; k < 7; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+    for (int k = 0; k < 7; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
     for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) s_acc[i] = 0.f;
     const int ntiles = B * tiles_y * tiles_x;
     const uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(dw_smem);
@@ -354,30 +429,38 @@ dwconv7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy,
             const int row = rg * 2 + oy;                                   // tile row of dy
             const uint8_t* inrow = s_in + (row + ky) * RS + cq * 8;        // halo row row + ky  (input row y + ky - 3)
             const uint8_t* dyrow = s_dy + row * TW * PIX_B + cq * 8;
-            float win[7][4];
+            float2 win[7][2];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) unpack4(*reinterpret_cast<const uint2*>(inrow + k * PIX_B), win[k + 1]);
+            for (int k = 0; k < 6; ++k) {
+                const uint2 raw = *reinterpret_cast<const uint2*>(inrow + k * PIX_B);
+                win[k + 1][0] = bf2_to_f2(raw.x);
+                win[k + 1][1] = bf2_to_f2(raw.y);
+            }
 #pragma unroll 8
             for (int xx = 0; xx < TW; ++xx) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k)
+                for (int k = 0; k < 6; ++k) { win[k][0] = win[k + 1][0]; win[k][1] = win[k + 1][1]; }
+                const uint2 raw = *reinterpret_cast<const uint2*>(inrow + (xx + 6) * PIX_B);
+                win[6][0] = bf2_to_f2(raw.x);
+                win[6][1] = bf2_to_f2(raw.y);
+                const uint2 graw = *reinterpret_cast<const uint2*>(dyrow + xx * PIX_B);
+                const float2 g0 = bf2_to_f2(graw.x), g1 = bf2_to_f2(graw.y);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) win[k][i] = win[k + 1][i];
-                unpack4(*reinterpret_cast<const uint2*>(inrow + (xx + 6) * PIX_B), win[6]);
-                float g[4];
-                unpack4(*reinterpret_cast<const uint2*>(dyrow + xx * PIX_B), g);
-#pragma unroll
-                for (int k = 0; k < 7; ++k)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(g[i], win[k][i], acc[k][i]);
+                for (int k = 0; k < 7; ++k) {
+                    ffma2(acc[k][0], g0, win[k][0]);
+                    ffma2(acc[k][1], g1, win[k][1]);
+                }
             }
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 7; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[(ky * 7 + k) * CB + cq * 4 + i], acc[k][i]);
+    for (int k = 0; k < 7; ++k) {
+        atomicAdd(&s_acc[(ky * 7 + k) * CB + cq * 4 + 0], acc[k][0].x);
+        atomicAdd(&s_acc[(ky * 7 + k) * CB + cq * 4 + 1], acc[k][0].y);
+        atomicAdd(&s_acc[(ky * 7 + k) * CB + cq * 4 + 2], acc[k][1].x);
+        atomicAdd(&s_acc[(ky * 7 + k) * CB + cq * 4 + 3], acc[k][1].y);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) atomicAdd(dw + (long long)(c0 + i % CB) * 49 + i / CB, s_acc[i]);
 }
@@ -390,11 +473,15 @@ int launch_dw_tile(const void* x, long long ld_x, void* y, long long ld_y, int B
     const int tiles_x = vk_cdiv(W, TW), tiles_y = vk_cdiv(H, TH);
     const long long ntiles = (long long)B * tiles_x * tiles_y;
     const int cblocks = C / CB;
-    const int smem = HALO_H * rs_fwd(TW) + (49 * CB + CB) * (int)sizeof(float);
+    const int smem = 2 * HALO_H * rs_fwd(TW) + (49 * CB + CB) * (int)sizeof(float);
+    // persistent: as many blocks as are resident at once (2 per SM by registers; shared memory allows it for every TW)
+    long long gx = ((long long)vkocr_sm_count() * 2) / cblocks;     // rounded DOWN: one block too many is a whole second wave
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
     cudaFuncSetAttribute(dwconv7_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    dwconv7_tile_kernel<TW><<<dim3((unsigned)ntiles, (unsigned)cblocks), 8 * TW, smem, s>>>(
+    dwconv7_tile_kernel<TW><<<dim3((unsigned)gx, (unsigned)cblocks), 8 * TW, smem, s>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), ld_x, reinterpret_cast<__nv_bfloat16*>(y), ld_y, B, H, W, C, wt, bias,
-        reinterpret_cast<const __nv_bfloat16*>(add), ld_add, tiles_x, tiles_y);
+        reinterpret_cast<const __nv_bfloat16*>(add), ld_add, tiles_x, tiles_y, (int)ntiles);
     return 0;
 }
 
@@ -405,11 +492,16 @@ int launch_dw_wgrad_tile(const void* dy, long long ld_dy, const void* x, long lo
     const long long ntiles = (long long)B * tiles_x * tiles_y;
     const int cblocks = C / CB;
     const int smem = HALO_H * rs_wg(TW) + TH * TW * PIX_B + 49 * CB * (int)sizeof(float);
-    const int per_sm = (220 * 1024) / (smem + 1024);
-    long long gy = ((long long)vkocr_sm_count() * per_sm + cblocks - 1) / cblocks;
+    cudaFuncSetAttribute(dwconv7_wgrad_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // persistent over tiles: exactly the number of blocks that are resident at once (registers, not shared memory, bound
+    // it), rounded DOWN -- a partial second wave costs a whole block's run time
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_wgrad_tile_kernel<TW>, 224, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    long long gy = ((long long)vkocr_sm_count() * per_sm) / cblocks;
     if (gy > ntiles) gy = ntiles;
     if (gy < 1) gy = 1;
-    cudaFuncSetAttribute(dwconv7_wgrad_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dwconv7_wgrad_tile_kernel<TW><<<dim3((unsigned)cblocks, (unsigned)gy), 224, smem, s>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy), ld_dy, reinterpret_cast<const __nv_bfloat16*>(x), ld_x, B, H, W, C, tiles_x,
         tiles_y, dw);

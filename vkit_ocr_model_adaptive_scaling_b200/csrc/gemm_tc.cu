@@ -221,7 +221,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 32 * EPI_WARPS);
+            mbar_init(tempty_bar(a), EPI_WARPS);      // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -297,7 +297,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 const uint32_t sb = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes + A_BYTES;
                 const int x0 = tx * p.BW + dx, y0 = ty * p.BH + dy;
-                if (!p.skip_tma)
+                if (!(p.skip_tma & 1))
                     for (int g = 0; g < nb; ++g) tma_load_4d(sb + (uint32_t)g * 8192u, &mapB, full_bar(s), t.n0 + g * 64, x0, y0, b);
                 if (++tx == p.tiles_x) {
                     tx = 0;
@@ -320,7 +320,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 for (int kb = 0; kb < t.num_kb; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
-                    if (p.skip_tma) {
+                    if (p.skip_tma & 1) {
                         mbar_arrive(full_bar(s));
                     } else {
                         mbar_expect_tx(full_bar(s), tx_bytes);
@@ -344,7 +344,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
                     const int x0 = tx * p.BW, y0 = ty * p.BH;
-                    if (p.skip_tma) {
+                    if (p.skip_tma & 1) {
                         mbar_arrive(full_bar(s));
                     } else {
                         mbar_expect_tx(full_bar(s), tx_bytes);
@@ -368,7 +368,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const uint32_t major = (p.mode == 0) ? 0u : 1u;
         uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (major << 15) | (major << 16) |
                          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const int dbg_major = p.skip_tma >> 1;   // debug (timing only, garbage data): bit0 -> A K-major, bit1 -> B K-major
+        const int dbg_major = (p.skip_tma >> 1) & 3;   // debug (timing only, garbage data): bit0 -> A K-major, bit1 -> B K-major
         if (dbg_major & 1) idesc &= ~(1u << 15);
         if (dbg_major & 2) idesc &= ~(1u << 16);
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -388,7 +388,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     const uint64_t bd = make_smem_desc(sb, 1, 64);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        tc_mma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        if (!(p.skip_tma & 32)) tc_mma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
                 } else {
                     // MN-major SWIZZLE_128B: 64-channel groups 8192 B apart (LBO), 8-pixel atoms 1024 B apart (SBO);
                     // one K=16 slice = 2 atoms = 2048 B.
@@ -611,7 +611,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
                     const int cb = c * 32;
                     const int nb = t.n0 + cb;
-                    if (nb >= col_end) break;
+                    if (nb >= col_end || (p.skip_tma & 16)) break;   // debug bit 4: epilogue = barrier traffic only
                     const int col = nb + seg * 8;
                     uint4 extra[4];
                     if (esrc) {
@@ -633,7 +633,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pack8(vals + 8 * j));
                         __syncwarp();
-                        if (col < col_end) {
+                        if (col < col_end && !(p.skip_tma & 8)) {   // debug bit 3: no global stores
                             __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(base);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -808,7 +808,8 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 }
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar(as));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));   // 384 same-address arrivals per tile serialised in the smem atomic unit
             if (++as == 2) { as = 0; aph ^= 1u; }
         }
     }
