@@ -177,10 +177,11 @@ dwconv7_wgrad_generic_kernel(const T* __restrict__ dy, long long ld_dy, const T*
 // Shared-memory tiled kernels for bf16 storage with C % 32 == 0 (every hot-path shape).  A block is persistent over the
 // TW x 8 pixel tiles of one 32-channel block: the (TW+6) x (8+6) halo tile is brought in with 16-byte cp.async copies
 // (out-of-image pixels are zero-filled by the copy itself = the conv padding) into one of two buffers while the other is
-// being consumed, and all arithmetic reads shared memory.  The kernels are FMA-bound (49 FMAs per output element against
-// 4 bytes of HBM traffic), so the inner loops are arranged for FMA density: each thread owns 4 channels x a 4 x 2 pixel
-// patch (forward / data gradient) or 4 channels x one kernel row (weight gradient) and converts every bf16 input once
-// per use row.  TW is 40 for the 160/80/40-pixel-wide maps of 640 x 640 training (exact tiling), 20 for 20, 32 otherwise.
+// being consumed, and all arithmetic reads shared memory.  The kernels are fp32-FMA-pipe-bound (49 FMAs per output element
+// against 4 bytes of HBM traffic), so the inner loops are arranged for FMA density: each thread owns 4 channels x a 4 x 2
+// pixel patch (forward / data gradient) or 4 channels x one kernel row (weight gradient), converts every bf16 input once
+// per use row and issues the arithmetic as packed FFMA2 (two channels per instruction) so that conversions, LDS and
+// address arithmetic fit into the issue slots the FMA pipe leaves free.  TW is 40 for the 160/80/40-pixel-wide maps of 640 x 640 training (exact tiling), 20 for 20, 32 otherwise.
 constexpr int TH = 8, CB = 32;
 constexpr int PIX_B = CB * 2;                       // bytes per pixel in the tile
 constexpr int HALO_H = TH + 6;
@@ -215,21 +216,6 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_x, int tiles_y)
     tc.y0 = (t % tiles_y) * TH;
     tc.b = t / tiles_y;
     return tc;
-}
-
-// halo tile of image b, channels [c0, c0+32), pixels [y0-3, y0+TH+3) x [x0-3, x0+TW+3) -> shared memory (row stride RS)
-template <int TW, int RS>
-__device__ __forceinline__ void load_halo(uint32_t smem, const __nv_bfloat16* __restrict__ x, long long ld_x, TileCoord tc, int H,
-                                          int W, int c0) {
-    constexpr int HW = TW + 6;
-    for (int q = threadIdx.x; q < HALO_H * HW * 4; q += blockDim.x) {
-        const int part = q & 3, pix = q >> 2;
-        const int hy = pix / HW, hx = pix - hy * HW;
-        const int yy = tc.y0 + hy - 3, xx = tc.x0 + hx - 3;
-        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        const __nv_bfloat16* src = ok ? x + (((long long)tc.b * H + yy) * W + xx) * ld_x + c0 + part * 8 : x;
-        cp_async16_zfill(smem + (uint32_t)(hy * RS + hx * PIX_B + part * 16), src, ok);
-    }
 }
 
 // Packed fp32 FMA (sm_100 FFMA2): d = a * b + d on two lanes.  Same FMA-pipe throughput as two FFMAs but ONE issue slot,
@@ -388,68 +374,84 @@ dwconv7_tile_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bf
     }
 }
 
-// Weight gradient.  Thread -> 4 channels (cq) x one kernel row ky x one pair of tile rows; it slides along x keeping the
-// 7 input vectors of its window in registers: acc[kx][4] += dy[y][x][4] * in[y + ky][x + kx][4].
+// Weight gradient.  Thread -> 4 channels (cq) x one kernel row ky x one tile row; it slides along x keeping the 7 input
+// vectors of its window in registers: acc[kx][4] += dy[y][x][4] * in[y + ky][x + kx][4].  Persistent over the tiles of one
+// 32-channel block with double-buffered (halo tile of x, tile of dy) stages: the copies of tile t+1 fly while tile t is
+// consumed, one block barrier per tile.
+constexpr int WG_THREADS = 8 * 7 * TH;          // 448
 template <int TW>
-__global__ void __launch_bounds__(224)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 dwconv7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ x,
                           long long ld_x, int B, int H, int W, int C, int tiles_x, int tiles_y, float* __restrict__ dw) {
     constexpr int RS = rs_wg(TW);
-    constexpr int BUF = HALO_H * RS + TH * TW * PIX_B;           // halo tile of x, then the dy tile
+    constexpr int STAGE = HALO_H * RS + TH * TW * PIX_B;         // halo tile of x, then the dy tile
+    constexpr int HW = TW + 6;
+    static_assert(HW * 4 + TW * 4 <= WG_THREADS, "one loader thread per 16-byte column of either tile");
     extern __shared__ __align__(128) uint8_t dw_smem[];
-    float* s_acc = reinterpret_cast<float*>(dw_smem + BUF);      // [49][CB]
+    float* s_acc = reinterpret_cast<float*>(dw_smem + 2 * STAGE);   // [49][CB]
     const int c0 = blockIdx.x * CB;
     const int cq = threadIdx.x & 7;
-    const int rest = threadIdx.x >> 3;          // 0..27
-    const int ky = rest % 7, rg = rest / 7;     // kernel row, row pair of the tile
+    const int rest = threadIdx.x >> 3;          // 0..55
+    const int ky = rest % 7, row = rest / 7;    // kernel row, tile row of dy
     float2 acc[7][2];
 #pragma unroll
     for (int k = 0; k < 7; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
     for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) s_acc[i] = 0.f;
     const int ntiles = B * tiles_y * tiles_x;
     const uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(dw_smem);
-    for (int t = blockIdx.y; t < ntiles; t += gridDim.y) {
+    // loaders: threads [0, HW*4) walk the halo columns of x, threads [HW*4, HW*4 + TW*4) the columns of dy
+    auto issue = [&](int t, int st) {
         const TileCoord tc = tile_coord<TW>(t, tiles_x, tiles_y);
-        __syncthreads();                        // previous tile fully consumed
-        load_halo<TW, RS>(smem_a, x, ld_x, tc, H, W, c0);
-        for (int q = threadIdx.x; q < TH * TW * 4; q += blockDim.x) {
-            const int part = q & 3, pix = q >> 2;
-            const int yy = tc.y0 + pix / TW, xx = tc.x0 + pix % TW;
-            const bool ok = yy < H && xx < W;
-            const __nv_bfloat16* src = ok ? dy + (((long long)tc.b * H + yy) * W + xx) * ld_dy + c0 + part * 8 : dy;
-            cp_async16_zfill(smem_a + (uint32_t)(HALO_H * RS + pix * PIX_B + part * 16), src, ok);
-        }
-        vk_cp_async_commit();
-        vk_cp_async_wait<0>();
-        __syncthreads();
-        const uint8_t* s_in = dw_smem;
-        const uint8_t* s_dy = s_in + HALO_H * RS;
+        const uint32_t base = smem_a + (uint32_t)(st * STAGE);
+        load_halo_cols<TW, RS>(base, x, ld_x, tc, H, W, c0);
+        const int q = (int)threadIdx.x - HW * 4;
+        if (q >= 0 && q < TW * 4) {
+            const int part = q & 3, px = q >> 2;
+            const int xx = tc.x0 + px;
+            const bool col_ok = xx < W;
+            const long long row_step = (long long)W * ld_dy;
+            const __nv_bfloat16* src = dy + (((long long)tc.b * H + tc.y0) * W + (col_ok ? xx : 0)) * ld_dy + c0 + part * 8;
+            uint32_t dst = base + (uint32_t)(HALO_H * RS + px * PIX_B + part * 16);
 #pragma unroll
-        for (int oy = 0; oy < 2; ++oy) {
-            const int row = rg * 2 + oy;                                   // tile row of dy
-            const uint8_t* inrow = s_in + (row + ky) * RS + cq * 8;        // halo row row + ky  (input row y + ky - 3)
-            const uint8_t* dyrow = s_dy + row * TW * PIX_B + cq * 8;
-            float2 win[7][2];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const uint2 raw = *reinterpret_cast<const uint2*>(inrow + k * PIX_B);
-                win[k + 1][0] = bf2_to_f2(raw.x);
-                win[k + 1][1] = bf2_to_f2(raw.y);
+            for (int r = 0; r < TH; ++r) {
+                const bool ok = col_ok && tc.y0 + r < H;
+                cp_async16_zfill(dst, ok ? src : dy, ok);
+                src += row_step;
+                dst += TW * PIX_B;
             }
+        }
+    };
+    int t = blockIdx.y, st = 0;
+    if (t < ntiles) issue(t, 0);
+    vk_cp_async_commit();
+    for (; t < ntiles; t += gridDim.y, st ^= 1) {
+        vk_cp_async_wait<0>();
+        __syncthreads();                        // tile t has landed; everybody is done with the other stage
+        if (t + (int)gridDim.y < ntiles) issue(t + gridDim.y, st ^ 1);
+        vk_cp_async_commit();
+        const uint8_t* s_in = dw_smem + st * STAGE;
+        const uint8_t* inrow = s_in + (row + ky) * RS + cq * 8;                       // halo row row + ky  (input row y + ky - 3)
+        const uint8_t* dyrow = s_in + HALO_H * RS + row * TW * PIX_B + cq * 8;
+        float2 win[7][2];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(inrow + k * PIX_B);
+            win[k + 1][0] = bf2_to_f2(raw.x);
+            win[k + 1][1] = bf2_to_f2(raw.y);
+        }
 #pragma unroll 8
-            for (int xx = 0; xx < TW; ++xx) {
+        for (int xx = 0; xx < TW; ++xx) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { win[k][0] = win[k + 1][0]; win[k][1] = win[k + 1][1]; }
-                const uint2 raw = *reinterpret_cast<const uint2*>(inrow + (xx + 6) * PIX_B);
-                win[6][0] = bf2_to_f2(raw.x);
-                win[6][1] = bf2_to_f2(raw.y);
-                const uint2 graw = *reinterpret_cast<const uint2*>(dyrow + xx * PIX_B);
-                const float2 g0 = bf2_to_f2(graw.x), g1 = bf2_to_f2(graw.y);
+            for (int k = 0; k < 6; ++k) { win[k][0] = win[k + 1][0]; win[k][1] = win[k + 1][1]; }
+            const uint2 raw = *reinterpret_cast<const uint2*>(inrow + (xx + 6) * PIX_B);
+            win[6][0] = bf2_to_f2(raw.x);
+            win[6][1] = bf2_to_f2(raw.y);
+            const uint2 graw = *reinterpret_cast<const uint2*>(dyrow + xx * PIX_B);
+            const float2 g0 = bf2_to_f2(graw.x), g1 = bf2_to_f2(graw.y);
 #pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    ffma2(acc[k][0], g0, win[k][0]);
-                    ffma2(acc[k][1], g1, win[k][1]);
-                }
+            for (int k = 0; k < 7; ++k) {
+                ffma2(acc[k][0], g0, win[k][0]);
+                ffma2(acc[k][1], g1, win[k][1]);
             }
         }
     }
@@ -491,18 +493,18 @@ int launch_dw_wgrad_tile(const void* dy, long long ld_dy, const void* x, long lo
     const int tiles_x = vk_cdiv(W, TW), tiles_y = vk_cdiv(H, TH);
     const long long ntiles = (long long)B * tiles_x * tiles_y;
     const int cblocks = C / CB;
-    const int smem = HALO_H * rs_wg(TW) + TH * TW * PIX_B + 49 * CB * (int)sizeof(float);
+    const int smem = 2 * (HALO_H * rs_wg(TW) + TH * TW * PIX_B) + 49 * CB * (int)sizeof(float);
     cudaFuncSetAttribute(dwconv7_wgrad_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    // persistent over tiles: exactly the number of blocks that are resident at once (registers, not shared memory, bound
-    // it), rounded DOWN -- a partial second wave costs a whole block's run time
+    // persistent over tiles: exactly the number of blocks that are resident at once, rounded DOWN -- a partial second
+    // wave costs a whole block's run time
     static int per_sm = 0;
     if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_wgrad_tile_kernel<TW>, 224, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_wgrad_tile_kernel<TW>, WG_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     }
     long long gy = ((long long)vkocr_sm_count() * per_sm) / cblocks;
     if (gy > ntiles) gy = ntiles;
     if (gy < 1) gy = 1;
-    dwconv7_wgrad_tile_kernel<TW><<<dim3((unsigned)cblocks, (unsigned)gy), 224, smem, s>>>(
+    dwconv7_wgrad_tile_kernel<TW><<<dim3((unsigned)cblocks, (unsigned)gy), WG_THREADS, smem, s>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy), ld_dy, reinterpret_cast<const __nv_bfloat16*>(x), ld_x, B, H, W, C, tiles_x,
         tiles_y, dw);
     return 0;
