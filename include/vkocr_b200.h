@@ -69,16 +69,17 @@ typedef struct VkocrEpilogue {
     long long ldo;
     int out_f32;
     int accumulate;       /* out += value (fp32 atomics; requires out_f32) */
-    void* out_pre;        /* optional copy of (acc + bias) before the activation (kept for GELU backward) */
+    void* out_pre;        /* optional second output: (acc + bias) before the activation; act 3: gelu'(acc + bias) */
     long long ld_pre;
     const float* bias;    /* [N] or NULL */
-    int act;              /* 0 none, 1 exact erf GELU (helper.py:100-101), 2 multiply by gelu'(aux) */
+    int act;              /* 0 none, 1 exact erf GELU (helper.py:100-101), 2 multiply by gelu'(aux),
+                             3 exact GELU with out_pre = gelu'(acc + bias), 4 multiply by aux */
     const float* col_scale;  /* [N] or NULL — ConvNeXt layer scale (convnext.py:38,56) */
     const float* row_scale;  /* [rows / rows_per_group] or NULL — stochastic-depth mask (convnext.py:41-53) */
     int rows_per_group;
     const void* residual; /* optional [rows, ld_res] storage dtype, added last (convnext.py:58) */
     long long ld_res;
-    const void* aux;      /* act == 2 operand */
+    const void* aux;      /* act == 2 / 4 operand */
     long long ld_aux;
     long long tn_s_tap, tn_s_i, tn_s_j; /* TN: G[tap,i,j] lands at out[tap*s_tap + i*s_i + j*s_j] (e.g. Conv2d OIHW) */
 } VkocrEpilogue;

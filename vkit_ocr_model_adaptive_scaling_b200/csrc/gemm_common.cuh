@@ -23,16 +23,16 @@ struct VkocrEpilogue {
     long long ldo;
     int out_f32;           // 1: `out` is fp32 regardless of the activation dtype
     int accumulate;        // 1: out += value (fp32 atomics; requires out_f32)
-    void* out_pre;         // optional copy of (acc + bias) before the activation, storage dtype
+    void* out_pre;         // optional second output, storage dtype: (acc + bias) before the activation; act == 3: gelu'(acc + bias)
     long long ld_pre;
     const float* bias;     // [N] or null
-    int act;               // 0 none, 1 exact GELU, 2 multiply by gelu'(aux)
+    int act;               // 0 none, 1 exact GELU, 2 multiply by gelu'(aux), 3 exact GELU with out_pre = gelu', 4 multiply by aux
     const float* col_scale;  // [N] or null  (ConvNeXt layer scale, convnext.py:38,56)
     const float* row_scale;  // [rows / rows_per_group] or null (stochastic-depth mask, convnext.py:41-53)
     int rows_per_group;
     const void* residual;  // optional [rows, ld_res] storage dtype, added last (convnext.py:58)
     long long ld_res;
-    const void* aux;       // act == 2: value *= gelu'(aux[m, n]) (GELU backward fused into the data-gradient GEMM)
+    const void* aux;       // act == 2: value *= gelu'(aux[m, n]); act == 4: value *= aux[m, n] (GELU backward fused into the data-gradient GEMM)
     long long ld_aux;
     // TN only: element (tap, i, j) is accumulated at out[tap*tn_s_tap + i*tn_s_i + j*tn_s_j] (lets the weight gradient
     // land directly in the parameter's own layout, e.g. Conv2d OIHW: s_tap=1, s_i=Cin*taps, s_j=taps)
@@ -65,9 +65,17 @@ template <typename T>
 __device__ __forceinline__ float vk_epilogue_value(const VkocrEpilogue& ep, long long m, int n, float acc) {
     float v = acc;
     if (ep.bias) v += __ldg(ep.bias + n);
-    if (ep.out_pre) reinterpret_cast<T*>(ep.out_pre)[m * ep.ld_pre + n] = vk_from_f32<T>(v);
-    if (ep.act == 1) v = vk_gelu(v);
-    else if (ep.act == 2) v *= vk_gelu_grad(vk_to_f32(reinterpret_cast<const T*>(ep.aux)[m * ep.ld_aux + n]));
+    if (ep.act == 3) {
+        float g, dg;
+        vk_gelu_both(v, &g, &dg);
+        if (ep.out_pre) reinterpret_cast<T*>(ep.out_pre)[m * ep.ld_pre + n] = vk_from_f32<T>(dg);
+        v = g;
+    } else {
+        if (ep.out_pre) reinterpret_cast<T*>(ep.out_pre)[m * ep.ld_pre + n] = vk_from_f32<T>(v);
+        if (ep.act == 1) v = vk_gelu(v);
+        else if (ep.act == 2) v *= vk_gelu_grad(vk_to_f32(reinterpret_cast<const T*>(ep.aux)[m * ep.ld_aux + n]));
+        else if (ep.act == 4) v *= vk_to_f32(reinterpret_cast<const T*>(ep.aux)[m * ep.ld_aux + n]);
+    }
     if (ep.col_scale) v *= __ldg(ep.col_scale + n);
     if (ep.row_scale) v *= __ldg(ep.row_scale + (m / ep.rows_per_group));
     if (ep.residual) v += vk_to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + n]);

@@ -444,7 +444,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
             const bool vec_ok = (p.mode == 0) && (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
-                                (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0);
+                                (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0) && ep.act <= 2;
             if (p.head_mode) {
                 // ---- fused head tail (one head per N tile): conv bias -> [conv output stored for the backward] ->
                 // LayerNorm over the head's `inner` columns -> exact GELU -> projection to O <= 4 maps (-> Softplus), all
@@ -593,7 +593,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 const uint32_t sw = (uint32_t)((lane >> 1) & 3);
                 const int r0 = q * 32;
                 const __nv_bfloat16* esrc = ep.residual ? reinterpret_cast<const __nv_bfloat16*>(ep.residual)
-                                                        : (ep.act == 2 ? reinterpret_cast<const __nv_bfloat16*>(ep.aux) : nullptr);
+                                                        : ((ep.act == 2 || ep.act == 4) ? reinterpret_cast<const __nv_bfloat16*>(ep.aux) : nullptr);
                 const long long eld = ep.residual ? ep.ld_res : ep.ld_aux;
                 const float rs = (ep.row_scale && row_ok) ? __ldg(ep.row_scale + fd_div((uint32_t)row, p.fd_rpg)) : 1.f;
                 // global pixel index of the 4 staged rows this lane moves (rows 8*i + lane/4 of the warp's quarter)
@@ -629,9 +629,9 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         __syncwarp();
                     }
                     // stage the lane's 32 finished values and write the warp's tile out as coalesced row segments
-                    auto store_tile = [&](const float* vals, void* base, long long ld) {
+                    auto store_packed = [&](const uint4 (&pk)[4], void* base, long long ld) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pack8(vals + 8 * j));
+                        for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pk[j]);
                         __syncwarp();
                         if (col < col_end && !(p.skip_tma & 8)) {   // debug bit 3: no global stores
                             __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(base);
@@ -645,6 +645,12 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                             }
                         }
                         __syncwarp();      // the tile is free again
+                    };
+                    auto store_tile = [&](const float* vals, void* base, long long ld) {
+                        uint4 pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pk[j] = pack8(vals + 8 * j);
+                        store_packed(pk, base, ld);
                     };
                     float v[32];
                     {
@@ -672,17 +678,39 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                             for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(ep.bias + nb + j) : 0.f;
                         }
                     }
-                    if (ep.out_pre) store_tile(v, ep.out_pre, ep.ld_pre);      // pre-activation copy (acc + bias)
-                    if (ep.act == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
-                    } else if (ep.act == 2) {
+                    if (ep.act == 3) {
+                        // GELU and its derivative share all transcendental work: the derivative is what the backward
+                        // needs (second output), the pre-activation itself is never read again
+                        uint4 pk[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            float f[8];
-                            unpack8(extra[j], f);
+                            float dg[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
+                            for (int e = 0; e < 8; ++e) vk_gelu_both(v[8 * j + e], &v[8 * j + e], &dg[e]);
+                            pk[j] = pack8(dg);
+                        }
+                        if (ep.out_pre) store_packed(pk, ep.out_pre, ep.ld_pre);
+                    } else {
+                        if (ep.out_pre) store_tile(v, ep.out_pre, ep.ld_pre);      // pre-activation copy (acc + bias)
+                        if (ep.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
+                        } else if (ep.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float f[8];
+                                unpack8(extra[j], f);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
+                            }
+                        } else if (ep.act == 4) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float f[8];
+                                unpack8(extra[j], f);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[8 * j + e] *= f[e];
+                            }
                         }
                     }
                     if (ep.col_scale && vec_in_smem && full) {
@@ -965,7 +993,7 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     p.M = g->W;
     p.staged_store = !ep->out_f32 && !ep->accumulate && (N % 8 == 0) && aligned(ep->out, ep->ldo) &&
                      (!ep->out_pre || aligned(ep->out_pre, ep->ld_pre)) && (!ep->residual || aligned(ep->residual, ep->ld_res)) &&
-                     (ep->act != 2 || aligned(ep->aux, ep->ld_aux)) && (long long)g->batch * g->H * g->W < (1LL << 31);
+                     ((ep->act != 2 && ep->act != 4) || aligned(ep->aux, ep->ld_aux)) && (long long)g->batch * g->H * g->W < (1LL << 31);
     return launch(mapA, mapB, p, stream);
 }
 

@@ -427,9 +427,11 @@ class ConvNextLayerFn(torch.autograd.Function):
         hid = 4 * C
         w1p, c1 = packed_linear_fwd(w1, dt)
         g = torch.empty((M, hid), dtype=dt, device=dev)
+        # training: the second output is gelu'(H_pre) (act 3) -- all the backward ever needs of the pre-activation, and it
+        # shares the transcendental work with the GELU itself
         hpre = torch.empty((M, hid), dtype=dt, device=dev) if train else None
         gemm_nt(lnout, 1, 1, M, C, lnout.stride(3), 1, w1p, c1, hid,
-                _epilogue(g, hid, out_pre=hpre, ld_pre=hid, bias=b1.detach(), act=1))
+                _epilogue(g, hid, out_pre=hpre, ld_pre=hid, bias=b1.detach(), act=3 if train else 1))
         w2p, c2 = packed_linear_fwd(w2, dt)
         y = alloc_nhwc(B, H, W, C, dt, dev)
         gamma = scale.detach().reshape(-1)
@@ -459,10 +461,10 @@ class ConvNextLayerFn(torch.autograd.Function):
         else:
             u = dy
             colsum(u, u.stride(3), M, C, su)
-        # dH_pre = (U . (gamma * W2)) * gelu'(H_pre)
+        # dH_pre = (U . (gamma * W2)) * gelu'(H_pre)   (hpre holds gelu'(H_pre), written by the forward)
         w2d, n2 = packed_linear_dgrad(w2, dt, scale)
         dh = torch.empty((M, hid), dtype=dt, device=dev)
-        gemm_nt(u, 1, 1, M, C, u.stride(3), 1, w2d, n2, hid, _epilogue(dh, hid, act=2, aux=hpre, ld_aux=hid))
+        gemm_nt(u, 1, 1, M, C, u.stride(3), 1, w2d, n2, hid, _epilogue(dh, hid, act=4, aux=hpre, ld_aux=hid))
         # S[c,k] = sum_p U[p,c] G[p,k]  -> dW2, dscale, db2
         s = _zeros_f32(C * hid, dev)
         gemm_tn(u, 1, 1, M, C, u.stride(3), 1, g, hid, hid, _epilogue(s, hid, out_f32=True, accumulate=True, tn=(0, hid, 1)))
