@@ -172,8 +172,45 @@ head_tail_fwd_kernel(const T* __restrict__ x, long long ld_x, int inner, const f
     }
 }
 
+// The lane's channel vectors of the row in `slot` as fp32 PAIRS, zeros beyond `inner`.
+template <typename T> struct PairUnpack;
+template <> struct PairUnpack<float> {
+    static __device__ __forceinline__ void run(const float4& raw, float2 (&p)[2]) { p[0] = make_float2(raw.x, raw.y); p[1] = make_float2(raw.z, raw.w); }
+};
+template <> struct PairUnpack<__nv_bfloat16> {
+    static __device__ __forceinline__ void run(const uint4& raw, float2 (&p)[4]) {
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+    }
+};
+template <typename T, int NVL>
+__device__ __forceinline__ void ring_fetch2(const uint4* ring, int slot, int lane, int inner, float2 (&f)[NVL][VkVec<T>::N / 2]) {
+    constexpr int V = VkVec<T>::N;
+#pragma unroll
+    for (int j = 0; j < NVL; ++j) {
+        const int c = (lane + 32 * j) * V;
+        if (c < inner) {
+            VkVec<T> v;
+            v.raw = *reinterpret_cast<const decltype(v.raw)*>(ring + (slot * NVL + j) * HT_THREADS + threadIdx.x);
+            PairUnpack<T>::run(v.raw, f[j]);
+            if (c + V > inner) {
+#pragma unroll
+                for (int i = 0; i < V / 2; ++i) {
+                    if (c + 2 * i >= inner) f[j][i].x = 0.f;
+                    if (c + 2 * i + 1 >= inner) f[j][i].y = 0.f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < V / 2; ++i) f[j][i] = make_float2(0.f, 0.f);
+        }
+    }
+}
+
 // Backward.  Per-channel gradient partials (dgamma, dbeta, conv-bias, dW2) live in registers of the lane that owns the
-// channel for all rows the warp visits.
+// channel for all rows the warp visits.  All per-element arithmetic runs on fp32 PAIRS (FFMA2 / FMUL2 / FADD2): the
+// kernel is bound by instruction issue, and a packed instruction takes one issue slot for two channels.
 template <typename T, int NVL, int O>
 __global__ void __launch_bounds__(HT_THREADS, (NVL * O <= 4) ? 2 : 1)
 head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int slice_w, const float* __restrict__ gamma,
@@ -182,6 +219,7 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
                      long long ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw2,
                      float* __restrict__ db2, float* __restrict__ dbias) {
     constexpr int V = VkVec<T>::N;
+    constexpr int P = V / 2;
     constexpr int CW = 32 * NVL * V;
     constexpr int RING = RingDepth<NVL>::value;
     extern __shared__ uint4 ring[];   // [RING][NVL][HT_THREADS] vectors, then [RING][HT_WARPS][2 * O] upstream values, then sacc
@@ -189,7 +227,7 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
     float* sacc = dring + RING * HT_WARPS * 2 * O;   // [(3 + O)][CW] + [O]
     // O >= 3: the projection weights stay in shared memory (32 registers of them would spill the accumulators)
     constexpr bool W_SMEM = O >= 3;
-    float* s_w = sacc + (3 + O) * CW + O;            // [O][CW], only when W_SMEM
+    float* s_w = sacc + (3 + O) * CW + O + ((3 + O) * CW + O) % 2;   // [O][CW], only when W_SMEM (8-byte aligned)
     for (int i = threadIdx.x; i < (3 + O) * CW + O; i += blockDim.x) sacc[i] = 0.f;
     if (W_SMEM)
         for (int i = threadIdx.x; i < O * CW; i += blockDim.x) {
@@ -200,24 +238,24 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
     const int lane = threadIdx.x & 31;
     const unsigned warp0 = blockIdx.x * HT_WARPS + (threadIdx.x >> 5);
     const unsigned nwarps = gridDim.x * HT_WARPS;
-    float gm[NVL][V], bt[NVL][V], w[W_SMEM ? 1 : O][NVL][V];
-    float ag[NVL][V], ab[NVL][V], ax[NVL][V], aw[O][NVL][V];
+    float2 gm[NVL][P], bt[NVL][P], w[W_SMEM ? 1 : O][NVL][P];
+    float2 ag[NVL][P], ab[NVL][P], ax[NVL][P], aw[O][NVL][P];
     float adb[O];
 #pragma unroll
     for (int o = 0; o < O; ++o) adb[o] = 0.f;
+    auto ldc = [&](const float* p, int c) { return c < inner ? __ldg(p + c) : 0.f; };
 #pragma unroll
     for (int j = 0; j < NVL; ++j)
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const int c = (lane + 32 * j) * V + i;
-            const bool ok = c < inner;
-            gm[j][i] = ok ? __ldg(gamma + c) : 0.f;
-            bt[j][i] = ok ? __ldg(beta + c) : 0.f;
-            ag[j][i] = ab[j][i] = ax[j][i] = 0.f;
+        for (int i = 0; i < P; ++i) {
+            const int c = (lane + 32 * j) * V + 2 * i;
+            gm[j][i] = make_float2(ldc(gamma, c), ldc(gamma, c + 1));
+            bt[j][i] = make_float2(ldc(beta, c), ldc(beta, c + 1));
+            ag[j][i] = ab[j][i] = ax[j][i] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int o = 0; o < O; ++o) {
-                if (!W_SMEM) w[o][j][i] = ok ? __ldg(w2 + (long long)o * inner + c) : 0.f;
-                aw[o][j][i] = 0.f;
+                if (!W_SMEM) w[o][j][i] = make_float2(ldc(w2 + (long long)o * inner, c), ldc(w2 + (long long)o * inner, c + 1));
+                aw[o][j][i] = make_float2(0.f, 0.f);
             }
         }
     const float inv = 1.f / inner;
@@ -241,12 +279,12 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
     for (int d = 0; d < RING; ++d) issue((unsigned long long)warp0 + (unsigned long long)d * nwarps, d);
     int slot = 0;
     for (unsigned r = warp0; r < rows; r += nwarps) {
-        float f[NVL][V];
+        float2 f[NVL][P];
         vk_cp_async_wait<RING - 1>();
         __syncwarp();                                   // the upstream values were copied by other lanes
-        ring_fetch<T, NVL>(ring, slot, lane, inner, f);
+        ring_fetch2<T, NVL>(ring, slot, lane, inner, f);
         // upstream gradient of the pre-softplus outputs (same value in every lane)
-        float dpre[O];
+        float2 dpre[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) {
             const float* dr = dring + (slot * HT_WARPS + wib) * 2 * O;
@@ -255,44 +293,65 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
                 const float y = dr[O + o];
                 d *= (y > 20.f) ? 1.f : (1.f - __expf(-y));   // sigmoid(pre) = 1 - exp(-softplus(pre))
             }
-            dpre[o] = d;
+            dpre[o] = vk_splat2(d);
             adb[o] += d;
         }
         __syncwarp();                                   // every lane has read the slot before it is refilled
         issue((unsigned long long)r + (unsigned long long)RING * nwarps, slot);
         slot = (slot + 1) & (RING - 1);
+        // LayerNorm statistics: one shuffle round of shifted sums (pad channels hold zeros and are corrected for)
         float mean, rstd;
-        row_stats<NVL, V>(f, inner, npad, inv, &mean, &rstd);
-        const float shift = -mean * rstd;
-        float s1 = 0.f, s2 = 0.f;
+        {
+            const float x0 = __shfl_sync(0xffffffffu, f[0][0].x, 0);
+            const float2 nx0 = vk_splat2(-x0);
+            float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < NVL; ++j)
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const float2 d = vk_add2(f[j][i], nx0);
+                    s = vk_add2(s, d);
+                    q = vk_fma2(d, d, q);
+                }
+            const float2 rsum = warp_sum2(s.x + s.y, q.x + q.y);
+            const float ss = rsum.x + (float)npad * x0;
+            const float qq = rsum.y - (float)npad * x0 * x0;
+            const float m = ss * inv;                         // mean - x0
+            mean = x0 + m;
+            rstd = rsqrtf(fmaxf(fmaf(-m, m, qq * inv), 0.f) + LN_EPS);
+        }
+        const float2 rstd2 = vk_splat2(rstd), shift2 = vk_splat2(-mean * rstd);
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
         // after this loop f holds xhat and dz holds d(loss)/d(LN output) * gamma per channel.  Pad channels: gamma = beta =
         // w = 0 there, so z = 0, dg = 0 and every product below vanishes without a mask.
-        float dz[NVL][V];
+        float2 dz[NVL][P];
 #pragma unroll
         for (int j = 0; j < NVL; ++j)
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const float h = fmaf(f[j][i], rstd, shift);
-                float g, gp;
-                vk_gelu_both(fmaf(h, gm[j][i], bt[j][i]), &g, &gp);
-                float dg = 0.f;
+            for (int i = 0; i < P; ++i) {
+                const float2 h = vk_fma2(f[j][i], rstd2, shift2);
+                float2 g, gp;
+                vk_gelu_both2(vk_fma2(h, gm[j][i], bt[j][i]), &g, &gp);
+                float2 dg;
 #pragma unroll
                 for (int o = 0; o < O; ++o) {
-                    const float wv = W_SMEM ? s_w[o * CW + (lane + 32 * j) * V + i] : w[o][j][i];
-                    dg = fmaf(dpre[o], wv, dg);
-                    aw[o][j][i] = fmaf(dpre[o], g, aw[o][j][i]);
+                    const float2 wv = W_SMEM ? *reinterpret_cast<const float2*>(s_w + o * CW + (lane + 32 * j) * V + 2 * i) : w[o][j][i];
+                    dg = o == 0 ? vk_mul2(dpre[0], wv) : vk_fma2(dpre[o], wv, dg);
+                    aw[o][j][i] = vk_fma2(dpre[o], g, aw[o][j][i]);
                 }
-                const float d = dg * gp;
-                const float dxh = d * gm[j][i];
+                const float2 d = vk_mul2(dg, gp);
+                const float2 dxh = vk_mul2(d, gm[j][i]);
                 f[j][i] = h;
                 dz[j][i] = dxh;
-                s1 += dxh;
-                s2 = fmaf(dxh, h, s2);
-                ag[j][i] = fmaf(d, h, ag[j][i]);
-                ab[j][i] += d;
+                s1 = vk_add2(s1, dxh);
+                s2 = vk_fma2(dxh, h, s2);
+                ag[j][i] = vk_fma2(d, h, ag[j][i]);
+                ab[j][i] = vk_add2(ab[j][i], d);
             }
-        const float2 ss = warp_sum2(s1, s2);
+        const float2 ss = warp_sum2(s1.x + s1.y, s2.x + s2.y);
         const float m1 = ss.x * inv, m2 = ss.y * inv;
+        // dx = rstd * (dz - m1 - xhat * m2) = dz * rstd + (xhat * (-m2 rstd) + (-m1 rstd))
+        const float2 cb = vk_splat2(-m1 * rstd), cc = vk_splat2(-m2 * rstd);
         T* dxr = dx + (long long)r * ld_dx;
 #pragma unroll
         for (int j = 0; j < NVL; ++j) {
@@ -300,11 +359,15 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
             if (c0 < slice_w) {
                 float fo[V];
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    float dxv = rstd * (dz[j][i] - m1 - f[j][i] * m2);
-                    if (c0 + V > inner) dxv = (c0 + i < inner) ? dxv : 0.f;
-                    fo[i] = dxv;
-                    ax[j][i] += dxv;
+                for (int i = 0; i < P; ++i) {
+                    float2 dxv = vk_fma2(dz[j][i], rstd2, vk_fma2(f[j][i], cc, cb));
+                    if (c0 + V > inner) {
+                        if (c0 + 2 * i >= inner) dxv.x = 0.f;
+                        if (c0 + 2 * i + 1 >= inner) dxv.y = 0.f;
+                    }
+                    fo[2 * i] = dxv.x;
+                    fo[2 * i + 1] = dxv.y;
+                    ax[j][i] = vk_add2(ax[j][i], dxv);
                 }
                 VkVec<T> vo;
                 vo.pack(fo);
@@ -318,11 +381,11 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
         for (int i = 0; i < V; ++i) {
             const int c = (lane + 32 * j) * V + i;
             if (c < inner) {
-                atomicAdd(&sacc[c], ag[j][i]);
-                atomicAdd(&sacc[CW + c], ab[j][i]);
-                atomicAdd(&sacc[2 * CW + c], ax[j][i]);
+                atomicAdd(&sacc[c], (i & 1) ? ag[j][i / 2].y : ag[j][i / 2].x);
+                atomicAdd(&sacc[CW + c], (i & 1) ? ab[j][i / 2].y : ab[j][i / 2].x);
+                atomicAdd(&sacc[2 * CW + c], (i & 1) ? ax[j][i / 2].y : ax[j][i / 2].x);
 #pragma unroll
-                for (int o = 0; o < O; ++o) atomicAdd(&sacc[(3 + o) * CW + c], aw[o][j][i]);
+                for (int o = 0; o < O; ++o) atomicAdd(&sacc[(3 + o) * CW + c], (i & 1) ? aw[o][j][i / 2].y : aw[o][j][i / 2].x);
             }
         }
     if (lane == 0) {
@@ -375,7 +438,7 @@ int launch_bwd(int O, const void* x, long long ld_x, int inner, int slice_w, con
 #define VK_HT_BWD(OO)                                                                                                       \
     cudaFuncSetAttribute(head_tail_bwd_kernel<T, NVL, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);         \
     head_tail_bwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS,                                                        \
-        RING * NVL * HT_THREADS * 16 + (RING * HT_WARPS * 2 * OO + (3 + OO + (OO >= 3 ? OO : 0)) * 32 * NVL * V + OO) * sizeof(float), s>>>(      \
+        RING * NVL * HT_THREADS * 16 + (RING * HT_WARPS * 2 * OO + (3 + OO + (OO >= 3 ? OO : 0)) * 32 * NVL * V + OO + 1) * sizeof(float), s>>>(      \
         reinterpret_cast<const T*>(x), ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, (unsigned)ppi, inv_ppi,  \
         (unsigned)rows, reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias)
     switch (O) {
