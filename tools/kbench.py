@@ -54,14 +54,14 @@ if 'mlp' in groups:
         b1 = rnd(hid, dtype=torch.float32); b2 = rnd(C, dtype=torch.float32); gam = torch.rand(C, device=dev)
         g = torch.empty(M, hid, device=dev, dtype=BF); hpre = torch.empty_like(g); dh = torch.empty_like(g)
         y = torch.empty(M, C, device=dev, dtype=BF)
-        ms = timeit(lambda: ops.gemm_nt(x, 1, 1, M, C, C, 1, w1, cp, hid, ops._epilogue(g, hid, out_pre=hpre, ld_pre=hid, bias=b1, act=1)))
-        report(f'mlp1 fwd  M{M} K{C} N{hid} +bias+gelu+pre', ms, (M * C + 2 * M * hid) * 2, 2.0 * M * C * hid)
+        ms = timeit(lambda: ops.gemm_nt(x, 1, 1, M, C, C, 1, w1, cp, hid, ops._epilogue(g, hid, out_pre=hpre, ld_pre=hid, bias=b1, act=3)))
+        report(f'mlp1 fwd  M{M} K{C} N{hid} +bias+gelu+gelu\'', ms, (M * C + 2 * M * hid) * 2, 2.0 * M * C * hid)
         ms = timeit(lambda: ops.gemm_nt(x, 1, 1, M, C, C, 1, w1, cp, hid, ops._epilogue(g, hid, bias=b1, act=1)))
         report(f'mlp1 eval M{M} K{C} N{hid} +bias+gelu', ms, (M * C + M * hid) * 2, 2.0 * M * C * hid)
         ms = timeit(lambda: ops.gemm_nt(g, 1, 1, M, hid, hid, 1, w2, hid, C, ops._epilogue(y, C, bias=b2, col_scale=gam, residual=x, ld_res=C)))
         report(f'mlp2 fwd  M{M} K{hid} N{C} +bias+scale+res', ms, (M * hid + 2 * M * C) * 2, 2.0 * M * C * hid)
-        ms = timeit(lambda: ops.gemm_nt(x, 1, 1, M, C, C, 1, w2d, cp, hid, ops._epilogue(dh, hid, act=2, aux=hpre, ld_aux=hid)))
-        report(f'mlp2 dgrad M{M} K{C} N{hid} *gelu\'(aux)', ms, (M * C + 2 * M * hid) * 2, 2.0 * M * C * hid)
+        ms = timeit(lambda: ops.gemm_nt(x, 1, 1, M, C, C, 1, w2d, cp, hid, ops._epilogue(dh, hid, act=4, aux=hpre, ld_aux=hid)))
+        report(f'mlp2 dgrad M{M} K{C} N{hid} *aux', ms, (M * C + 2 * M * hid) * 2, 2.0 * M * C * hid)
         ms = timeit(lambda: ops.gemm_nt(dh, 1, 1, M, hid, hid, 1, w1d, hid, C, ops._epilogue(y, C)))
         report(f'mlp1 dgrad M{M} K{hid} N{C}', ms, (M * hid + M * C) * 2, 2.0 * M * C * hid)
         s = torch.zeros(C * hid, device=dev)

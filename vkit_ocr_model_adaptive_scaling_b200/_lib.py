@@ -128,6 +128,8 @@ def _load() -> ctypes.CDLL:
     path = _build.LIB
     if not os.path.exists(path) or os.environ.get('VKOCR_B200_REBUILD') == '1':
         path = _build.build()
+    if os.environ.get('VKOCR_B200_LIB'):        # development: A/B a differently built copy of the same ABI
+        path = os.environ['VKOCR_B200_LIB']
     lib = ctypes.CDLL(path)
     lib.vkocr_last_error.restype = ctypes.c_char_p
     lib.vkocr_launch_count.restype = ctypes.c_longlong

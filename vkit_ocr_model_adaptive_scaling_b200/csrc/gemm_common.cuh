@@ -23,7 +23,7 @@ struct VkocrEpilogue {
     long long ldo;
     int out_f32;           // 1: `out` is fp32 regardless of the activation dtype
     int accumulate;        // 1: out += value (fp32 atomics; requires out_f32)
-    void* out_pre;         // optional second output, storage dtype: (acc + bias) before the activation; act == 3: gelu'(acc + bias)
+    void* out_pre;         // optional second output, storage dtype: (acc + bias) before the activation; act == 3: gelu'(acc + bias) (fp16 bits when the storage is 16-bit)
     long long ld_pre;
     const float* bias;     // [N] or null
     int act;               // 0 none, 1 exact GELU, 2 multiply by gelu'(aux), 3 exact GELU with out_pre = gelu', 4 multiply by aux
@@ -59,6 +59,16 @@ struct VkocrHeadTail {
     int softplus[VKOCR_MAX_HEADS];
 };
 
+// gelu' side channel (act 3 writes it, act 4 reads it): in 16-bit storage it travels as IEEE fp16 BITS inside the bf16
+// buffer -- |gelu'| <= 1.13, and fp16's 11-bit significand keeps the derivative 8x more accurate than a bf16 rounding
+// (a bf16-rounded derivative alone raised the end-to-end bf16 gradient error of the TINY model from 1.3e-2 to 2.1e-2).
+template <typename T> __device__ __forceinline__ void vk_store_dgelu(T* p, float v);
+template <> __device__ __forceinline__ void vk_store_dgelu<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void vk_store_dgelu<__nv_bfloat16>(__nv_bfloat16* p, float v) { *reinterpret_cast<__half*>(p) = __float2half_rn(v); }
+template <typename T> __device__ __forceinline__ float vk_load_dgelu(const T* p);
+template <> __device__ __forceinline__ float vk_load_dgelu<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float vk_load_dgelu<__nv_bfloat16>(const __nv_bfloat16* p) { return __half2float(*reinterpret_cast<const __half*>(p)); }
+
 // Apply the epilogue to one accumulator value and return the value to store in `out`.
 // Side effect: writes out_pre when requested.
 template <typename T>
@@ -68,13 +78,13 @@ __device__ __forceinline__ float vk_epilogue_value(const VkocrEpilogue& ep, long
     if (ep.act == 3) {
         float g, dg;
         vk_gelu_both(v, &g, &dg);
-        if (ep.out_pre) reinterpret_cast<T*>(ep.out_pre)[m * ep.ld_pre + n] = vk_from_f32<T>(dg);
+        if (ep.out_pre) vk_store_dgelu<T>(reinterpret_cast<T*>(ep.out_pre) + m * ep.ld_pre + n, dg);
         v = g;
     } else {
         if (ep.out_pre) reinterpret_cast<T*>(ep.out_pre)[m * ep.ld_pre + n] = vk_from_f32<T>(v);
         if (ep.act == 1) v = vk_gelu(v);
         else if (ep.act == 2) v *= vk_gelu_grad(vk_to_f32(reinterpret_cast<const T*>(ep.aux)[m * ep.ld_aux + n]));
-        else if (ep.act == 4) v *= vk_to_f32(reinterpret_cast<const T*>(ep.aux)[m * ep.ld_aux + n]);
+        else if (ep.act == 4) v *= vk_load_dgelu<T>(reinterpret_cast<const T*>(ep.aux) + m * ep.ld_aux + n);
     }
     if (ep.col_scale) v *= __ldg(ep.col_scale + n);
     if (ep.row_scale) v *= __ldg(ep.row_scale + (m / ep.rows_per_group));

@@ -30,6 +30,7 @@ constexpr int NUM_THREADS = 512;         // warps 0-3: TMA / MMA / TMEM alloc / 
 constexpr int EPI_WARPS = 12;            // three warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int HEAD_PAR_BYTES = 7 * 256 * 4;                 // fused head tail: gamma, beta, conv bias, w2[4] of the CTA's head
 constexpr int HEAD_XCH_BYTES = EPI_WARPS * 32 * 6 * 4;      // per-warp partial row statistics (2) and projections (4)
+constexpr int PREFETCH_BYTES = EPI_WARPS * EPI_TILE_BYTES;   // second set of staging tiles, carved out of the operand-stage budget
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 
@@ -69,6 +70,7 @@ struct TcParams {
     int stage_bytes;
     int skip_tma;            // debug: producers arrive without loading (timing experiments)
     int staged_store;        // NT: aligned bf16 outputs leave through the shared-memory staging tiles
+    int prefetch_extra;      // NT staged path: residual / aux tiles are prefetched one chunk ahead (cp.async) into a second set of staging tiles
     int M;                   // NT plain GEMM: number of rows
     long long units;
     int head_mode;           // NT: fused head tail epilogue (ht valid)
@@ -144,6 +146,23 @@ __device__ __forceinline__ void unpack8(uint4 raw, float* f) {
         f[2 * i + 1] = v.y;
     }
 }
+// fp16 flavour for the gelu' side channel (see vk_store_dgelu)
+__device__ __forceinline__ void unpack8_f16(uint4 raw, float* f) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = __half22float2(h[i]);
+        f[2 * i] = v.x;
+        f[2 * i + 1] = v.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8_f16(const float* f) {
+    uint4 raw;
+    __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return raw;
+}
 __device__ __forceinline__ uint4 pack8(const float* f) {
     uint4 raw;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
@@ -169,14 +188,17 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        // The wait lives in the SAME asm statement as the load: as a separate statement nothing ties it to the 32 result
+        // registers, and the compiler may schedule their consumers (in particular non-volatile inline-asm arithmetic)
+        // between the asynchronous load and its wait -- observed as a 1.5e-2 -> 2.0e-2 jump of the bf16 gradient error.
+        "tcgen05.wait::ld.sync.aligned;"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.  Offsets are in 16-byte units.
@@ -427,6 +449,8 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         }
+        bool pf_issued = false;                 // the first chunk of the coming tile is already being prefetched
+        const uint32_t pre_base = bar_base + 256u;
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit t = decode(u);
             bool row_ok;
@@ -608,13 +632,50 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 }
                 const int seg = lane & 3;
                 const int col_end = (t.n0 + BN < p.N) ? t.n0 + BN : p.N;   // 8-column groups are all-or-nothing
+                // Prefetch of the residual / aux tile of chunk cc of tile tt into the warp's second staging tile (same
+                // swizzled layout).  A synchronous load here exposes a full DRAM round trip per chunk, which bounded the
+                // K <= 384 GEMMs; the copy for the next chunk (or the next tile's first chunk) now flies during this one.
+                const uint32_t pwb = pre_base + (uint32_t)(warp - 4) * (uint32_t)EPI_TILE_BYTES;
+                auto issue_prefetch = [&](const Unit& tt, int cc) {
+                    const int ce = (tt.n0 + BN < p.N) ? tt.n0 + BN : p.N;
+                    const int pc = tt.n0 + cc * 32 + seg * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = 8 * i + (lane >> 2);
+                        const int rl = r0 + rr;
+                        const int yy = tt.y0 + (rl >> p.bw_shift), xx = tt.x0 + (rl & (p.BW - 1));
+                        const bool ok = yy < p.H && xx < p.W && pc < ce && cc < chunks;
+                        const long long px = (long long)((tt.b * p.H + yy) * p.W + xx);
+                        const void* src = ok ? static_cast<const void*>(esrc + px * eld + pc) : static_cast<const void*>(esrc);
+                        const int nbytes = ok ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pwb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4)),
+                                     "l"(src), "r"(nbytes) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                const bool prefetch = p.prefetch_extra && esrc != nullptr;
+                if (prefetch && !pf_issued) issue_prefetch(t, cpart);
+                pf_issued = false;
                 for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
                     const int cb = c * 32;
                     const int nb = t.n0 + cb;
                     if (nb >= col_end || (p.skip_tma & 16)) break;   // debug bit 4: epilogue = barrier traffic only
                     const int col = nb + seg * 8;
                     uint4 extra[4];
-                    if (esrc) {
+                    if (prefetch) {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) extra[j] = lds128(pwb + (uint32_t)lane * 64u + (((uint32_t)j ^ sw) << 4));
+                        __syncwarp();
+                        const int cn = c + EPI_WARPS / 4;
+                        if (cn < chunks && t.n0 + cn * 32 < col_end) {
+                            issue_prefetch(t, cn);
+                        } else if (u + gridDim.x < p.units) {
+                            issue_prefetch(decode(u + gridDim.x), cpart);
+                            pf_issued = true;
+                        }
+                    } else if (esrc) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int rr = 8 * i + (lane >> 2);
@@ -687,7 +748,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                             float dg[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) vk_gelu_both(v[8 * j + e], &v[8 * j + e], &dg[e]);
-                            pk[j] = pack8(dg);
+                            pk[j] = pack8_f16(dg);
                         }
                         if (ep.out_pre) store_packed(pk, ep.out_pre, ep.ld_pre);
                     } else {
@@ -707,7 +768,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float f[8];
-                                unpack8(extra[j], f);
+                                unpack8_f16(extra[j], f);
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) v[8 * j + e] *= f[e];
                             }
@@ -932,7 +993,7 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaSt
     p.fd_i = make_fastdiv((uint32_t)(p.i_tiles > 0 ? p.i_tiles : 1));
     p.fd_taps = make_fastdiv((uint32_t)(p.ks * p.ks));
     p.fd_rpg = make_fastdiv((uint32_t)(p.ep.rows_per_group > 0 ? p.ep.rows_per_group : 1));
-    p.num_stages = MAX_SMEM / p.stage_bytes;
+    p.num_stages = (MAX_SMEM - (p.prefetch_extra ? PREFETCH_BYTES : 0)) / p.stage_bytes;
     if (p.num_stages > 8) p.num_stages = 8;
     if (p.mode == 1)
         if (const char* e = getenv("VKOCR_TN_STAGES")) p.num_stages = atoi(e) < p.num_stages ? atoi(e) : p.num_stages;
@@ -994,6 +1055,10 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     p.staged_store = !ep->out_f32 && !ep->accumulate && (N % 8 == 0) && aligned(ep->out, ep->ldo) &&
                      (!ep->out_pre || aligned(ep->out_pre, ep->ld_pre)) && (!ep->residual || aligned(ep->residual, ep->ld_res)) &&
                      ((ep->act != 2 && ep->act != 4) || aligned(ep->aux, ep->ld_aux)) && (long long)g->batch * g->H * g->W < (1LL << 31);
+    // short-K GEMMs with a residual / aux operand: one 24 KB set of prefetch tiles comes out of the operand-stage budget
+    p.prefetch_extra = p.staged_store && (ep->residual || ep->act == 2 || ep->act == 4) && !p.head_mode &&
+                       g->ks * g->ks * p.kb_per_tap <= 12 && (MAX_SMEM - PREFETCH_BYTES) / p.stage_bytes >= 2;
+    if (const char* e = getenv("VKOCR_NO_PREFETCH")) { if (atoi(e)) p.prefetch_extra = 0; }
     return launch(mapA, mapB, p, stream);
 }
 
