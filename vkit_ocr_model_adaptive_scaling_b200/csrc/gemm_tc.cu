@@ -17,6 +17,7 @@
 //   TN  G[tap,i,j] = sum_pix P[pix,i] * Q[pix+off(tap), j]               A,B MN-major, split over pixels, fp32 red.add
 #include "gemm_common.cuh"
 #include <cuda.h>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace {
@@ -500,7 +501,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 const uint32_t sw = (uint32_t)((lane >> 1) & 3);
                 const int r0 = q * 32;
                 const int seg = lane & 3;
-                const bool store_conv = ep.out != nullptr;
+                const bool store_conv = ep.out != nullptr && !(p.skip_tma & 128);   // debug bit 7: no conv output store
                 int pix[4];
                 unsigned okmask = 0;
 #pragma unroll
@@ -564,33 +565,41 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 const float mean = S1 * inv;
                 const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, S2 * inv), 0.f) + 1e-6f);
                 const float shift = -mean * rstd;
-                // phase 2: normalise, GELU, project
+                // phase 2: normalise, GELU, project.  Specialised on the head's output count: the per-column parameters are
+                // broadcast shared-memory reads, and shared-memory bandwidth is what the MMA operand fetch of the next tile
+                // lives on (a 1-output head reading 4 weight rows cost the GEMM 10 % of its rate).
                 float dot[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
-                    const int cb = c * 32;
-                    if (cb >= inner) break;
-                    uint32_t acc[32];
-                    tc_ld32(taddr + (uint32_t)cb, acc);
+                auto phase2 = [&](auto oc) {
+                    constexpr int OO = decltype(oc)::value;
+                    for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
+                        const int cb = c * 32;
+                        if (cb >= inner || (p.skip_tma & 64)) break;   // debug bit 6: no phase 2
+                        uint32_t acc[32];
+                        tc_ld32(taddr + (uint32_t)cb, acc);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(s_par + 512 + cb + j);
-                        const float4 g4 = *reinterpret_cast<const float4*>(s_par + cb + j);
-                        const float4 e4 = *reinterpret_cast<const float4*>(s_par + 256 + cb + j);
-                        float z[4];
-                        z[0] = fmaf(fmaf(__uint_as_float(acc[j]) + b4.x, rstd, shift), g4.x, e4.x);
-                        z[1] = fmaf(fmaf(__uint_as_float(acc[j + 1]) + b4.y, rstd, shift), g4.y, e4.y);
-                        z[2] = fmaf(fmaf(__uint_as_float(acc[j + 2]) + b4.z, rstd, shift), g4.z, e4.z);
-                        z[3] = fmaf(fmaf(__uint_as_float(acc[j + 3]) + b4.w, rstd, shift), g4.w, e4.w);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_par + 512 + cb + j);
+                            const float4 g4 = *reinterpret_cast<const float4*>(s_par + cb + j);
+                            const float4 e4 = *reinterpret_cast<const float4*>(s_par + 256 + cb + j);
+                            float ge[4];
+                            ge[0] = vk_gelu(fmaf(fmaf(__uint_as_float(acc[j]) + b4.x, rstd, shift), g4.x, e4.x));
+                            ge[1] = vk_gelu(fmaf(fmaf(__uint_as_float(acc[j + 1]) + b4.y, rstd, shift), g4.y, e4.y));
+                            ge[2] = vk_gelu(fmaf(fmaf(__uint_as_float(acc[j + 2]) + b4.z, rstd, shift), g4.z, e4.z));
+                            ge[3] = vk_gelu(fmaf(fmaf(__uint_as_float(acc[j + 3]) + b4.w, rstd, shift), g4.w, e4.w));
 #pragma unroll
-                        for (int o = 0; o < 4; ++o) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(s_par + (3 + o) * 256 + cb + j);   // zero beyond inner / O
-                            dot[o] = fmaf(vk_gelu(z[0]), w4.x, dot[o]);
-                            dot[o] = fmaf(vk_gelu(z[1]), w4.y, dot[o]);
-                            dot[o] = fmaf(vk_gelu(z[2]), w4.z, dot[o]);
-                            dot[o] = fmaf(vk_gelu(z[3]), w4.w, dot[o]);
+                            for (int o = 0; o < OO; ++o) {
+                                const float4 w4 = *reinterpret_cast<const float4*>(s_par + (3 + o) * 256 + cb + j);   // zero beyond inner
+                                dot[o] = fmaf(ge[0], w4.x, dot[o]);
+                                dot[o] = fmaf(ge[1], w4.y, dot[o]);
+                                dot[o] = fmaf(ge[2], w4.z, dot[o]);
+                                dot[o] = fmaf(ge[3], w4.w, dot[o]);
+                            }
                         }
                     }
-                }
+                };
+                if (O == 1) phase2(std::integral_constant<int, 1>{});
+                else if (O == 2) phase2(std::integral_constant<int, 2>{});
+                else phase2(std::integral_constant<int, 4>{});
 #pragma unroll
                 for (int o = 0; o < 4; ++o) s_xd[(wi * 32 + lane) * 4 + o] = dot[o];
                 asm volatile("bar.sync %0, 96;" ::"r"(2 + q) : "memory");
