@@ -341,11 +341,11 @@ def run_ours(args) -> None:
             main_stream.wait_event(ev)
             a, b = step(r, p_)
             mark_consumed(k)
-        barrier()
         result_host, d2h = None, 8
         sampler2 = ClockSampler(local_rank) if rank == 0 else None
         if sampler2 is not None:
-            time.sleep(0.6)                                 # let nvidia-smi come up before the timed region
+            time.sleep(0.6)                                 # let nvidia-smi come up (before the barrier: every rank starts together)
+        barrier()
         t0e = time.time()
         e0.record()
         nxt = stage()                                       # step 0's copy is exposed; every later copy overlaps a step
