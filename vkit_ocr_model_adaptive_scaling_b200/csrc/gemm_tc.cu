@@ -71,6 +71,7 @@ struct TcParams {
     int stage_bytes;
     int skip_tma;            // debug: producers arrive without loading (timing experiments)
     int staged_store;        // NT: aligned bf16 outputs leave through the shared-memory staging tiles
+    int cta2;                // NT: CTA pairs (cluster of 2, tcgen05 cta_group::2): M = 256 per pair, each CTA stages its 128 pixel rows and HALF of the weight tile
     int prefetch_extra;      // NT staged path: residual / aux tiles are prefetched one chunk ahead (cp.async) into a second set of staging tiles
     int M;                   // NT plain GEMM: number of rows
     long long units;
@@ -128,6 +129,50 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) forms.  The TMA loads of BOTH CTAs signal the leader's full barrier, the leader's MMA
+// commit arrives on the barriers of both CTAs (multicast), the follower's epilogue releases the accumulator remotely.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {   // arrives on `bar` (same offset) in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
@@ -214,6 +259,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo1
 }
 
 // ------------------------------------------------------------------------------------------------- kernel
+// CTA2: compile-time, because every tcgen05 instruction of a kernel must name the same cta_group (and a kernel that uses
+// cta_group::2 can only be launched as clusters of two).
+template <bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const __grid_constant__ TcParams p) {
@@ -244,18 +292,38 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), EPI_WARPS);      // one arrival per epilogue warp
+            mbar_init(tempty_bar(a), CTA2 ? 2 * EPI_WARPS : EPI_WARPS);      // one arrival per epilogue warp (of both CTAs of a pair)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
     tc_fence_after();
+    constexpr bool cta2 = CTA2;
+    uint32_t cta_rank = 0u;
+    if constexpr (CTA2) cta_rank = cluster_ctarank();
+    // work items: units (one CTA each), or unit PAIRS (two pixel tiles x one N tile) per cluster in pair mode
+    const long long w0 = cta2 ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+    const long long wstride = cta2 ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+    const long long wcount = cta2 ? (p.units >> 1) : p.units;
+    auto unit_of = [&](long long w) -> long long {
+        if (!cta2) return w;
+        uint32_t mp, nt;
+        fd_divmod((uint32_t)w, p.fd_n, &mp, &nt);
+        return (long long)(2u * mp + cta_rank) * p.n_tiles + nt;
+    };
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
@@ -308,7 +376,8 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         int s = 0;
         uint32_t ph = 0;
         const int nb = (BN + 63) / 64;
-        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        for (long long w = w0; w < wcount; w += wstride) {
+            const long long u = unit_of(w);
             const Unit t = decode(u);
             const int dy = t.tap / p.ks - half, dx = t.tap % p.ks - half;
             int kt = t.kt_begin;
@@ -336,19 +405,29 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const uint32_t tx_bytes = (p.mode == 0) ? (uint32_t)(A_BYTES + BN * 128) : (uint32_t)(2 * 8192 + ((BN + 63) / 64) * 8192);
         // All per-k-block coordinates are tracked incrementally: integer divisions here sit on the critical path of a
         // single thread (a handful of dependent divides per k-block costs more than the k-block's MMAs).
-        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        for (long long w = w0; w < wcount; w += wstride) {
+            const long long u = unit_of(w);
             const Unit t = decode(u);
             if (p.mode == 0) {
                 int c0 = 0, dy = -half, dx = -half;
                 for (int kb = 0; kb < t.num_kb; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
-                    if (p.skip_tma & 1) {
-                        mbar_arrive(full_bar(s));
+                    if constexpr (CTA2) {
+                        // both CTAs' copies complete on the LEADER's full barrier; each brings its pixel rows and its half of
+                        // the weight tile
+                        const uint32_t fb = cta_rank ? mapa_cta(full_bar(s), 0u) : full_bar(s);
+                        if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2u * (uint32_t)(A_BYTES + (BN >> 1) * 128));
+                        tma_load_4d_2cta(sa, &mapA, fb, c0, t.x0 + dx, t.y0 + dy, t.b);
+                        tma_load_2d_2cta(sa + A_BYTES, &mapB, fb, kb * BK, t.n0 + (int)cta_rank * (BN >> 1));
                     } else {
-                        mbar_expect_tx(full_bar(s), tx_bytes);
-                        tma_load_4d(sa, &mapA, full_bar(s), c0, t.x0 + dx, t.y0 + dy, t.b);
-                        tma_load_2d(sa + A_BYTES, &mapB, full_bar(s), kb * BK, t.n0);
+                        if (p.skip_tma & 1) {
+                            mbar_arrive(full_bar(s));
+                        } else {
+                            mbar_expect_tx(full_bar(s), tx_bytes);
+                            tma_load_4d(sa, &mapA, full_bar(s), c0, t.x0 + dx, t.y0 + dy, t.b);
+                            tma_load_2d(sa + A_BYTES, &mapB, full_bar(s), kb * BK, t.n0);
+                        }
                     }
                     c0 += BK;
                     if (c0 >= p.kb_per_tap * BK) {
@@ -382,19 +461,20 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ================================================================ MMA issuer
+    } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+        // ================================================================ MMA issuer (pair mode: the leader CTA only)
         int s = 0;
         uint32_t ph = 0;
         int as = 0;
         uint32_t aph = 0;
         const uint32_t major = (p.mode == 0) ? 0u : 1u;
         uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (major << 15) | (major << 16) |
-                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((cta2 ? 2 * BM : BM) >> 4) << 24);
         const int dbg_major = (p.skip_tma >> 1) & 3;   // debug (timing only, garbage data): bit0 -> A K-major, bit1 -> B K-major
         if (dbg_major & 1) idesc &= ~(1u << 15);
         if (dbg_major & 2) idesc &= ~(1u << 16);
-        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        for (long long w = w0; w < wcount; w += wstride) {
+            const long long u = unit_of(w);
             const Unit t = decode(u);
             if (t.num_kb == 0) continue;
             mbar_wait(tempty_bar(as), aph ^ 1u);
@@ -410,8 +490,10 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     const uint64_t ad = make_smem_desc(sa, 1, 64);
                     const uint64_t bd = make_smem_desc(sb, 1, 64);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        if (!(p.skip_tma & 32)) tc_mma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if constexpr (CTA2) tc_mma2(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        else if (!(p.skip_tma & 32)) tc_mma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    }
                 } else {
                     // MN-major SWIZZLE_128B: 64-channel groups 8192 B apart (LBO), 8-pixel atoms 1024 B apart (SBO);
                     // one K=16 slice = 2 atoms = 2048 B.
@@ -420,12 +502,14 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     const uint64_t ka = (dbg_major & 1) ? 2 : 128, kbs = (dbg_major & 2) ? 2 : 128;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        tc_mma(tmem_d, ad + ka * (uint64_t)k, bd + kbs * (uint64_t)k, idesc, (kb | k) ? 1u : 0u);
+                        if constexpr (!CTA2) tc_mma(tmem_d, ad + ka * (uint64_t)k, bd + kbs * (uint64_t)k, idesc, (kb | k) ? 1u : 0u);
                 }
-                tc_commit(empty_bar(s));
+                if constexpr (CTA2) tc_commit2(empty_bar(s));
+                else tc_commit(empty_bar(s));
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
-            tc_commit(tfull_bar(as));
+            if constexpr (CTA2) tc_commit2(tfull_bar(as));
+            else tc_commit(tfull_bar(as));
             if (++as == 2) { as = 0; aph ^= 1u; }
         }
     } else if (warp >= 4) {
@@ -452,7 +536,8 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
         bool pf_issued = false;                 // the first chunk of the coming tile is already being prefetched
         const uint32_t pre_base = bar_base + 256u;
-        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        for (long long w = w0; w < wcount; w += wstride) {
+            const long long u = unit_of(w);
             const Unit t = decode(u);
             bool row_ok;
             long long row;
@@ -680,8 +765,8 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         const int cn = c + EPI_WARPS / 4;
                         if (cn < chunks && t.n0 + cn * 32 < col_end) {
                             issue_prefetch(t, cn);
-                        } else if (u + gridDim.x < p.units) {
-                            issue_prefetch(decode(u + gridDim.x), cpart);
+                        } else if (w + wstride < wcount) {
+                            issue_prefetch(decode(unit_of(w + wstride)), cpart);
                             pf_issued = true;
                         }
                     } else if (esrc) {
@@ -907,16 +992,21 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));   // 384 same-address arrivals per tile serialised in the smem atomic unit
+            if (lane == 0) {                               // one arrival per warp (384 same-address arrivals serialise)
+                if (cta_rank) mbar_arrive_remote(mapa_cta(tempty_bar(as), 0u));   // pair mode: the leader's MMA thread waits for both
+                else mbar_arrive(tempty_bar(as));
+            }
             if (++as == 2) { as = 0; aph ^= 1u; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();  // nobody signals the peer's barriers / reads its tiles after this point
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if constexpr (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -991,8 +1081,10 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaSt
     static bool attr_set = false;
     const int smem = MAX_SMEM + 1024 + EPI_WARPS * EPI_TILE_BYTES + HEAD_PAR_BYTES + HEAD_XCH_BYTES + 256;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(vkocr_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(vkocr_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(vkocr_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d, pair): %s", smem, cudaGetErrorString(e));
         attr_set = true;
     }
     VK_REQUIRE(p.units < (1LL << 31), VKOCR_BAD_SHAPE, "gemm_tc: %lld work units", p.units);
@@ -1008,9 +1100,33 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaSt
         if (const char* e = getenv("VKOCR_TN_STAGES")) p.num_stages = atoi(e) < p.num_stages ? atoi(e) : p.num_stages;
     if (const char* e = getenv("VKOCR_DEBUG_SKIP_TMA")) p.skip_tma = atoi(e);
     const long long sms = vkocr_sm_count();
+    if (p.cta2) {
+        // one cluster of two CTAs per SM pair; in head mode the cluster count is a multiple of the head count so that a
+        // cluster keeps its head (and the head's parameters in shared memory) for its whole life
+        long long clusters = sms / 2;
+        if (clusters > p.units / 2) clusters = p.units / 2;
+        if (p.head_mode && clusters >= p.n_tiles) clusters = clusters / p.n_tiles * p.n_tiles;
+        if (clusters <= 0) return VKOCR_OK;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, vkocr_gemm_tc_kernel<true>, mapA, mapB, p);
+        VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaLaunchKernelEx(cluster 2): %s", cudaGetErrorString(e));
+        VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
+        return VKOCR_OK;
+    }
     const int grid = (int)(p.units < sms ? p.units : sms);
     if (grid <= 0) return VKOCR_OK;
-    vkocr_gemm_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, p);
+    vkocr_gemm_tc_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, p);
     VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
     return VKOCR_OK;
 }
@@ -1045,8 +1161,14 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
         p.ht = *heads;
     }
     p.n_tiles = vk_cdiv(N, p.BN);
-    p.stage_bytes = A_BYTES + p.BN * 128;
-    p.units = (long long)p.batch * p.tiles_y * p.tiles_x * p.n_tiles;
+    const long long pix_tiles = (long long)p.batch * p.tiles_y * p.tiles_x;
+    // CTA pairs (cta_group::2) for the long-K GEMMs: with one CTA per tile every operand byte is written to shared memory
+    // once (TMA) and read once (MMA), ~200 B/clk at full MMA rate against the SM's 128 B/clk -- the tensor pipe sat at
+    // 62 % (ncu).  A pair shares the weight tile: each CTA stages its 128 pixel rows and HALF of the weight rows.
+    p.cta2 = (pix_tiles % 2 == 0) && (p.BN % 16 == 0) && (g->ks * g->ks * (g->c_pad / BK) >= 16) && vkocr_sm_count() % 2 == 0;
+    if (const char* e = getenv("VKOCR_CTA2")) p.cta2 = p.cta2 && atoi(e) != 0;
+    p.stage_bytes = A_BYTES + (p.cta2 ? p.BN / 2 : p.BN) * 128;
+    p.units = pix_tiles * p.n_tiles;
     p.ep = *ep;
     CUtensorMap mapA, mapB;
     int rc = encode_nhwc(&mapA, x, g->C, g->W, g->H, g->batch, g->ld_x, p.BW, p.BH);
@@ -1054,7 +1176,7 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     const long long kw = (long long)g->ks * g->ks * g->c_pad;
     const uint64_t dims[2] = {(uint64_t)kw, (uint64_t)N};
     const uint64_t str[1] = {(uint64_t)kw * 2};
-    const uint32_t box[2] = {64, (uint32_t)p.BN};
+    const uint32_t box[2] = {64, (uint32_t)(p.cta2 ? p.BN / 2 : p.BN)};
     VK_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, VKOCR_BAD_ALIGN, "packed weight not 16-byte aligned");
     rc = encode_map(&mapB, w_packed, 2, dims, str, box);
     if (rc) return rc;
