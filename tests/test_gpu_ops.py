@@ -412,3 +412,68 @@ def test_dwconv7_tiled_kernels_against_conv2d(vk, shape):
     wd = w.double().requires_grad_(True)
     (torch.nn.functional.conv2d(xd, wd, None, padding=3, groups=C) * add.double()).sum().backward()
     assert_close(dw, wd.grad, 1e-5, 'dwconv7 weight gradient')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(2, 32, 32, 384, 384, 3), (3, 20, 28, 384, 208, 3), (4, 16, 16, 1536, 384, 1), (1, 24, 40, 128, 832, 3)])
+def test_gemm_cta_pair_mode_is_bit_identical(vk, shape, monkeypatch):
+    """The CTA-pair schedule of the tcgen05 GEMM (cluster of 2, cta_group::2, each CTA stages half of the weight tile)
+    accumulates every output element over the same K order as the one-CTA schedule: results must be bit-identical."""
+    from vkit_ocr_model_adaptive_scaling_b200 import ops
+    B, H, W, C, N, ks = shape
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(N + H)
+    x = ops.alloc_nhwc(B, H, W, C, torch.bfloat16, dev)
+    x.copy_(torch.randn(B, C, H, W, generator=g))
+    w = (torch.randn(N, ks * ks * C, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    outs = []
+    for mode in ('0', '1'):
+        monkeypatch.setenv('VKOCR_CTA2', mode)
+        out = ops.alloc_nhwc(B, H, W, N, torch.bfloat16, dev)
+        ops.gemm_nt(x, B, H, W, C, x.stride(3), ks, w, C, N, ops._epilogue(out, out.stride(3), bias=bias))
+        torch.cuda.synchronize()
+        outs.append(out.float().clone())
+    assert torch.isfinite(outs[1]).all()
+    assert torch.equal(outs[0], outs[1])
+    # and both agree with the convolution itself
+    wt = w.float().reshape(N, ks, ks, C).permute(0, 3, 1, 2).double()
+    ref = torch.nn.functional.conv2d(x.double(), wt, bias.double(), padding=ks // 2)
+    assert_close(outs[1], ref, 4e-3, 'pair-mode implicit-GEMM convolution')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(640, 96), (300, 192), (1000, 384)])
+def test_mlp_epilogue_gelu_with_derivative_side_channel(vk, shape):
+    """ConvNeXt MLP up-projection epilogue act 3 (convnext.py:29-37): out = GELU(xW^T + b), second output = GELU'(xW^T + b)
+    (fp16 bits in the 16-bit buffer); act 4 multiplies a data gradient by that side channel.  Checked against the erf
+    formulas in fp64 on the same bf16 operands."""
+    from vkit_ocr_model_adaptive_scaling_b200 import ops
+    M, C = shape
+    hid = 4 * C
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(M)
+    cp = (C + 63) // 64 * 64
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16).to(dev)
+    w = torch.zeros(hid, cp)
+    w[:, :C] = torch.randn(hid, C, generator=g) * (C ** -0.5)
+    w = w.to(torch.bfloat16).to(dev)
+    b = torch.randn(hid, generator=g).to(dev)
+    out = torch.empty(M, hid, dtype=torch.bfloat16, device=dev)
+    side = torch.empty(M, hid, dtype=torch.bfloat16, device=dev)
+    ops.gemm_nt(x, 1, 1, M, C, C, 1, w, cp, hid, ops._epilogue(out, hid, out_pre=side, ld_pre=hid, bias=b, act=3))
+    h = x.double() @ w[:, :C].double().t() + b.double()
+    cdf = 0.5 * (1 + torch.erf(h / 2 ** 0.5))
+    pdf = torch.exp(-h * h / 2) / (2 * np.pi) ** 0.5
+    assert_close(out.float(), h * cdf, 4e-3, 'GELU output')
+    dgelu = side.view(torch.float16).double()
+    assert float((dgelu - (cdf + h * pdf)).abs().max()) <= 1.5e-3, 'GELU derivative side channel (fp16 bits)'
+    # backward use: dH = (U W2) * side
+    u = torch.randn(M, C, generator=g).to(torch.bfloat16).to(dev)
+    w2 = torch.zeros(hid, cp)
+    w2[:, :C] = torch.randn(hid, C, generator=g) * (C ** -0.5)
+    w2 = w2.to(torch.bfloat16).to(dev)
+    dh = torch.empty(M, hid, dtype=torch.bfloat16, device=dev)
+    ops.gemm_nt(u, 1, 1, M, C, C, 1, w2, cp, hid, ops._epilogue(dh, hid, act=4, aux=side, ld_aux=hid))
+    ref = (u.double() @ w2[:, :C].double().t()) * dgelu
+    assert_close(dh.float(), ref, 4e-3, 'data gradient times the side channel')
