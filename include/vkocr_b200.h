@@ -249,6 +249,17 @@ int vkocr_ingest_image_u8(const void* img, int B, int H, int W, float* out, int 
 int vkocr_rough_postprocess(const float* logit, const float* height, int B, int h, int w, int valid_h, int valid_w, float thr,
                             float height_min, void* mask_out, float* height_out, void* stream);
 
+/* ----------------------------------------------------------------------------------- precise inference tensor post-ops
+ * vkocr_precise_postprocess: the tensor side of AdaptiveScalingInferencing.precise_infer after forward_precise
+ * (inferencing/adaptive_scaling.py:326-386): sigmoid of the char-prob logits with the padding forced to 0, softmax over
+ * the 4 corner-angle channels, NCHW -> NHWC permutes of the offset / angle / distance maps.
+ * vkocr_peak_mask: the peak picking of precise_build_grouped_polygons (:477-491): mat[~char_mask] = 0,
+ * scipy.ndimage.maximum_filter(mat, size) == mat, and mat >= thr. */
+int vkocr_precise_postprocess(const float* prob_logit, const float* offset, const float* angle, const float* distance, int B, int h,
+                              int w, int dist_channels, int valid_h, int valid_w, float* prob_out, float* offset_out,
+                              float* angle_out, float* distance_out, void* stream);
+int vkocr_peak_mask(const float* prob, const void* char_mask, int B, int h, int w, int size, float thr, void* peaks_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

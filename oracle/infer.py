@@ -48,3 +48,36 @@ def rough_postprocess(mask_feature: torch.Tensor, height_feature: torch.Tensor, 
             hmap[:, begin:] = 0.0
     hmap[hmap < height_min] = 0.0
     return mask, hmap, (math.ceil(image_height / fdf), math.ceil(image_width / fdf))
+
+
+def precise_postprocess(prob_feature: torch.Tensor, offset_feature: torch.Tensor, angle_feature: torch.Tensor,
+                        distance_feature: torch.Tensor, image_height: int, image_width: int, padded_height: int,
+                        padded_width: int, upsampling_factor: int = 2):
+    """vkit_open_model/inferencing/adaptive_scaling.py:322-386 for one image: (1, C, h, w) network outputs -> score map (h, w),
+    offsets (h, w, 2), softmax angle distribution (h, w, 4), distances (h, w, D), all float32 numpy."""
+    prob = torch.sigmoid(prob_feature[0][0].clone()).numpy().astype(np.float32)
+    offsets = torch.permute(offset_feature[0], [1, 2, 0]).numpy().astype(np.float32)
+    angles = torch.softmax(torch.permute(angle_feature[0], [1, 2, 0]), dim=-1).numpy().astype(np.float32)
+    distances = torch.permute(distance_feature[0], [1, 2, 0]).numpy().astype(np.float32)
+    fdf = 4 // upsampling_factor
+    if image_height < padded_height:
+        begin = math.ceil(image_height / fdf)
+        if begin < prob.shape[0]:
+            prob[begin:] = 0.0
+    if image_width < padded_width:
+        begin = math.ceil(image_width / fdf)
+        if begin < prob.shape[1]:
+            prob[:, begin:] = 0.0
+    return prob, offsets, angles, distances
+
+
+def peak_mask(score_map: np.ndarray, char_mask: np.ndarray = None, size: int = 5, positive_thr: float = 0.7) -> np.ndarray:
+    """vkit_open_model/inferencing/adaptive_scaling.py:477-491: maximum_filter peaks of the (masked) char-prob map."""
+    from scipy.ndimage import maximum_filter
+    mat = score_map.copy()
+    if char_mask is not None:
+        mat[~char_mask.astype(bool)] = 0
+    np_local_maximum = maximum_filter(mat, size=size)
+    np_mask = (np_local_maximum == mat)
+    np_mask[mat < positive_thr] = 0
+    return np_mask.astype(np.uint8)

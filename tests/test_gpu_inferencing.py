@@ -82,3 +82,47 @@ def test_rough_postprocess_kernel_on_synthetic_maps(vk):
     assert shape == (45, 71)
     assert np.array_equal(mask[0].cpu().numpy(), want_mask) and 0.2 < want_mask.mean() < 0.8
     assert np.array_equal(hmap[0].cpu().numpy(), want_h) and 0.1 < (want_h == 0).mean() < 0.9
+
+
+def test_precise_infer_tensors_against_oracle(vk):
+    """uint8 image -> forward_precise -> device post-ops, against the oracle restatement of inferencing/adaptive_scaling.py:
+    322-386 applied to the same network outputs (the network itself is covered by tests/test_gpu_model.py)."""
+    from oracle import infer as oi
+    from oracle import synth
+    M = vk.model
+    model = M.AdaptiveScaling(M.AdaptiveScalingConfig(size=M.AdaptiveScalingSize.TINY, neck_head_type=M.AdaptiveScalingNeckHeadType.UPERNEXT))
+    model.load_state_dict(synth.synth_state_dict('tiny', 'upernext', seed=5), strict=True)
+    model.cuda().eval()
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, size=(75, 118, 3), dtype=np.uint8)       # pads to 96 x 128
+    with vk.precision(torch.float32):
+        prob, offs, angs, dists = vk.inferencing.precise_infer_tensors(model, torch.from_numpy(img).cuda())
+        x = vk.inferencing.ingest_images(torch.from_numpy(img).cuda(), 32)
+        with torch.no_grad():
+            feats = [f.cpu() for f in model.forward_precise(x)]
+    want = oi.precise_postprocess(*feats, 75, 118, 96, 128)
+    for got, ref, what in zip((prob, offs, angs, dists), want, ('prob', 'offset', 'angle', 'distance')):
+        got = got[0].cpu().numpy()
+        assert got.shape == ref.shape, (what, got.shape, ref.shape)
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-6), what
+    assert np.abs(angs[0].cpu().numpy().sum(-1) - 1).max() < 1e-5
+    assert prob[0, 38:].abs().sum() == 0 and prob[0, :, 59:].abs().sum() == 0          # ceil(75 / 2), ceil(118 / 2)
+
+
+@pytest.mark.parametrize('size', [5, 3, 4])
+def test_peak_mask_against_scipy_maximum_filter(vk, size):
+    """Peak picking (inferencing/adaptive_scaling.py:477-491) bit-exactly against scipy's maximum_filter, with plateaus (ties),
+    a char mask, and maps smaller than the window."""
+    from oracle import infer as oi
+    rng = np.random.default_rng(size)
+    for (h, w) in ((37, 53), (4, 3), (1, 9)):
+        score = rng.random((2, h, w)).astype(np.float32)
+        score[0] = np.round(score[0] * 8) / 8                           # plateaus: ties must count as peaks on both sides
+        cmask = (rng.random((2, h, w)) > 0.3).astype(np.uint8)
+        cfg = vk.inferencing.PreciseInferConfig(precise_build_polygons_maximum_filter_size=size)
+        for use_mask in (False, True):
+            got = vk.inferencing.find_peaks(torch.from_numpy(score).cuda(), torch.from_numpy(cmask).cuda() if use_mask else None, cfg)
+            for b in range(2):
+                want = oi.peak_mask(score[b], cmask[b] if use_mask else None, size=size, positive_thr=0.7)
+                assert np.array_equal(got[b].cpu().numpy(), want), (h, w, b, use_mask)
+        assert got.sum() > 0

@@ -109,6 +109,9 @@ _SIGNATURES = {
     'vkocr_scale_rows': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p],
     'vkocr_ingest_image_u8': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     'vkocr_rough_postprocess': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
+    'vkocr_precise_postprocess': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p],
+    'vkocr_peak_mask': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
     'vkocr_sumsq_f32': [c_void_p, c_ll, c_void_p, c_void_p],
     'vkocr_adamw_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float, c_float, c_float,
                          c_void_p, c_float, c_float, c_void_p],
