@@ -73,7 +73,8 @@ typedef struct VkocrEpilogue {
     long long ld_pre;
     const float* bias;    /* [N] or NULL */
     int act;              /* 0 none, 1 exact erf GELU (helper.py:100-101), 2 multiply by gelu'(aux),
-                             3 exact GELU with out_pre = gelu'(acc + bias), 4 multiply by aux */
+                             3 exact GELU with out_pre = row_scale * gelu'(acc + bias) and out zeroed where row_scale == 0
+                             (stochastic-depth mask, convnext.py:41-53), 4 multiply by aux */
     const float* col_scale;  /* [N] or NULL — ConvNeXt layer scale (convnext.py:38,56) */
     const float* row_scale;  /* [rows / rows_per_group] or NULL — stochastic-depth mask (convnext.py:41-53) */
     int rows_per_group;
@@ -223,8 +224,11 @@ int vkocr_hard_negative_bce_bwd(const float* pred, const float* gt, const float*
 int vkocr_pack_weight(const float* w, long long s_row, long long s_tap, long long s_col, int rows, int taps, int cols, int flip,
                       const float* col_scale, void* out, int out_dtype, long long o_row, long long o_tap, void* stream);
 int vkocr_unpack_grad(const float* g, int N, int T, int C, float* y, long long s_n, long long s_t, long long s_c, void* stream);
-int vkocr_mlp2_grad_finalize(const float* S, const float* sU, const float* W2, const float* b2, const float* gamma, int C, int K,
-                             float* dW2, float* dgamma, float* db2, void* stream);
+/* S: [C, K] product dY^T G with row stride ld_s, scaled by s_scale on the way in (1 / p_keep when G was stored with the
+ * dropped samples zeroed); sU[c * ld_su]: masked column sums of dY (a column of the same product when G carries the mask
+ * channel). */
+int vkocr_mlp2_grad_finalize(const float* S, long long ld_s, float s_scale, const float* sU, long long ld_su, const float* W2,
+                             const float* b2, const float* gamma, int C, int K, float* dW2, float* dgamma, float* db2, void* stream);
 int vkocr_accumulate_f32(const float* a, float* y, long long n, void* stream);
 int vkocr_scale_rows(int dtype, const void* x, long long ld_x, void* y, long long ld_y, long long rows, int C,
                      const float* scale, int rows_per_group, void* stream);

@@ -75,15 +75,27 @@ def test_convnext_layer_stochastic_depth_mask(vk, dtype):
     layer.train()
     x = torch.randn(6, 64, 8, 8, generator=torch.Generator().manual_seed(2)).to(dev)
     torch.manual_seed(77)
+    xin = x.clone().requires_grad_(True)
     with vk.precision(dtype):
-        y = layer(x.clone().requires_grad_(True))
+        y = layer(xin)
     torch.manual_seed(77)
     mask = torch.empty([6, 1, 1, 1], dtype=torch.float32, device=dev).bernoulli_(0.5).div_(0.5)
     assert 0 < int((mask == 0).sum()) < 6, 'seed should drop some but not all samples'
-    ref = om.convnext_layer(oracle_params(layer), '', x.double(), mask.double())
+    params = oracle_params(layer)
+    xo = x.double().requires_grad_(True)
+    ref = om.convnext_layer(params, '', xo, mask.double())
     assert_close(y.float(), ref, TOL[dtype], 'stochastic depth output')
     dropped = (mask.reshape(-1) == 0).nonzero().reshape(-1)
     assert_close(y.float()[dropped], x[dropped], TOL[dtype], 'dropped samples are the identity')
+    # backward through the masked branch: the mask rides in the GELU-derivative side channel and in the mask column of the
+    # activation buffer (ops.ConvNextLayerFn), the oracle applies it the reference's way
+    probe = _probe(tuple(ref.shape), 9, dev)
+    with vk.precision(dtype):
+        (y.float() * probe).sum().backward()
+    (ref * probe.double()).sum().backward()
+    torch.cuda.synchronize()
+    assert_close(xin.grad.float(), xo.grad, PER_TENSOR_GRAD_TOL[dtype], 'input gradient under the mask')
+    compare_grads(layer, params, dtype, 'parameters under the mask')
 
 
 @pytest.mark.parametrize('dtype', DTYPES)

@@ -26,7 +26,7 @@ struct VkocrEpilogue {
     void* out_pre;         // optional second output, storage dtype: (acc + bias) before the activation; act == 3: gelu'(acc + bias) (fp16 bits when the storage is 16-bit)
     long long ld_pre;
     const float* bias;     // [N] or null
-    int act;               // 0 none, 1 exact GELU, 2 multiply by gelu'(aux), 3 exact GELU with out_pre = gelu', 4 multiply by aux
+    int act;               // 0 none, 1 exact GELU, 2 multiply by gelu'(aux), 3 exact GELU with out_pre = row_scale * gelu' (and out zeroed where row_scale == 0), 4 multiply by aux
     const float* col_scale;  // [N] or null  (ConvNeXt layer scale, convnext.py:38,56)
     const float* row_scale;  // [rows / rows_per_group] or null (stochastic-depth mask, convnext.py:41-53)
     int rows_per_group;
@@ -78,8 +78,14 @@ __device__ __forceinline__ float vk_epilogue_value(const VkocrEpilogue& ep, long
     if (ep.act == 3) {
         float g, dg;
         vk_gelu_both(v, &g, &dg);
-        if (ep.out_pre) vk_store_dgelu<T>(reinterpret_cast<T*>(ep.out_pre) + m * ep.ld_pre + n, dg);
-        v = g;
+        // with a row scale (stochastic-depth mask m_b in {0, 1/p_keep}) the outputs are prepared for the backward: the
+        // derivative side channel carries m_b * gelu', the activation of dropped samples is zeroed (see ConvNextLayerFn)
+        const float rs3 = ep.row_scale ? __ldg(ep.row_scale + (m / ep.rows_per_group)) : 1.f;
+        if (ep.out_pre) vk_store_dgelu<T>(reinterpret_cast<T*>(ep.out_pre) + m * ep.ld_pre + n, dg * rs3);
+        v = rs3 != 0.f ? g : 0.f;
+        if (ep.col_scale) v *= __ldg(ep.col_scale + n);
+        if (ep.residual) v += vk_to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + n]);
+        return v;
     } else {
         if (ep.out_pre) reinterpret_cast<T*>(ep.out_pre)[m * ep.ld_pre + n] = vk_from_f32<T>(v);
         if (ep.act == 1) v = vk_gelu(v);

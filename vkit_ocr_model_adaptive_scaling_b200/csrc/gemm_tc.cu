@@ -842,6 +842,13 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                             float dg[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) vk_gelu_both(v[8 * j + e], &v[8 * j + e], &dg[e]);
+                            if (ep.row_scale) {       // stochastic-depth mask: side channel = m_b * gelu', dropped samples' activation = 0
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    dg[e] *= rs;
+                                    v[8 * j + e] = rs != 0.f ? v[8 * j + e] : 0.f;
+                                }
+                            }
                             pk[j] = pack8_f16(dg);
                         }
                         if (ep.out_pre) store_packed(pk, ep.out_pre, ep.ld_pre);
@@ -886,7 +893,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                             for (int j = 0; j < 32; ++j) v[j] *= (nb + j < p.N) ? __ldg(ep.col_scale + nb + j) : 0.f;
                         }
                     }
-                    if (ep.row_scale) {
+                    if (ep.row_scale && ep.act != 3) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] *= rs;
                     }

@@ -36,26 +36,28 @@ unpack_grad_kernel(const float* __restrict__ g, int N, int T, int C, float* __re
     y[n * s_n + t * s_t + c * s_c] += g[idx];
 }
 
-// ConvNeXt MLP second Linear: S[c,k] = sum_p U[p,c] G[p,k] (U = layer-output gradient x drop mask), sU[c] = sum_p U[p,c]
+// ConvNeXt MLP second Linear: S[c,k] = s_scale * sum_p dY[p,c] G[p,k] (G zeroed for dropped samples, s_scale = 1 / p_keep),
+// sU[c] = sum_p m_b(p) dY[p,c] (the mask channel's column of the same product)
 //   dW2[c,k] += gamma[c] * S[c,k];  dgamma[c] += sum_k W2[c,k] S[c,k] + b2[c] sU[c];  db2[c] += gamma[c] sU[c]
 // (out = x + gamma * (G W2^T + b2), convnext.py:35-38,56-58)
 __global__ void __launch_bounds__(256)
-mlp2_grad_finalize_kernel(const float* __restrict__ S, const float* __restrict__ sU, const float* __restrict__ W2,
-                          const float* __restrict__ b2, const float* __restrict__ gamma, int C, int K, float* __restrict__ dW2,
-                          float* __restrict__ dgamma, float* __restrict__ db2) {
+mlp2_grad_finalize_kernel(const float* __restrict__ S, long long ld_s, float s_scale, const float* __restrict__ sU, long long ld_su,
+                          const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ gamma, int C, int K,
+                          float* __restrict__ dW2, float* __restrict__ dgamma, float* __restrict__ db2) {
     __shared__ float scratch[33];
     const int c = blockIdx.x;
     const float g = gamma[c];
     float dot = 0.f;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        const float s = S[(long long)c * K + k];
+        const float s = S[(long long)c * ld_s + k] * s_scale;
         dW2[(long long)c * K + k] += g * s;
         dot = fmaf(W2[(long long)c * K + k], s, dot);
     }
     dot = vk_block_sum(dot, scratch);
     if (threadIdx.x == 0) {
-        dgamma[c] += dot + b2[c] * sU[c];
-        db2[c] += g * sU[c];
+        const float su = sU[(long long)c * ld_su];
+        dgamma[c] += dot + b2[c] * su;
+        db2[c] += g * su;
     }
 }
 
@@ -96,11 +98,12 @@ int vkocr_pack_weight(const float* w, long long s_row, long long s_tap, long lon
     return VKOCR_OK;
 }
 
-int vkocr_mlp2_grad_finalize(const float* S, const float* sU, const float* W2, const float* b2, const float* gamma, int C, int K,
-                             float* dW2, float* dgamma, float* db2, void* stream) {
+int vkocr_mlp2_grad_finalize(const float* S, long long ld_s, float s_scale, const float* sU, long long ld_su, const float* W2,
+                             const float* b2, const float* gamma, int C, int K, float* dW2, float* dgamma, float* db2, void* stream) {
     VK_REQUIRE(S && sU && W2 && b2 && gamma && dW2 && dgamma && db2, VKOCR_BAD_ARGUMENT, "mlp2_grad_finalize: null argument");
     if (C == 0) return VKOCR_OK;
-    mlp2_grad_finalize_kernel<<<C, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(S, sU, W2, b2, gamma, C, K, dW2, dgamma, db2);
+    mlp2_grad_finalize_kernel<<<C, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(S, ld_s, s_scale, sU, ld_su, W2, b2, gamma, C, K, dW2,
+                                                                                      dgamma, db2);
     VK_CHECK_LAUNCH("mlp2_grad_finalize_kernel");
     return VKOCR_OK;
 }

@@ -53,7 +53,8 @@ class ConvNextBlockLayer(nn.Module):
         b = self.block
         return ops.ConvNextLayerFn.apply(x, b[0].weight, b[0].bias, b[2].weight, b[2].bias, b[3].weight, b[3].bias,
                                          b[5].weight, b[5].bias, self.block_scale,
-                                         self.stochastic_depth_mask(x.shape[0], x.device))
+                                         self.stochastic_depth_mask(x.shape[0], x.device),
+                                         1.0 / (1.0 - self.prob_bypass) if self.prob_bypass < 1.0 else 1.0)
 
 
 class ConvNextBlock(nn.Module):

@@ -426,7 +426,8 @@ class ConvNextLayerFn(torch.autograd.Function):
     """x + mask * scale * Linear2(GELU(Linear1(LN(dwconv7x7(x)))))  (ConvNextBlockLayer, convnext.py:20-59)."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale, drop_mask: Optional[Tensor]) -> Tensor:
+    def forward(ctx, x: Tensor, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale, drop_mask: Optional[Tensor],
+                inv_keep: float = 1.0) -> Tensor:
         B, H, W, C, ld = geom(x)
         M = B * H * W
         dt, dev = x.dtype, x.device
@@ -447,22 +448,36 @@ class ConvNextLayerFn(torch.autograd.Function):
         layernorm_fwd(conv, conv.stride(3), lnout, lnout.stride(3), M, C, ln_w.detach(), ln_b.detach(), 0, mean, rstd)
         hid = 4 * C
         w1p, c1 = packed_linear_fwd(w1, dt)
-        g = torch.empty((M, hid), dtype=dt, device=dev)
-        # training: the second output is gelu'(H_pre) (act 3) -- all the backward ever needs of the pre-activation, and it
-        # shares the transcendental work with the GELU itself
+        if train:
+            # 8 extra columns per row, [m_b, 0 .. 0] (m_b = the sample's stochastic-depth factor, 1 without a mask): the
+            # weight-gradient GEMM dY^T . [G | m] delivers the masked column sums of dY (-> db2, dscale) as column `hid`.
+            # With a mask the up-projection epilogue also zeroes G for dropped samples and stores m_b * gelu' in the side
+            # channel, so the backward runs on dY itself: no masked copy of the gradient, no separate column-sum pass.
+            gbuf = torch.empty((M, hid + 8), dtype=dt, device=dev)
+            tail = torch.zeros((B, 1, 8), dtype=dt, device=dev)
+            tail[:, 0, 0] = 1.0 if drop_mask is None else drop_mask.to(dt)
+            gbuf.view(B, H * W, hid + 8)[:, :, hid:] = tail
+            g = gbuf[:, :hid]
+        else:
+            g = torch.empty((M, hid), dtype=dt, device=dev)
+        ldg = g.stride(0)
+        # training: the second output is (m_b *) gelu'(H_pre) (act 3) -- all the backward ever needs of the pre-activation,
+        # and it shares the transcendental work with the GELU itself
         hpre = torch.empty((M, hid), dtype=dt, device=dev) if train else None
         gemm_nt(lnout, 1, 1, M, C, lnout.stride(3), 1, w1p, c1, hid,
-                _epilogue(g, hid, out_pre=hpre, ld_pre=hid, bias=b1.detach(), act=3 if train else 1))
+                _epilogue(g, ldg, out_pre=hpre, ld_pre=hid, bias=b1.detach(), act=3 if train else 1,
+                          row_scale=drop_mask if train else None, rows_per_group=H * W))
         w2p, c2 = packed_linear_fwd(w2, dt)
         y = alloc_nhwc(B, H, W, C, dt, dev)
         gamma = scale.detach().reshape(-1)
-        gemm_nt(g, 1, 1, M, hid, hid, 1, w2p, c2, C,
+        gemm_nt(g, 1, 1, M, hid, ldg, 1, w2p, c2, C,
                 _epilogue(y, y.stride(3), bias=b2.detach(), col_scale=gamma, row_scale=drop_mask, rows_per_group=H * W,
                           residual=x, ld_res=ld))
         if train:
             ctx.save_for_backward(x, conv, mean, rstd, lnout, hpre, g, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale,
                                   drop_mask if drop_mask is not None else torch.empty(0, device=dev))
             ctx.has_mask = drop_mask is not None
+            ctx.inv_keep = float(inv_keep) if drop_mask is not None else 1.0
         return y
 
     @staticmethod
@@ -474,23 +489,17 @@ class ConvNextLayerFn(torch.autograd.Function):
         dt, dev = x.dtype, x.device
         dy = to_nhwc(dy, dt)
         gamma = scale.detach().reshape(-1)
-        su = _zeros_f32(C, dev)
-        if ctx.has_mask:
-            u = alloc_nhwc(B, H, W, C, dt, dev)
-            L.check(L.LIB.vkocr_scale_rows_colsum(_tag(dt), L.ptr(dy), dy.stride(3), L.ptr(u), u.stride(3), M, C, L.ptr(mask), H * W,
-                                                  L.ptr(su), _s()), 'scale_rows_colsum')
-        else:
-            u = dy
-            colsum(u, u.stride(3), M, C, su)
-        # dH_pre = (U . (gamma * W2)) * gelu'(H_pre)   (hpre holds gelu'(H_pre), written by the forward)
+        # dH_pre = (dY . (gamma * W2)) * (m_b gelu'(H_pre))   (hpre holds m_b * gelu'(H_pre), written by the forward)
         w2d, n2 = packed_linear_dgrad(w2, dt, scale)
         dh = torch.empty((M, hid), dtype=dt, device=dev)
-        gemm_nt(u, 1, 1, M, C, u.stride(3), 1, w2d, n2, hid, _epilogue(dh, hid, act=4, aux=hpre, ld_aux=hid))
-        # S[c,k] = sum_p U[p,c] G[p,k]  -> dW2, dscale, db2
-        s = _zeros_f32(C * hid, dev)
-        gemm_tn(u, 1, 1, M, C, u.stride(3), 1, g, hid, hid, _epilogue(s, hid, out_f32=True, accumulate=True, tn=(0, hid, 1)))
-        L.check(L.LIB.vkocr_mlp2_grad_finalize(L.ptr(s), L.ptr(su), L.ptr(w2.detach()), L.ptr(b2.detach()), L.ptr(gamma), C, hid,
-                                               L.ptr(grad_buffer(w2)), L.ptr(grad_buffer(scale)), L.ptr(grad_buffer(b2)), _s()),
+        gemm_nt(dy, 1, 1, M, C, dy.stride(3), 1, w2d, n2, hid, _epilogue(dh, hid, act=4, aux=hpre, ld_aux=hid))
+        # S[c,k] = sum_p dY[p,c] [G | m][p,k]  -> dW2, dscale, db2 (column `hid` = masked column sums of dY)
+        ldg = g.stride(0)
+        s = _zeros_f32(C * ldg, dev)
+        gemm_tn(dy, 1, 1, M, C, dy.stride(3), 1, g, ldg, ldg, _epilogue(s, ldg, out_f32=True, accumulate=True, tn=(0, ldg, 1)))
+        L.check(L.LIB.vkocr_mlp2_grad_finalize(L.ptr(s), ldg, ctx.inv_keep, s.data_ptr() + 4 * hid, ldg, L.ptr(w2.detach()),
+                                               L.ptr(b2.detach()), L.ptr(gamma), C, hid, L.ptr(grad_buffer(w2)),
+                                               L.ptr(grad_buffer(scale)), L.ptr(grad_buffer(b2)), _s()),
                 'mlp2_grad_finalize')
         del s, g
         ldl = lnout.stride(3)
@@ -516,7 +525,7 @@ class ConvNextLayerFn(torch.autograd.Function):
             dx = alloc_nhwc(B, H, W, C, dt, dev)
             dwconv7(dconv, dx, packed_dwconv(dw_w, True), None, dy)   # + residual gradient
         _ready(dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, scale)
-        return (dx,) + (None,) * 10
+        return (dx,) + (None,) * 11
 
 
 class PatchConvFn(torch.autograd.Function):
