@@ -131,8 +131,9 @@ int vkocr_layernorm_bwd(int dtype, const void* dy, long long ld_dy, const void* 
                         const float* rstd, const float* gamma, const float* beta, int act, void* dx, long long ld_dx,
                         long long rows, int C, float* dgamma, float* dbeta, float* dxsum, void* stream);
 int vkocr_colsum(int dtype, const void* x, long long ld, long long rows, int C, float* out, void* stream);
-/* y = scale[row / rows_per_group] * x and out[c] += sum_rows y[row, c]: the stochastic-depth mask applied to the incoming
- * gradient of a ConvNeXt layer (model/convnext.py:41-53) fused with the bias-gradient column sum. */
+/* y = scale[row / rows_per_group] * x (skipped when y is null) and out[c] += sum_rows scale * x[row, c]: the
+ * stochastic-depth mask applied to the incoming gradient of a ConvNeXt layer (model/convnext.py:41-53) fused with the
+ * bias-gradient column sum. */
 int vkocr_scale_rows_colsum(int dtype, const void* x, long long ld_x, void* y, long long ld_y, long long rows, int C,
                             const float* scale, int rows_per_group, float* out, void* stream);
 

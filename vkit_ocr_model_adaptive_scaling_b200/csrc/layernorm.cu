@@ -734,7 +734,7 @@ int vkocr_colsum(int dtype, const void* x, long long ld, long long rows, int C, 
 // incoming gradient of a ConvNeXt layer, convnext.py:41-53, fused with the bias-gradient column sum)
 int vkocr_scale_rows_colsum(int dtype, const void* x, long long ld_x, void* y, long long ld_y, long long rows, int C,
                             const float* scale, int rows_per_group, float* out, void* stream) {
-    VK_REQUIRE(x && y && scale && out && rows_per_group > 0, VKOCR_BAD_ARGUMENT, "scale_rows_colsum: bad argument");
+    VK_REQUIRE(x && scale && out && rows_per_group > 0, VKOCR_BAD_ARGUMENT, "scale_rows_colsum: bad argument");   // y may be null: sums only
     if (rows == 0 || C == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     bool done = false;

@@ -448,18 +448,9 @@ class ConvNextLayerFn(torch.autograd.Function):
         layernorm_fwd(conv, conv.stride(3), lnout, lnout.stride(3), M, C, ln_w.detach(), ln_b.detach(), 0, mean, rstd)
         hid = 4 * C
         w1p, c1 = packed_linear_fwd(w1, dt)
-        if train:
-            # 8 extra columns per row, [m_b, 0 .. 0] (m_b = the sample's stochastic-depth factor, 1 without a mask): the
-            # weight-gradient GEMM dY^T . [G | m] delivers the masked column sums of dY (-> db2, dscale) as column `hid`.
-            # With a mask the up-projection epilogue also zeroes G for dropped samples and stores m_b * gelu' in the side
-            # channel, so the backward runs on dY itself: no masked copy of the gradient, no separate column-sum pass.
-            gbuf = torch.empty((M, hid + 8), dtype=dt, device=dev)
-            tail = torch.zeros((B, 1, 8), dtype=dt, device=dev)
-            tail[:, 0, 0] = 1.0 if drop_mask is None else drop_mask.to(dt)
-            gbuf.view(B, H * W, hid + 8)[:, :, hid:] = tail
-            g = gbuf[:, :hid]
-        else:
-            g = torch.empty((M, hid), dtype=dt, device=dev)
+        # With a stochastic-depth mask m_b the up-projection epilogue zeroes G for dropped samples and stores m_b * gelu' in
+        # the side channel, so the backward runs on dY itself (no masked copy of the gradient).
+        g = torch.empty((M, hid), dtype=dt, device=dev)
         ldg = g.stride(0)
         # training: the second output is (m_b *) gelu'(H_pre) (act 3) -- all the backward ever needs of the pre-activation,
         # and it shares the transcendental work with the GELU itself
@@ -493,13 +484,18 @@ class ConvNextLayerFn(torch.autograd.Function):
         w2d, n2 = packed_linear_dgrad(w2, dt, scale)
         dh = torch.empty((M, hid), dtype=dt, device=dev)
         gemm_nt(dy, 1, 1, M, C, dy.stride(3), 1, w2d, n2, hid, _epilogue(dh, hid, act=4, aux=hpre, ld_aux=hid))
-        # S[c,k] = sum_p dY[p,c] [G | m][p,k]  -> dW2, dscale, db2 (column `hid` = masked column sums of dY)
-        ldg = g.stride(0)
-        s = _zeros_f32(C * ldg, dev)
-        gemm_tn(dy, 1, 1, M, C, dy.stride(3), 1, g, ldg, ldg, _epilogue(s, ldg, out_f32=True, accumulate=True, tn=(0, ldg, 1)))
-        L.check(L.LIB.vkocr_mlp2_grad_finalize(L.ptr(s), ldg, ctx.inv_keep, s.data_ptr() + 4 * hid, ldg, L.ptr(w2.detach()),
-                                               L.ptr(b2.detach()), L.ptr(gamma), C, hid, L.ptr(grad_buffer(w2)),
-                                               L.ptr(grad_buffer(scale)), L.ptr(grad_buffer(b2)), _s()),
+        # sU[c] = sum_p m_b dY[p,c];  S[c,k] = sum_p dY[p,c] G[p,k] over the kept samples (x 1/p_keep in the finaliser)
+        su = _zeros_f32(C, dev)
+        if ctx.has_mask:
+            L.check(L.LIB.vkocr_scale_rows_colsum(_tag(dt), L.ptr(dy), dy.stride(3), None, 0, M, C, L.ptr(mask), H * W, L.ptr(su), _s()),
+                    'scale_rows_colsum')
+        else:
+            colsum(dy, dy.stride(3), M, C, su)
+        s = _zeros_f32(C * hid, dev)
+        gemm_tn(dy, 1, 1, M, C, dy.stride(3), 1, g, hid, hid, _epilogue(s, hid, out_f32=True, accumulate=True, tn=(0, hid, 1)))
+        L.check(L.LIB.vkocr_mlp2_grad_finalize(L.ptr(s), hid, ctx.inv_keep, L.ptr(su), 1, L.ptr(w2.detach()), L.ptr(b2.detach()),
+                                               L.ptr(gamma), C, hid, L.ptr(grad_buffer(w2)), L.ptr(grad_buffer(scale)),
+                                               L.ptr(grad_buffer(b2)), _s()),
                 'mlp2_grad_finalize')
         del s, g
         ldl = lnout.stride(3)
