@@ -489,3 +489,33 @@ def test_mlp_epilogue_gelu_with_derivative_side_channel(vk, shape):
     ops.gemm_nt(u, 1, 1, M, C, C, 1, w2, cp, hid, ops._epilogue(dh, hid, act=4, aux=side, ld_aux=hid))
     ref = (u.double() @ w2[:, :C].double().t()) * dgelu
     assert_close(dh.float(), ref, 4e-3, 'data gradient times the side channel')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', [(2, 8, 20, 20, 160, 160, 0), (2, 8, 1, 1, 20, 20, 0), (1, 16, 6, 6, 20, 20, 0), (2, 8, 3, 3, 20, 20, 0),
+                                  (1, 8, 5, 7, 12, 17, 0), (2, 8, 10, 10, 20, 20, 0), (2, 8, 20, 20, 80, 80, 1), (1, 8, 7, 5, 29, 23, 1)])
+def test_upsample_adjoint_against_interpolate(vk, case):
+    """Up-sampling (F.interpolate bilinear align_corners=False / nearest: upernext.py:59-82,174-197, fpn.py:121-144) and its
+    gather-form adjoint at every lane-split width of the kernel, against torch's own forward and autograd in fp32."""
+    from vkit_ocr_model_adaptive_scaling_b200 import ops
+    B, C, h, w, H, W, mode = case
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(h * 100 + H)
+    src = ops.alloc_nhwc(B, h, w, C, torch.float32, dev)
+    src.copy_(torch.randn(B, C, h, w, generator=g))
+    dst = ops.alloc_nhwc(B, H, W, C, torch.float32, dev)
+    ops.upsample_fwd(src, dst, C, mode, False)
+    xs = src.detach().clone().contiguous().requires_grad_(True)
+    ref = F.interpolate(xs, size=(H, W), mode='bilinear' if mode == 0 else 'nearest', **({'align_corners': False} if mode == 0 else {}))
+    assert_close(dst, ref.detach(), 1e-6, 'up-sampling forward')
+    gd = ops.alloc_nhwc(B, H, W, C, torch.float32, dev)
+    gd.copy_(torch.randn(B, C, H, W, generator=g))
+    gs = ops.alloc_nhwc(B, h, w, C, torch.float32, dev, zero=True)
+    ops.upsample_bwd(gd, gs, C, mode, False)
+    ref.backward(gd.contiguous())
+    assert_close(gs, xs.grad, 1e-5, 'up-sampling adjoint')
+    base = torch.randn(B, C, h, w, generator=g).to(dev)
+    gs2 = ops.alloc_nhwc(B, h, w, C, torch.float32, dev)
+    gs2.copy_(base)
+    ops.upsample_bwd(gd, gs2, C, mode, True)
+    assert_close(gs2, xs.grad + base, 1e-5, 'accumulating adjoint')
