@@ -150,6 +150,11 @@ int vkocr_upsample_fwd(int dtype, const void* src, long long ld_s, int h, int w,
                        int C, int mode, int accumulate, void* stream);
 int vkocr_upsample_bwd(int dtype, const void* ddst, long long ld_d, int H, int W, void* dsrc, long long ld_s, int h, int w, int B,
                        int C, int mode, int accumulate, void* stream);
+/* The same adjoint in two separable passes (x, then y) through a caller-owned fp32 workspace [B, H, w, C]: for large
+ * scale factors (PPM / top-down paths, upernext.py:59-82,174-197) where the one-pass gather has few threads and large
+ * windows.  Workspace: B * H * w * C floats.  Requires 16-byte aligned channel vectors. */
+int vkocr_upsample_bwd_separable(int dtype, const void* ddst, long long ld_d, int H, int W, void* dsrc, long long ld_s, int h, int w,
+                                 int B, int C, int mode, int accumulate, float* workspace, void* stream);
 int vkocr_avgpool_fwd(int dtype, const void* x, long long ld_x, int H, int W, void* y, long long ld_y, int S, int B, int C,
                       void* stream);
 int vkocr_avgpool_bwd(int dtype, const void* dy, long long ld_y, int S, void* dx, long long ld_x, int H, int W, int B, int C,

@@ -316,6 +316,14 @@ def upsample_bwd(ddst: Tensor, dsrc: Tensor, C: int, mode: int, accumulate: bool
     _, _, H, W = ddst.shape
     if L.PROFILE.active:
         L.PROFILE.note(f'upsample_bwd {B}x{H}x{W}->{h}x{w} C{C} mode{mode}', 0.0, (B * h * w + B * H * W) * C * ddst.element_size())
+    V = 16 // ddst.element_size()
+    if (H >= 3 * h or W >= 3 * w) and C % V == 0 and ddst.stride(3) % V == 0 and dsrc.stride(3) % V == 0 \
+            and ddst.data_ptr() % 16 == 0 and dsrc.data_ptr() % 16 == 0:
+        # large scale factors (PPM / top-down paths): two separable passes through an fp32 workspace [B, H, w, C]
+        ws = torch.empty(B * H * w * C, dtype=torch.float32, device=ddst.device)
+        L.check(L.LIB.vkocr_upsample_bwd_separable(_tag(ddst.dtype), L.ptr(ddst), ddst.stride(3), H, W, L.ptr(dsrc), dsrc.stride(3),
+                                                   h, w, B, C, mode, int(accumulate), L.ptr(ws), _s()), 'upsample_bwd_separable')
+        return
     L.check(L.LIB.vkocr_upsample_bwd(_tag(ddst.dtype), L.ptr(ddst), ddst.stride(3), H, W, L.ptr(dsrc), dsrc.stride(3), h, w, B, C,
                                      mode, int(accumulate), _s()), 'upsample_bwd')
 
