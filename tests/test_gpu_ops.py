@@ -493,7 +493,8 @@ def test_mlp_epilogue_gelu_with_derivative_side_channel(vk, shape):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', [(2, 8, 20, 20, 160, 160, 0), (2, 8, 1, 1, 20, 20, 0), (1, 16, 6, 6, 20, 20, 0), (2, 8, 3, 3, 20, 20, 0),
-                                  (1, 8, 5, 7, 12, 17, 0), (2, 8, 10, 10, 20, 20, 0), (2, 8, 20, 20, 80, 80, 1), (1, 8, 7, 5, 29, 23, 1)])
+                                  (1, 8, 5, 7, 12, 17, 0), (2, 8, 10, 10, 20, 20, 0), (2, 8, 20, 20, 80, 80, 1), (1, 8, 7, 5, 29, 23, 1),
+                                  (2, 16, 9, 13, 18, 26, 1), (1, 8, 1, 1, 2, 2, 1)])
 def test_upsample_adjoint_against_interpolate(vk, case):
     """Up-sampling (F.interpolate bilinear align_corners=False / nearest: upernext.py:59-82,174-197, fpn.py:121-144) and its
     gather-form adjoint at every lane-split width of the kernel, against torch's own forward and autograd in fp32."""
@@ -519,3 +520,7 @@ def test_upsample_adjoint_against_interpolate(vk, case):
     gs2.copy_(base)
     ops.upsample_bwd(gd, gs2, C, mode, True)
     assert_close(gs2, xs.grad + base, 1e-5, 'accumulating adjoint')
+    dst2 = ops.alloc_nhwc(B, H, W, C, torch.float32, dev)
+    dst2.copy_(gd)
+    ops.upsample_fwd(src, dst2, C, mode, True)
+    assert_close(dst2, ref.detach() + gd, 1e-6, 'accumulating forward')

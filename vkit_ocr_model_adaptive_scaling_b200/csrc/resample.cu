@@ -251,6 +251,93 @@ upsample_bwd_y_kernel(const float* __restrict__ ws, int H, T* __restrict__ dsrc,
     out.store(sp);
 }
 
+// ------------------------------------------------------------------------------------------------- exact x2 nearest
+// F.interpolate(scale 2, mode='nearest') of the FPN top-down path and head inputs (fpn.py:121-144,197-204):
+// dst[2i+p, 2j+q] = src[i, j]; the adjoint sums the 2x2 block.  One thread = one 16-byte channel vector of one source
+// pixel (consecutive threads on consecutive channel vectors: every access is a coalesced row segment).
+template <typename T>
+__global__ void __launch_bounds__(256)
+nearest2x_fwd_kernel(const T* __restrict__ src, long long ld_s, int h, int w, T* __restrict__ dst, long long ld_d, int B, int CV,
+                     int accumulate) {
+    constexpr int V = VkVec<T>::N;
+    const long long total = (long long)B * h * w * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int j = (int)(r % w);
+    r /= w;
+    const int i = (int)(r % h);
+    const long long b = r / h;
+    VkVec<T> v;
+    v.load(src + ((b * h + i) * w + j) * ld_s + cv * V);
+    float f[V];
+    if (accumulate) v.unpack(f);
+    T* d0 = dst + ((b * 2 * h + 2 * i) * (2LL * w) + 2 * j) * ld_d + cv * V;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            T* dp = d0 + ((long long)p * 2 * w + q) * ld_d;
+            if (accumulate) {
+                VkVec<T> o;
+                o.load(dp);
+                float g[V];
+                o.unpack(g);
+#pragma unroll
+                for (int e = 0; e < V; ++e) g[e] += f[e];
+                o.pack(g);
+                o.store(dp);
+            } else {
+                v.store(dp);
+            }
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nearest2x_bwd_kernel(const T* __restrict__ ddst, long long ld_d, T* __restrict__ dsrc, long long ld_s, int h, int w, int B, int CV,
+                     int accumulate) {
+    constexpr int V = VkVec<T>::N;
+    const long long total = (long long)B * h * w * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int j = (int)(r % w);
+    r /= w;
+    const int i = (int)(r % h);
+    const long long b = r / h;
+    const T* d0 = ddst + ((b * 2 * h + 2 * i) * (2LL * w) + 2 * j) * ld_d + cv * V;
+    VkVec<T> v[4];
+    v[0].load(d0);
+    v[1].load(d0 + ld_d);
+    v[2].load(d0 + 2LL * w * ld_d);
+    v[3].load(d0 + (2LL * w + 1) * ld_d);
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float f[V];
+        v[k].unpack(f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += f[e];
+    }
+    T* sp = dsrc + ((b * h + i) * w + j) * ld_s + cv * V;
+    if (accumulate) {
+        VkVec<T> o;
+        o.load(sp);
+        float f[V];
+        o.unpack(f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += f[e];
+    }
+    VkVec<T> out;
+    out.pack(acc);
+    out.store(sp);
+}
+
 // ------------------------------------------------------------------------------------------------- exact x2 bilinear
 // F.interpolate(scale 2, mode='bilinear', align_corners=False) is the separable 2-tap filter {0.25, 0.75} with the source
 // index clamped at the borders (out[2k] = .25 in[k-1] + .75 in[k], out[2k+1] = .75 in[k] + .25 in[k+1]); its adjoint is
@@ -664,6 +751,15 @@ int vkocr_upsample_fwd(int dtype, const void* src, long long ld_s, int h, int w,
         VK_CHECK_LAUNCH("upsample2x_fwd_kernel");
         return VKOCR_OK;
     }
+    if (vec && mode == 1 && H == 2 * h && W == 2 * w) {
+        const int V = dtype == VKOCR_F32 ? 4 : 8;
+        const long long total = (long long)B * h * w * (C / V);
+        VK_DISPATCH_DTYPE(dtype, T, (nearest2x_fwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                        reinterpret_cast<const T*>(src), ld_s, h, w, reinterpret_cast<T*>(dst), ld_d, B, C / V,
+                                        accumulate)));
+        VK_CHECK_LAUNCH("nearest2x_fwd_kernel");
+        return VKOCR_OK;
+    }
     VK_DISPATCH_DTYPE(dtype, T, (vec ? launch_upsample_fwd<T, VkVec<T>>(src, ld_s, h, w, dst, ld_d, H, W, B, C, mode, accumulate, s)
                                      : launch_upsample_fwd<T, VkScalar<T>>(src, ld_s, h, w, dst, ld_d, H, W, B, C, mode, accumulate, s)));
     VK_CHECK_LAUNCH("upsample_fwd_kernel");
@@ -685,6 +781,15 @@ int vkocr_upsample_bwd(int dtype, const void* ddst, long long ld_d, int H, int W
                                         reinterpret_cast<const T*>(ddst), ld_d, reinterpret_cast<T*>(dsrc), ld_s, h, w, B, C / V,
                                         accumulate)));
         VK_CHECK_LAUNCH("upsample2x_bwd_kernel");
+        return VKOCR_OK;
+    }
+    if (vec && mode == 1 && H == 2 * h && W == 2 * w) {
+        const int V = dtype == VKOCR_F32 ? 4 : 8;
+        const long long total = (long long)B * h * w * (C / V);
+        VK_DISPATCH_DTYPE(dtype, T, (nearest2x_bwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                                        reinterpret_cast<const T*>(ddst), ld_d, reinterpret_cast<T*>(dsrc), ld_s, h, w, B, C / V,
+                                        accumulate)));
+        VK_CHECK_LAUNCH("nearest2x_bwd_kernel");
         return VKOCR_OK;
     }
     VK_DISPATCH_DTYPE(dtype, T, (vec ? launch_upsample_bwd<T, VkVec<T>>(ddst, ld_d, H, W, dsrc, ld_s, h, w, B, C, mode, accumulate, s)
