@@ -157,6 +157,10 @@ int vkocr_upsample_bwd_separable(int dtype, const void* ddst, long long ld_d, in
                                  int B, int C, int mode, int accumulate, float* workspace, void* stream);
 int vkocr_avgpool_fwd(int dtype, const void* x, long long ld_x, int H, int W, void* y, long long ld_y, int S, int B, int C,
                       void* stream);
+/* The same pooling in two separable passes (columns of every row, then rows) through a caller-owned fp32 workspace of
+ * B * H * S * C floats: for bins of hundreds of pixels (PPM scales 1..6, upernext.py:59-82). */
+int vkocr_avgpool_fwd_separable(int dtype, const void* x, long long ld_x, int H, int W, void* y, long long ld_y, int S, int B, int C,
+                                float* workspace, void* stream);
 int vkocr_avgpool_bwd(int dtype, const void* dy, long long ld_y, int S, void* dx, long long ld_x, int H, int W, int B, int C,
                       int accumulate, void* stream);
 int vkocr_patchify_image(int dtype, const float* img, int B, int Cin, int H, int W, int p, void* out, int c_pad, void* stream);

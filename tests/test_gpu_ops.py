@@ -524,3 +524,24 @@ def test_upsample_adjoint_against_interpolate(vk, case):
     dst2.copy_(gd)
     ops.upsample_fwd(src, dst2, C, mode, True)
     assert_close(dst2, ref.detach() + gd, 1e-6, 'accumulating forward')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', [(2, 16, 20, 20, 1), (2, 16, 20, 20, 3), (1, 8, 64, 64, 6), (2, 8, 17, 23, 2), (1, 8, 5, 7, 3)])
+def test_adaptive_avgpool_against_torch(vk, case):
+    """nn.AdaptiveAvgPool2d(S) of the PPM block (upernext.py:59-65) on NHWC, one-pass and separable kernels, with gradient."""
+    from vkit_ocr_model_adaptive_scaling_b200 import ops
+    B, C, H, W, S = case
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(H * 10 + S)
+    x = ops.alloc_nhwc(B, H, W, C, torch.float32, dev)
+    x.copy_(torch.randn(B, C, H, W, generator=g))
+    xin = x.detach().requires_grad_(True)
+    y = ops.AvgPoolFn.apply(xin, S)
+    xr = x.detach().clone().contiguous().requires_grad_(True)
+    ref = F.adaptive_avg_pool2d(xr, S)
+    assert_close(y, ref.detach(), 1e-6, 'adaptive average pool')
+    pr = torch.randn(B, C, S, S, generator=g).to(dev)
+    (y * pr).sum().backward()
+    (ref * pr).sum().backward()
+    assert_close(xin.grad, xr.grad, 1e-6, 'adaptive average pool gradient')

@@ -84,6 +84,7 @@ _SIGNATURES = {
     'vkocr_upsample_bwd_separable': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p],
     'vkocr_avgpool_fwd': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+    'vkocr_avgpool_fwd_separable': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p],
     'vkocr_avgpool_bwd': [c_int, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p],
     'vkocr_patchify_image': [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     'vkocr_space_to_depth2': [c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_void_p],

@@ -515,6 +515,71 @@ avgpool_fwd_kernel(const T* __restrict__ x, long long ld_x, int H, int W, T* __r
     out.store(y + (((long long)b * S + i) * S + j) * ld_y + c);
 }
 
+// Separable form for large bins (PPM scales 1..6 on a 20x20 .. 64x64 map: a bin holds up to 4096 pixels and there are only
+// B * S * S * C / V outputs, so one thread per output is a serial, latency-bound sum: 0.2 TB/s at 2048^2 inference).
+// Pass 1 sums every image row over the bin's columns into fp32 ws[B, H, S, C]; pass 2 sums the bin's rows and scales.
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_rows_kernel(const T* __restrict__ x, long long ld_x, int H, int W, float* __restrict__ ws, int S, int B, int CV) {
+    constexpr int V = VkVec<T>::N;
+    const long long total = (long long)B * H * S * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int j = (int)(r % S);
+    const long long row = r / S;                        // b * H + yy
+    const int x0 = bin_lo(j, W, S), x1 = bin_hi(j, W, S);
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    const T* rp = x + row * W * ld_x + cv * V;
+    for (int xx = x0; xx < x1; ++xx) {
+        VkVec<T> v;
+        v.load(rp + (long long)xx * ld_x);
+        float f[V];
+        v.unpack(f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += f[e];
+    }
+    float* o = ws + idx * V;
+#pragma unroll
+    for (int e = 0; e < V; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_cols_kernel(const float* __restrict__ ws, int H, int W, T* __restrict__ y, long long ld_y, int S, int B, int CV) {
+    constexpr int V = VkVec<T>::N;
+    const long long total = (long long)B * S * S * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int j = (int)(r % S);
+    r /= S;
+    const int i = (int)(r % S);
+    const int b = (int)(r / S);
+    const int y0 = bin_lo(i, H, S), y1 = bin_hi(i, H, S), x0 = bin_lo(j, W, S), x1 = bin_hi(j, W, S);
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    for (int yy = y0; yy < y1; ++yy) {
+        const float* p = ws + ((((long long)b * H + yy) * S + j) * CV + cv) * V;
+#pragma unroll
+        for (int e = 0; e < V; e += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(p + e);
+            acc[e] += f.x; acc[e + 1] += f.y; acc[e + 2] += f.z; acc[e + 3] += f.w;
+        }
+    }
+    const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] *= inv;
+    VkVec<T> out;
+    out.pack(acc);
+    out.store(y + (((long long)b * S + i) * S + j) * ld_y + cv * V);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 avgpool_bwd_kernel(const T* __restrict__ dy, long long ld_y, int S, T* __restrict__ dx, long long ld_x, int H, int W, int B, int C,
@@ -831,6 +896,25 @@ int vkocr_avgpool_fwd(int dtype, const void* x, long long ld_x, int H, int W, vo
     VK_DISPATCH_DTYPE(dtype, T, (avgpool_fwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
                                     reinterpret_cast<const T*>(x), ld_x, H, W, reinterpret_cast<T*>(y), ld_y, S, B, C)));
     VK_CHECK_LAUNCH("avgpool_fwd_kernel");
+    return VKOCR_OK;
+}
+
+// The same pooling in two separable passes through a caller-owned fp32 workspace [B, H, S, C] (large bins).
+int vkocr_avgpool_fwd_separable(int dtype, const void* x, long long ld_x, int H, int W, void* y, long long ld_y, int S, int B, int C,
+                                float* workspace, void* stream) {
+    VK_REQUIRE(x && y && workspace && S >= 1, VKOCR_BAD_ARGUMENT, "avgpool_fwd_separable: bad argument");
+    VK_REQUIRE(vec_ok(dtype, C, ld_x, ld_y) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, VKOCR_BAD_ALIGN,
+               "avgpool_fwd_separable: C %d / strides not vector aligned", C);
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    const long long t1 = (long long)B * H * S * (C / V), t2 = (long long)B * S * S * (C / V);
+    if (t2 == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    VK_DISPATCH_DTYPE(dtype, T, (avgpool_rows_kernel<T><<<(unsigned)((t1 + 255) / 256), 256, 0, s>>>(
+                                    reinterpret_cast<const T*>(x), ld_x, H, W, workspace, S, B, C / V)));
+    VK_CHECK_LAUNCH("avgpool_rows_kernel");
+    VK_DISPATCH_DTYPE(dtype, T, (avgpool_cols_kernel<T><<<(unsigned)((t2 + 255) / 256), 256, 0, s>>>(
+                                    workspace, H, W, reinterpret_cast<T*>(y), ld_y, S, B, C / V)));
+    VK_CHECK_LAUNCH("avgpool_cols_kernel");
     return VKOCR_OK;
 }
 

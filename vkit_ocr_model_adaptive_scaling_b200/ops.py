@@ -648,7 +648,12 @@ class AvgPoolFn(torch.autograd.Function):
     def forward(ctx, x: Tensor, S: int) -> Tensor:
         B, H, W, C, ld = geom(x)
         y = alloc_nhwc(B, S, S, C, x.dtype, x.device)
-        L.check(L.LIB.vkocr_avgpool_fwd(_tag(x.dtype), L.ptr(x), ld, H, W, L.ptr(y), y.stride(3), S, B, C, _s()), 'avgpool_fwd')
+        if H * W >= 64 * S * S:      # bins of >= 64 pixels: two separable passes instead of one serial sum per output
+            ws = torch.empty(B * H * S * C, dtype=torch.float32, device=x.device)
+            L.check(L.LIB.vkocr_avgpool_fwd_separable(_tag(x.dtype), L.ptr(x), ld, H, W, L.ptr(y), y.stride(3), S, B, C, L.ptr(ws),
+                                                      _s()), 'avgpool_fwd_separable')
+        else:
+            L.check(L.LIB.vkocr_avgpool_fwd(_tag(x.dtype), L.ptr(x), ld, H, W, L.ptr(y), y.stride(3), S, B, C, _s()), 'avgpool_fwd')
         ctx.meta = (B, H, W, C, S)
         return y
 
