@@ -112,6 +112,28 @@ int vkocr_gemm_nt_heads(int dtype, const void* x, const VkocrConvGeom* g, const 
 int vkocr_gemm_tn(int dtype, int backend, const void* pmat, const VkocrConvGeom* g, const void* qmat, int J, long long ld_q,
                   const VkocrEpilogue* ep, void* stream);
 
+/* ------------------------------------------------------------- heads with up-sampling: convolve first, resample after
+ * Replaces F.interpolate(x, scale_factor) -> conv k x k -> LayerNorm -> GELU -> Linear (-> Softplus) of
+ * UperNextHead.forward (model/upernext.py:233-248, bilinear) / FpnHead.forward (model/fpn.py:193-208, nearest; 5x5 for
+ * factors in (2, 4]) and nn.Softplus (model/adaptive_scaling.py:101,140) for upsampling_factor >= 2.  The channel mixing
+ * of the convolution commutes with the per-channel interpolation:
+ *     conv(up(x))[r, s] = bias + sum_{dy,dx} up(Z_{dy,dx})[r + dy - k/2, s + dx - k/2],  Z_{dy,dx} = x . W[:, :, dy, dx]^T
+ * so the contraction is ONE plain vkocr_gemm_nt on the low-resolution map (N = k*k*ntot columns ordered
+ * tap * ntot + head * slot + n; factor^2 fewer FLOPs, the up-sampled tensor never exists) and the interpolation runs on its
+ * output:
+ * vkocr_head_combine_fwd: z [B*h*w, ld_z] -> per head interpolate + shift + sum + conv bias -> LayerNorm -> GELU ->
+ *   Linear(inner -> O <= 4) (-> Softplus) -> heads->out[h] (NCHW fp32 at (factor*h, factor*w)); conv_out (nullable):
+ *   [B*H*W, ld_conv] the pre-LayerNorm conv output in storage dtype, which vkocr_head_tail_bwd consumes.
+ * vkocr_head_combine_bwd: the exact adjoint, d(conv output) [B*H*W, ld_dc] (`width` = ntot channels) -> dz [B*h*w, ld_z];
+ *   the data / weight gradients are then plain vkocr_gemm_nt / vkocr_gemm_tn calls on (dz, x).
+ * mode: 0 bilinear (align_corners=False), 1 nearest.  algo: 0 = pick (a shared-memory-tiled kernel for factor 2, 3x3),
+ * 1 = force the generic gather kernel (cross-check in the tests). */
+int vkocr_head_combine_fwd(int dtype, const void* z, long long ld_z, int B, int h, int w, int factor, int mode, int ks, int ntot,
+                           const float* conv_bias, const VkocrHeadTail* heads, void* conv_out, long long ld_conv, int algo,
+                           void* stream);
+int vkocr_head_combine_bwd(int dtype, const void* dconv, long long ld_dc, int B, int h, int w, int factor, int mode, int ks,
+                           int width, void* dz, long long ld_z, int algo, void* stream);
+
 /* ---------------------------------------------------------------------------------------- depthwise 7x7 conv
  * Replaces helper.dconv7x7 (helper.py:61-73; convnext.py:30) forward, data gradient (same kernel, mirrored taps,
  * `add` fuses the residual gradient of convnext.py:58) and weight gradient.  `wt` is the [49][C] fp32 tap table
@@ -240,6 +262,10 @@ int vkocr_unpack_grad(const float* g, int N, int T, int C, float* y, long long s
 int vkocr_mlp2_grad_finalize(const float* S, long long ld_s, float s_scale, const float* sU, long long ld_su, const float* W2,
                              const float* b2, const float* gamma, int C, int K, float* dW2, float* dgamma, float* db2, void* stream);
 int vkocr_accumulate_f32(const float* a, float* y, long long n, void* stream);
+/* y[i0*y0 + i1*y1 + i2*y2] += g[i0*g0 + i1*g1 + i2*g2] for i0 < n0, i1 < n1, i2 < n2 (strides in elements): a weight
+ * gradient from GEMM order (e.g. the tap-major rows of the head-group product) into the Conv2d OIHW parameter layout. */
+int vkocr_scatter_add_f32(const float* g, long long g0, long long g1, long long g2, int n0, int n1, int n2, float* y, long long y0,
+                          long long y1, long long y2, void* stream);
 int vkocr_scale_rows(int dtype, const void* x, long long ld_x, void* y, long long ld_y, long long rows, int C,
                      const float* scale, int rows_per_group, void* stream);
 

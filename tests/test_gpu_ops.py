@@ -225,6 +225,50 @@ def test_softplus_head_and_odd_inner(vk, dtype):
     _run_pair(vk, dtype, head, lambda m, t: m(t), lambda p, t: om.head_forward(p, '0.', t, 'upernext', 2, softplus=True), x)
 
 
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('kind,shape', [('upernext', (2, 64, 9, 13)), ('fpn', (2, 64, 9, 13)), ('upernext', (1, 384, 1, 1)),
+                                        ('fpn', (1, 64, 1, 7)), ('upernext', (3, 64, 7, 1)), ('upernext', (1, 64, 5, 20))])
+def test_head_x2_convolve_first_against_oracle(vk, dtype, kind, shape):
+    """x2 heads run 'convolve first, resample after' (csrc/head_combine.cu): odd sizes, 1-pixel-wide maps (every clamp and
+    padding case of the tiled kernels), tiles that straddle the image edge."""
+    from oracle import model as om
+    cls = vk.model.UperNextHead if kind == 'upernext' else vk.model.FpnHead
+    head = cls(shape[1], 3, upsampling_factor=2, init_output_bias=-0.2)
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(16))
+    _run_pair(vk, dtype, head, lambda m, t: m(t), lambda p, t: om.head_forward(p, '', t, kind, 2), x)
+
+
+@pytest.mark.parametrize('kind', ['upernext', 'fpn'])
+def test_head_convolve_first_kernels_agree(vk, kind):
+    """The shared-memory-tiled combine / adjoint kernels, the generic gather kernels and the legacy path (up-sample, then
+    implicit-GEMM conv) are three statements of one linear map: in fp32 mode they must agree to rounding."""
+    from vkit_ocr_model_adaptive_scaling_b200 import ops
+    dev = torch.device('cuda')
+    cls = vk.model.UperNextHead if kind == 'upernext' else vk.model.FpnHead
+    head = cls(48, 4, upsampling_factor=2, init_output_bias=0.1).to(dev)
+    randomize(head, 31)
+    x0 = torch.randn(2, 48, 11, 19, generator=torch.Generator().manual_seed(17)).to(dev)
+    pr = _probe((2, 4, 22, 38), 5, dev)
+    results = []
+    try:
+        for tapsplit, algo in ((True, 0), (True, 1), (False, 0)):
+            ops.TAPSPLIT, ops.COMBINE_ALGO = tapsplit, algo
+            head.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_(True)
+            with vk.precision(torch.float32):
+                y = head(x)
+                (y * pr).sum().backward()
+            torch.cuda.synchronize()
+            results.append((y.detach().clone(), x.grad.clone(), {n: p.grad.clone() for n, p in head.named_parameters()}))
+    finally:
+        ops.TAPSPLIT, ops.COMBINE_ALGO = True, 0
+    for other, what in ((results[1], 'generic kernels'), (results[2], 'legacy path')):
+        assert_close(results[0][0], other[0], 2e-5, f'{what}: output')
+        assert_close(results[0][1], other[1], 2e-5, f'{what}: input gradient')
+        for n in results[0][2]:
+            assert_close(results[0][2][n], other[2][n], 5e-5, f'{what}: grad {n}', atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------------------- losses
 def _loss_inputs(B, H, W, inset, P, seed, dev):
     from oracle import synth

@@ -68,6 +68,10 @@ _SIGNATURES = {
     'vkocr_gemm_nt': [c_int, c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, _P(Epilogue), c_void_p],
     'vkocr_gemm_nt_heads': [c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, _P(Epilogue), _P(HeadTail), c_void_p],
     'vkocr_gemm_tn': [c_int, c_int, c_void_p, _P(ConvGeom), c_void_p, c_int, c_ll, _P(Epilogue), c_void_p],
+    'vkocr_head_combine_fwd': [c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, _P(HeadTail), c_void_p,
+                               c_ll, c_int, c_void_p],
+    'vkocr_head_combine_bwd': [c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p],
+    'vkocr_scatter_add_f32': [c_void_p, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_ll, c_ll, c_void_p],
     'vkocr_layernorm_fwd': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_float, c_int,
                             c_void_p, c_void_p, c_void_p],
     'vkocr_layernorm_bwd': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

@@ -36,6 +36,19 @@ unpack_grad_kernel(const float* __restrict__ g, int N, int T, int C, float* __re
     y[n * s_n + t * s_t + c * s_c] += g[idx];
 }
 
+// y[i0*y0 + i1*y1 + i2*y2] += g[i0*g0 + i1*g1 + i2*g2]: a weight gradient from any GEMM order into the parameter's layout
+__global__ void __launch_bounds__(256)
+scatter_add_kernel(const float* __restrict__ g, long long g0, long long g1, long long g2, int n0, int n1, int n2,
+                   float* __restrict__ y, long long y0, long long y1, long long y2) {
+    const long long total = (long long)n0 * n1 * n2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int i2 = (int)(idx % n2);
+    const int i1 = (int)((idx / n2) % n1);
+    const long long i0 = idx / ((long long)n2 * n1);
+    y[i0 * y0 + i1 * y1 + i2 * y2] += g[i0 * g0 + i1 * g1 + i2 * g2];
+}
+
 // ConvNeXt MLP second Linear: S[c,k] = s_scale * sum_p dY[p,c] G[p,k] (G zeroed for dropped samples, s_scale = 1 / p_keep),
 // sU[c] = sum_p m_b(p) dY[p,c] (the mask channel's column of the same product)
 //   dW2[c,k] += gamma[c] * S[c,k];  dgamma[c] += sum_k W2[c,k] S[c,k] + b2[c] sU[c];  db2[c] += gamma[c] sU[c]
@@ -114,6 +127,17 @@ int vkocr_unpack_grad(const float* g, int N, int T, int C, float* y, long long s
     if (total == 0) return VKOCR_OK;
     unpack_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, N, T, C, y, s_n, s_t, s_c);
     VK_CHECK_LAUNCH("unpack_grad_kernel");
+    return VKOCR_OK;
+}
+
+int vkocr_scatter_add_f32(const float* g, long long g0, long long g1, long long g2, int n0, int n1, int n2, float* y, long long y0,
+                          long long y1, long long y2, void* stream) {
+    VK_REQUIRE(g && y, VKOCR_BAD_ARGUMENT, "scatter_add_f32: null argument");
+    const long long total = (long long)n0 * n1 * n2;
+    if (total == 0) return VKOCR_OK;
+    scatter_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, g0, g1, g2, n0, n1, n2, y,
+                                                                                                             y0, y1, y2);
+    VK_CHECK_LAUNCH("scatter_add_kernel");
     return VKOCR_OK;
 }
 

@@ -197,6 +197,37 @@ def packed_conv_dgrad(ws: Sequence[Tensor], dtype: torch.dtype, n_slot: Optional
     return buf, n_pad
 
 
+def packed_tapsplit_fwd(ws: Sequence[Tensor], dtype: torch.dtype, slot: int) -> Tuple[Tensor, int, int]:
+    """Conv2d weights (N_h, C, k, k) of the heads of a group -> [k*k * ntot, c_pad] operand of Z = X . W_tap^T with rows
+    ordered tap * ntot + head * slot + n (see csrc/head_combine.cu)."""
+    C, k = ws[0].shape[1], ws[0].shape[2]
+    T = k * k
+    c_pad = _ceil_to(C, 64)
+    ntot = slot * len(ws)
+
+    def fill(b: Tensor) -> None:
+        for h, w in enumerate(ws):
+            _pack(w.detach(), C * T, 1, T, w.shape[0], T, C, 0, None, b, h * slot * c_pad, c_pad, ntot * c_pad)
+
+    buf = PACK.get(('tapsplit_fwd', tuple(id(w) for w in ws), dtype, slot), list(ws), (T * ntot, c_pad), dtype, fill)
+    return buf, c_pad, T * ntot
+
+
+def packed_tapsplit_dgrad(ws: Sequence[Tensor], dtype: torch.dtype, slot: int) -> Tuple[Tensor, int]:
+    """Conv2d weights -> [C, k_pad] operand of dX = dZ . W with columns ordered tap * ntot + head * slot + n."""
+    C, k = ws[0].shape[1], ws[0].shape[2]
+    T = k * k
+    ntot = slot * len(ws)
+    k_pad = _ceil_to(T * ntot, 64)
+
+    def fill(b: Tensor) -> None:
+        for h, w in enumerate(ws):
+            _pack(w.detach(), T, 1, C * T, C, T, w.shape[0], 0, None, b, h * slot, k_pad, ntot)
+
+    buf = PACK.get(('tapsplit_dgrad', tuple(id(w) for w in ws), dtype, slot), list(ws), (C, k_pad), dtype, fill)
+    return buf, k_pad
+
+
 def packed_patch_fwd(w: Tensor, dtype: torch.dtype) -> Tuple[Tensor, int]:
     """Patchify conv weight (N, C, p, p), stride p -> [N, c_pad] with k = (ky*p+kx)*C + c."""
     N, C, p, _ = w.shape
@@ -238,6 +269,8 @@ def _epilogue(out: Tensor, ldo: int, *, out_f32: bool = False, accumulate: bool 
                       None if aux is None else aux.data_ptr(), ld_aux, tn[0], tn[1], tn[2])
 
 
+TAPSPLIT = True     # heads with upsampling_factor >= 2: convolve on the low-resolution map, resample after (head_combine.cu)
+COMBINE_ALGO = 0    # tests set this to 1 to force the generic gather kernels of head_combine.cu (cross-check of the tiled ones)
 SIMT_BACKEND = 0  # tests set this to 1 to route bf16 GEMMs through the SIMT kernel (cross-check of the tcgen05 path)
 
 
@@ -749,27 +782,18 @@ class HeadGroupFn(torch.autograd.Function):
         B, h, w, C, ld = geom(x)
         dt, dev = x.dtype, x.device
         H, W = h * factor, w * factor
-        if factor > 1:
-            up = alloc_nhwc(B, H, W, C, dt, dev)
-            upsample_fwd(x, up, C, mode, False)
-        else:
-            up = x
         inners = [int(hd[0].shape[0]) for hd in heads]
         ks = int(heads[0][0].shape[2])
         slot = _ceil_to(max(inners), 16)
         ntot = slot * nh
-        wp, c_pad, rows = packed_conv_fwd([hd[0] for hd in heads], dt, slot)
         bias = torch.zeros(ntot, dtype=torch.float32, device=dev)
         for i, hd in enumerate(heads):
             bias[i * slot:i * slot + inners[i]].copy_(hd[1].detach())   # tiny staging copy of the conv biases
         train = _needs_grad(ctx)
         M = B * H * W
         outs = [torch.empty((B, int(hd[4].shape[0]), H, W), dtype=torch.float32, device=dev) for hd in heads]
-        fused = dt == torch.bfloat16 and SIMT_BACKEND == 0 and nh <= L.MAX_HEADS and slot <= 256
-        if fused:
-            # conv + every head's LayerNorm/GELU/projection(/Softplus) in ONE tcgen05 GEMM: the tails run in the epilogue on
-            # the fp32 accumulators; the bf16 conv output is only written when the backward will need it
-            conv = alloc_nhwc(B, H, W, ntot, dt, dev) if train else None
+
+        def head_tail() -> L.HeadTail:
             ht = L.HeadTail()
             ht.num_heads, ht.slot, ht.pixels_per_image = nh, slot, H * W
             for i, hd in enumerate(heads):
@@ -777,34 +801,69 @@ class HeadGroupFn(torch.autograd.Function):
                 ht.w2[i], ht.b2[i] = hd[4].detach().data_ptr(), hd[5].detach().data_ptr()
                 ht.out[i] = outs[i].data_ptr()
                 ht.inner[i], ht.out_channels[i], ht.softplus[i] = inners[i], int(hd[4].shape[0]), int(softplus[i])
+            return ht
+
+        tapsplit = factor > 1 and TAPSPLIT and nh <= L.MAX_HEADS and slot <= 256 and max(int(hd[4].shape[0]) for hd in heads) <= 4
+        up = None
+        if tapsplit:
+            # convolve first, resample after (csrc/head_combine.cu): Z = X . W_tap^T on the LOW-resolution map -- factor^2
+            # fewer FLOPs than the conv on the up-sampled map, which is never built -- then one pass that interpolates,
+            # shifts and sums the taps and runs every head's LayerNorm/GELU/projection(/Softplus) on the fp32 sums
+            T = ks * ks
+            wz, c_pad, nz = packed_tapsplit_fwd([hd[0] for hd in heads], dt, slot)
+            m_low = B * h * w
+            z = torch.empty((m_low, nz), dtype=dt, device=dev)
+            gemm_nt(x, 1, 1, m_low, C, ld, 1, wz, c_pad, nz, _epilogue(z, nz))
+            conv = alloc_nhwc(B, H, W, ntot, dt, dev) if train else None
+            ht = head_tail()
             if L.PROFILE.active:
-                L.PROFILE.note(f'gemm_nt_heads ks{ks} M{M} K{ks * ks * C} N{ntot}', 2.0 * M * ks * ks * C * ntot)
-            g = L.ConvGeom(B, H, W, ks, C, up.stride(3), c_pad)
-            ep = L.Epilogue(None if conv is None else conv.data_ptr(), ntot if conv is None else conv.stride(3), 0, 0, None, 0,
-                            bias.data_ptr(), 0, None, None, 1, None, 0, None, 0, 0, 0, 0)
-            L.check(L.LIB.vkocr_gemm_nt_heads(_tag(dt), L.ptr(up), ctypes.byref(g), L.ptr(wp), ntot, ctypes.byref(ep), ctypes.byref(ht),
-                                              _s()), 'gemm_nt_heads')
+                L.PROFILE.note(f'head_combine_fwd {B}x{h}x{w} x{factor} ks{ks} N{ntot}', 0.0,
+                               (m_low * nz + (M * ntot if train else 0)) * z.element_size() + 4.0 * M * sum(int(hd[4].shape[0]) for hd in heads))
+            L.check(L.LIB.vkocr_head_combine_fwd(_tag(dt), L.ptr(z), nz, B, h, w, factor, mode, ks, ntot, L.ptr(bias), ctypes.byref(ht),
+                                                 L.ptr(conv), 0 if conv is None else conv.stride(3), COMBINE_ALGO, _s()),
+                    'head_combine_fwd')
+            del z
         else:
-            conv = alloc_nhwc(B, H, W, ntot, dt, dev)
-            gemm_nt(up, B, H, W, C, up.stride(3), ks, wp, c_pad, ntot, _epilogue(conv, conv.stride(3), bias=bias))
-            for i, hd in enumerate(heads):
-                O = int(hd[4].shape[0])
-                sl = conv[:, i * slot:(i + 1) * slot]
+            if factor > 1:
+                up = alloc_nhwc(B, H, W, C, dt, dev)
+                upsample_fwd(x, up, C, mode, False)
+            else:
+                up = x
+            wp, c_pad, rows = packed_conv_fwd([hd[0] for hd in heads], dt, slot)
+            fused = dt == torch.bfloat16 and SIMT_BACKEND == 0 and nh <= L.MAX_HEADS and slot <= 256
+            if fused:
+                # conv + every head's LayerNorm/GELU/projection(/Softplus) in ONE tcgen05 GEMM: the tails run in the epilogue
+                # on the fp32 accumulators; the bf16 conv output is only written when the backward will need it
+                conv = alloc_nhwc(B, H, W, ntot, dt, dev) if train else None
+                ht = head_tail()
                 if L.PROFILE.active:
-                    L.PROFILE.note(f'head_tail_fwd rows{M} inner{inners[i]} O{O}', 0.0, M * (slot * conv.element_size() + 4 * O))
-                L.check(L.LIB.vkocr_head_tail_fwd(_tag(dt), L.ptr(sl), conv.stride(3), inners[i], slot, L.ptr(hd[2].detach()),
-                                                  L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), L.ptr(hd[5].detach()), O,
-                                                  int(softplus[i]), L.ptr(outs[i]), H * W, M, _s()), 'head_tail_fwd')
+                    L.PROFILE.note(f'gemm_nt_heads ks{ks} M{M} K{ks * ks * C} N{ntot}', 2.0 * M * ks * ks * C * sum(inners))
+                g = L.ConvGeom(B, H, W, ks, C, up.stride(3), c_pad)
+                ep = L.Epilogue(None if conv is None else conv.data_ptr(), ntot if conv is None else conv.stride(3), 0, 0, None, 0,
+                                bias.data_ptr(), 0, None, None, 1, None, 0, None, 0, 0, 0, 0)
+                L.check(L.LIB.vkocr_gemm_nt_heads(_tag(dt), L.ptr(up), ctypes.byref(g), L.ptr(wp), ntot, ctypes.byref(ep),
+                                                  ctypes.byref(ht), _s()), 'gemm_nt_heads')
+            else:
+                conv = alloc_nhwc(B, H, W, ntot, dt, dev)
+                gemm_nt(up, B, H, W, C, up.stride(3), ks, wp, c_pad, ntot, _epilogue(conv, conv.stride(3), bias=bias))
+                for i, hd in enumerate(heads):
+                    O = int(hd[4].shape[0])
+                    sl = conv[:, i * slot:(i + 1) * slot]
+                    if L.PROFILE.active:
+                        L.PROFILE.note(f'head_tail_fwd rows{M} inner{inners[i]} O{O}', 0.0, M * (slot * conv.element_size() + 4 * O))
+                    L.check(L.LIB.vkocr_head_tail_fwd(_tag(dt), L.ptr(sl), conv.stride(3), inners[i], slot, L.ptr(hd[2].detach()),
+                                                      L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), L.ptr(hd[5].detach()), O,
+                                                      int(softplus[i]), L.ptr(outs[i]), H * W, M, _s()), 'head_tail_fwd')
         if train:
-            ctx.save_for_backward(x, up, conv, *outs, *params)
-            ctx.meta = (nh, factor, mode, tuple(softplus), slot, ks)
+            ctx.save_for_backward(x, x if up is None else up, conv, *outs, *params)
+            ctx.meta = (nh, factor, mode, tuple(softplus), slot, ks, tapsplit)
         else:
             del conv
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts: Tensor):
-        nh, factor, mode, softplus, slot, ks = ctx.meta
+        nh, factor, mode, softplus, slot, ks, tapsplit = ctx.meta
         saved = ctx.saved_tensors
         x, up, conv = saved[0], saved[1], saved[2]
         outs = saved[3:3 + nh]
@@ -831,25 +890,47 @@ class HeadGroupFn(torch.autograd.Function):
                                               L.ptr(grad_buffer(hd[2])), L.ptr(grad_buffer(hd[3])), L.ptr(grad_buffer(hd[4])),
                                               L.ptr(grad_buffer(hd[5])), L.ptr(grad_buffer(hd[1])), _s()), 'head_tail_bwd')
         T = ks * ks
-        # weight gradient of all heads in one pass over (dconv, up): G[n_total, C, T] in OIHW order, then per-head slices
-        gw = _zeros_f32(ntot * C * T, dev)
-        gemm_tn(dconv, B, H, W, ntot, dconv.stride(3), ks, up, C, up.stride(3),
-                _epilogue(gw, C, out_f32=True, accumulate=True, tn=(1, C * T, T)))
-        for i, hd in enumerate(heads):
-            inner = int(hd[0].shape[0])
-            n = inner * C * T
-            L.check(L.LIB.vkocr_accumulate_f32(ctypes.c_void_p(gw.data_ptr() + 4 * i * slot * C * T), L.ptr(grad_buffer(hd[0])), n, _s()),
-                    'accumulate_f32')
         dx = None
-        if ctx.needs_input_grad[0]:
-            wd, n_pad = packed_conv_dgrad([hd[0] for hd in heads], dt, slot)
-            dup = alloc_nhwc(B, H, W, C, dt, dev)
-            gemm_nt(dconv, B, H, W, ntot, dconv.stride(3), ks, wd, n_pad, C, _epilogue(dup, dup.stride(3)))
-            if factor > 1:
+        if tapsplit:
+            # adjoint of the interpolate + shift + sum, then two plain GEMMs on the low-resolution grid
+            m_low = B * h * w
+            nz = T * ntot
+            dz = torch.empty((m_low, nz), dtype=dt, device=dev)
+            if L.PROFILE.active:
+                L.PROFILE.note(f'head_combine_bwd {B}x{h}x{w} x{factor} ks{ks} N{ntot}', 0.0, (M * ntot + m_low * nz) * dz.element_size())
+            L.check(L.LIB.vkocr_head_combine_bwd(_tag(dt), L.ptr(dconv), dconv.stride(3), B, h, w, factor, mode, ks, ntot, L.ptr(dz), nz,
+                                                 COMBINE_ALGO, _s()), 'head_combine_bwd')
+            del dconv
+            gw = _zeros_f32(nz * C, dev)
+            gemm_tn(dz, 1, 1, m_low, nz, nz, 1, x, C, ld, _epilogue(gw, C, out_f32=True, accumulate=True, tn=(0, C, 1)))
+            for i, hd in enumerate(heads):
+                inner = int(hd[0].shape[0])
+                # gw[(tap * ntot + i * slot + n) * C + c]  ->  grad[(n * C + c) * T + tap]
+                L.check(L.LIB.vkocr_scatter_add_f32(ctypes.c_void_p(gw.data_ptr() + 4 * i * slot * C), C, ntot * C, 1, inner, T, C,
+                                                    L.ptr(grad_buffer(hd[0])), C * T, 1, T, _s()), 'scatter_add_f32')
+            if ctx.needs_input_grad[0]:
+                wd, k_pad = packed_tapsplit_dgrad([hd[0] for hd in heads], dt, slot)
                 dx = alloc_nhwc(B, h, w, C, dt, dev)
-                upsample_bwd(dup, dx, C, mode, False)
-            else:
-                dx = dup
+                gemm_nt(dz, 1, 1, m_low, nz, nz, 1, wd, k_pad, C, _epilogue(dx, dx.stride(3)))
+        else:
+            # weight gradient of all heads in one pass over (dconv, up): G[n_total, C, T] in OIHW order, then per-head slices
+            gw = _zeros_f32(ntot * C * T, dev)
+            gemm_tn(dconv, B, H, W, ntot, dconv.stride(3), ks, up, C, up.stride(3),
+                    _epilogue(gw, C, out_f32=True, accumulate=True, tn=(1, C * T, T)))
+            for i, hd in enumerate(heads):
+                inner = int(hd[0].shape[0])
+                n = inner * C * T
+                L.check(L.LIB.vkocr_accumulate_f32(ctypes.c_void_p(gw.data_ptr() + 4 * i * slot * C * T), L.ptr(grad_buffer(hd[0])), n, _s()),
+                        'accumulate_f32')
+            if ctx.needs_input_grad[0]:
+                wd, n_pad = packed_conv_dgrad([hd[0] for hd in heads], dt, slot)
+                dup = alloc_nhwc(B, H, W, C, dt, dev)
+                gemm_nt(dconv, B, H, W, ntot, dconv.stride(3), ks, wd, n_pad, C, _epilogue(dup, dup.stride(3)))
+                if factor > 1:
+                    dx = alloc_nhwc(B, h, w, C, dt, dev)
+                    upsample_bwd(dup, dx, C, mode, False)
+                else:
+                    dx = dup
         _ready(*params)
         return (dx, None, None, None) + (None,) * len(params)
 
