@@ -1173,7 +1173,10 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     // once (TMA) and read once (MMA), ~200 B/clk at full MMA rate against the SM's 128 B/clk -- the tensor pipe sat at
     // 62 % (ncu).  A pair shares the weight tile: each CTA stages its 128 pixel rows and HALF of the weight rows.
     p.cta2 = (pix_tiles % 2 == 0) && (p.BN % 16 == 0) && (g->ks * g->ks * (g->c_pad / BK) >= 16) && vkocr_sm_count() % 2 == 0;
-    if (const char* e = getenv("VKOCR_CTA2")) p.cta2 = p.cta2 && atoi(e) != 0;
+    if (const char* e = getenv("VKOCR_CTA2")) {   // 0: never, 2: whenever the shape allows it (experiments)
+        if (atoi(e) == 2) p.cta2 = (pix_tiles % 2 == 0) && (p.BN % 16 == 0) && vkocr_sm_count() % 2 == 0;
+        else p.cta2 = p.cta2 && atoi(e) != 0;
+    }
     p.stage_bytes = A_BYTES + (p.cta2 ? p.BN / 2 : p.BN) * 128;
     p.units = pix_tiles * p.n_tiles;
     p.ep = *ep;

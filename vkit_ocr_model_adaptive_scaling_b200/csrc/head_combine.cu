@@ -296,13 +296,15 @@ hc_bwd_generic_kernel(const T* __restrict__ dc, long long ld_dc, Geom g, int wid
 //   a = 0: dy 0 -> (i-1, i), dy 1 -> (i-1, i), dy 2 -> (i, i+1);   a = 1: dy 0 -> (i-1, i), dy 1 -> (i, i+1), dy 2 -> (i, i+1)
 // with the rows clamped into [0, h) (the clamp of align_corners=False interpolation folds onto the same two rows) and the
 // pair's weights taken from the interpolation of Y; a Y outside [0, 2h) is conv padding: weights 0.  Same for columns.
+// The kernels are bound by instruction issue, so all per-element arithmetic runs on packed fp32 pairs (FFMA2), the tails of
+// the two output pixels of a (row, low-res column) run together (shared V loads, interleaved dependency chains), and the
+// warp reductions keep only half of the values per butterfly round.
 constexpr int HC_TJ = 8;            // low-res columns per tile
 constexpr int HC_R = 2;             // low-res rows per tile
 constexpr int HC_QL = HC_TJ + 2;    // columns of V kept per tile (one halo column each side)
-__device__ __forceinline__ int hc_pos(int a, int d, int k) {   // offset of the k-th source row of (parity a, tap d)
+__device__ __forceinline__ constexpr int hc_pos(int a, int d, int k) {   // offset of the k-th source row of (parity a, tap d)
     // a=0: (-1,0) (-1,0) (0,1);  a=1: (-1,0) (0,1) (0,1)
-    const int first = (a == 0) ? (d == 2 ? 0 : -1) : (d == 0 ? -1 : 0);
-    return first + k;
+    return ((a == 0) ? (d == 2 ? 0 : -1) : (d == 0 ? -1 : 0)) + k;
 }
 // weights of the two (clamped) source rows of up-sampled coordinate Y = 2 i + a + d - 1
 __device__ __forceinline__ float2 hc_pair_weights(int i, int a, int d, int in, int mode) {
@@ -323,19 +325,181 @@ __device__ __forceinline__ float2 hc_pair_weights(int i, int a, int d, int in, i
 // thread per vector writes and when one lane per vector reads.
 __device__ __forceinline__ int hc_plane(int cv, int e, int nvec) { return (e >> 2) * (nvec * 4) + cv * 4; }
 
+// 16 bytes of storage -> V/2 fp32 pairs
+template <typename T> struct HcPairs;
+template <> struct HcPairs<__nv_bfloat16> {
+    static constexpr int NP = 4;
+    static __device__ __forceinline__ void unpack(const uint4& raw, float2 (&p)[4]) {
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+    }
+    static __device__ __forceinline__ uint4 pack(const float2 (&p)[4]) {
+        uint4 raw;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(p[i].x, p[i].y);
+        return raw;
+    }
+};
+template <> struct HcPairs<float> {
+    static constexpr int NP = 2;
+    static __device__ __forceinline__ void unpack(const uint4& raw, float2 (&p)[2]) {
+        p[0] = make_float2(__uint_as_float(raw.x), __uint_as_float(raw.y));
+        p[1] = make_float2(__uint_as_float(raw.z), __uint_as_float(raw.w));
+    }
+    static __device__ __forceinline__ uint4 pack(const float2 (&p)[2]) {
+        return make_uint4(__float_as_uint(p[0].x), __float_as_uint(p[0].y), __float_as_uint(p[1].x), __float_as_uint(p[1].y));
+    }
+};
+__device__ __forceinline__ uint4 hc_ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// Forward-only exact GELU of a pair (vk_gelu with the polynomial packed; one MUFU.EX2 per element)
+__device__ __forceinline__ float2 hc_gelu2(float2 x) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 a = make_float2(fminf(ax.x, 9.f), fminf(ax.y, 9.f));
+    float2 q = vk_fma2(a, vk_splat2(-3.159132926264e-05f), vk_splat2(7.531542511152e-04f));
+    q = vk_fma2(q, a, vk_splat2(-8.015595779370e-03f));
+    q = vk_fma2(q, a, vk_splat2(5.328616913828e-02f));
+    q = vk_fma2(q, a, vk_splat2(4.588905654064e-01f));
+    q = vk_fma2(q, a, vk_splat2(1.151150930355e+00f));
+    q = vk_fma2(q, a, vk_splat2(1.f));
+    const float2 e = make_float2(vk_ex2(-q.x), vk_ex2(-q.y));
+    return vk_fma2(make_float2(-ax.x, -ax.y), e, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+
+// Sum N (power of two, <= 8) per-lane values over the warp, keeping half of the values per butterfly round while more
+// than one is left: N - 1 + (5 - log2 N) shuffles instead of 5 N.  On return v[0] of lane L is the total of value
+// L >> (5 - log2 N).
+template <int N>
+__device__ __forceinline__ void hc_reduce_multi(float (&v)[N], int lane) {
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8, "hc_reduce_multi: N");
+    int mask = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1) {
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float keep = upper ? v[i + n / 2] : v[i];
+            const float send = upper ? v[i] : v[i + n / 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+        mask >>= 1;
+    }
+#pragma unroll
+    for (; mask > 0; mask >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], mask);
+}
+
+template <int O> struct HcPow2 { static constexpr int value = O <= 1 ? 1 : (O <= 2 ? 2 : 4); };
+
+// Per-lane pairs of the tail's per-channel parameters (lane owns channels (lane + 32 j) V .. + V of the head).
+template <int NVL, int NP, int O>
+struct TailPar2 {
+    float2 gm[NVL][NP], bt[NVL][NP], w[O][NVL][NP];
+    float bias2;      // b2[o] of the (pixel, o) this lane writes after the projection reduce
+    __device__ __forceinline__ void load(const HeadArgs& hd, int lane) {
+        auto ldc = [&](const float* p, int c) { return c < hd.inner ? __ldg(p + c) : 0.f; };
+#pragma unroll
+        for (int j = 0; j < NVL; ++j)
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const int c = (lane + 32 * j) * NP * 2 + 2 * i;
+                gm[j][i] = make_float2(ldc(hd.gamma, c), ldc(hd.gamma, c + 1));
+                bt[j][i] = make_float2(ldc(hd.beta, c), ldc(hd.beta, c + 1));
+#pragma unroll
+                for (int o = 0; o < O; ++o)
+                    w[o][j][i] = make_float2(ldc(hd.w2 + (long long)o * hd.inner, c), ldc(hd.w2 + (long long)o * hd.inner, c + 1));
+            }
+        constexpr int OP = HcPow2<O>::value;
+        constexpr int NV = 2 * OP;                    // values of the projection reduce: (pixel, o)
+        const int idx = lane / (32 / NV);
+        const int o = idx % OP;
+        bias2 = o < O ? __ldg(hd.b2 + o) : 0.f;
+    }
+};
+
+// LayerNorm -> GELU -> projection (-> Softplus) of TWO pixels whose `inner` conv outputs sit across the warp in c0 / c1
+// (pad channels hold exact zeros); results to out0[o * ostride] / out1[o * ostride].
+template <int NVL, int NP, int O>
+__device__ __forceinline__ void hc_tail2(const float2 (&c0)[NVL][NP], const float2 (&c1)[NVL][NP], const TailPar2<NVL, NP, O>& tp,
+                                         int lane, int inner, int softplus, float* out0, float* out1, long long ostride) {
+    const float x0 = __shfl_sync(0xffffffffu, c0[0][0].x, 0);
+    const float x1 = __shfl_sync(0xffffffffu, c1[0][0].x, 0);
+    const float2 n0 = vk_splat2(-x0), n1 = vk_splat2(-x1);
+    float2 s0 = make_float2(0.f, 0.f), q0 = s0, s1 = s0, q1 = s0;
+#pragma unroll
+    for (int j = 0; j < NVL; ++j)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const float2 d0 = vk_add2(c0[j][i], n0), d1 = vk_add2(c1[j][i], n1);
+            s0 = vk_add2(s0, d0);
+            q0 = vk_fma2(d0, d0, q0);
+            s1 = vk_add2(s1, d1);
+            q1 = vk_fma2(d1, d1, q1);
+        }
+    float st[4] = {s0.x + s0.y, q0.x + q0.y, s1.x + s1.y, q1.x + q1.y};
+    hc_reduce_multi<4>(st, lane);
+    const float sA = __shfl_sync(0xffffffffu, st[0], 0), qA = __shfl_sync(0xffffffffu, st[0], 8);
+    const float sB = __shfl_sync(0xffffffffu, st[0], 16), qB = __shfl_sync(0xffffffffu, st[0], 24);
+    const int npad = NVL * 32 * NP * 2 - inner;
+    const float inv = 1.f / (float)inner;
+    const float mA = (sA + (float)npad * x0) * inv, mB = (sB + (float)npad * x1) * inv;          // mean - x0
+    const float vA = fmaf(-mA, mA, (qA - (float)npad * x0 * x0) * inv), vB = fmaf(-mB, mB, (qB - (float)npad * x1 * x1) * inv);
+    const float rA = rsqrtf(fmaxf(vA, 0.f) + LN_EPS), rB = rsqrtf(fmaxf(vB, 0.f) + LN_EPS);
+    const float2 rs0 = vk_splat2(rA), sh0 = vk_splat2(-(x0 + mA) * rA), rs1 = vk_splat2(rB), sh1 = vk_splat2(-(x1 + mB) * rB);
+    constexpr int OP = HcPow2<O>::value;
+    float2 d0[O], d1[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) d0[o] = d1[o] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NVL; ++j)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            // pad channels: gamma = beta = 0 -> gelu(0) = 0
+            const float2 g0 = hc_gelu2(vk_fma2(vk_fma2(c0[j][i], rs0, sh0), tp.gm[j][i], tp.bt[j][i]));
+            const float2 g1 = hc_gelu2(vk_fma2(vk_fma2(c1[j][i], rs1, sh1), tp.gm[j][i], tp.bt[j][i]));
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+                d0[o] = vk_fma2(g0, tp.w[o][j][i], d0[o]);
+                d1[o] = vk_fma2(g1, tp.w[o][j][i], d1[o]);
+            }
+        }
+    float dv[2 * OP];
+#pragma unroll
+    for (int o = 0; o < OP; ++o) {
+        dv[o] = o < O ? d0[o < O ? o : 0].x + d0[o < O ? o : 0].y : 0.f;
+        dv[OP + o] = o < O ? d1[o < O ? o : 0].x + d1[o < O ? o : 0].y : 0.f;
+    }
+    hc_reduce_multi<2 * OP>(dv, lane);
+    constexpr int GROUP = 32 / (2 * OP);
+    if ((lane & (GROUP - 1)) == 0) {
+        const int idx = lane / GROUP;
+        const int o = idx % OP;
+        if (o < O) {
+            float v = dv[0] + tp.bias2;
+            if (softplus) v = vk_softplus(v);
+            ((idx / OP) ? out1 : out0)[(long long)o * ostride] = v;
+        }
+    }
+}
+
 template <typename T, int NVL, int O>
 __global__ void __launch_bounds__(256, 2)
 hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ conv, long long ld_conv, int cw, int tiles_j,
                   int tiles_i, long long ntiles) {
     constexpr int V = VkVec<T>::N;
+    constexpr int NP = HcPairs<T>::NP;
     extern __shared__ float4 hc_smem4[];
-    float* sV = reinterpret_cast<float*>(hc_smem4);                          // [R][2][3][QL][cw]
-    float2* sWr = reinterpret_cast<float2*>(sV + HC_R * 2 * 3 * HC_QL * cw);   // [R][2][3] row-pair weights
-    float2* sWc = sWr + HC_R * 2 * 3;                                         // [TJ][2][3] column-pair weights
+    float* sV = reinterpret_cast<float*>(hc_smem4);                           // [R][2][3][QL][cw]
+    float* sBias = sV + HC_R * 2 * 3 * HC_QL * cw;                            // [cw] conv bias in plane order
+    float2* sWr = reinterpret_cast<float2*>(sBias + cw);                      // [R][2][3][2] row weights, splatted
+    float2* sWc = sWr + HC_R * 2 * 3 * 2;                                     // [TJ][2][3] column-pair weights (wA, wB)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    TailPar<NVL, V, O> tp;
-    tp.load(hd, lane);
     const int cvn = cw / V;                            // channel vectors that hold real channels
+    TailPar2<NVL, NP, O> tp;
+    tp.load(hd, lane);
+    for (int c = threadIdx.x; c < cw; c += blockDim.x)
+        sBias[hc_plane(c / V, c % V, cvn) + (c & 3)] = c < hd.inner ? __ldg(hd.bias + c) : 0.f;
     const long long ppi = (long long)g.H * g.W;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int jt = (int)(tile % tiles_j);
@@ -345,7 +509,9 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
         const int i0 = it * HC_R, j0 = jt * HC_TJ;
         if (threadIdx.x < HC_R * 2 * 3) {
             const int d = threadIdx.x % 3, a = (threadIdx.x / 3) & 1, li = threadIdx.x / 6;
-            sWr[threadIdx.x] = (i0 + li < g.h) ? hc_pair_weights(i0 + li, a, d, g.h, g.mode) : make_float2(0.f, 0.f);
+            const float2 wv = (i0 + li < g.h) ? hc_pair_weights(i0 + li, a, d, g.h, g.mode) : make_float2(0.f, 0.f);
+            sWr[2 * threadIdx.x] = vk_splat2(wv.x);
+            sWr[2 * threadIdx.x + 1] = vk_splat2(wv.y);
         } else if (threadIdx.x >= 32 && threadIdx.x < 32 + HC_TJ * 2 * 3) {
             const int t = threadIdx.x - 32;
             const int d = t % 3, b2 = (t / 3) & 1, jl = t / 6;
@@ -353,132 +519,156 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
         }
         __syncthreads();
         // ---------------- phase 1: V[li][a][dx][ql][c] = sum_dy (wA Z_{dy,dx}[rowA, q, c] + wB Z_{dy,dx}[rowB, q, c])
-        int rk[HC_R + 2];
+        {
+            long long rowoff[HC_R + 2];
 #pragma unroll
-        for (int k = 0; k < HC_R + 2; ++k) {
-            const int rr = i0 - 1 + k;
-            rk[k] = rr < 0 ? 0 : (rr > g.h - 1 ? g.h - 1 : rr);
+            for (int k = 0; k < HC_R + 2; ++k) {
+                int rr = i0 - 1 + k;
+                rr = rr < 0 ? 0 : (rr > g.h - 1 ? g.h - 1 : rr);
+                rowoff[k] = (long long)rr * g.w * g.ld_z;
+            }
+            const T* zb = z + (long long)b * g.h * g.w * g.ld_z + hd.col0;
+            const int items = HC_QL * 3 * cvn;
+            for (int item = threadIdx.x; item < items; item += blockDim.x) {
+                const int cv = item % cvn;
+                const int t3 = item / cvn;
+                const int dx = t3 % 3;
+                const int ql = t3 / 3;
+                int q = j0 - 1 + ql;
+                q = q < 0 ? 0 : (q > g.w - 1 ? g.w - 1 : q);
+                const T* zq = zb + (long long)q * g.ld_z + dx * g.ntot + cv * V;
+                // all loads first (10 of the 12 (tap row, source row) combinations are read)
+                uint4 raw[3][HC_R + 2];
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int k = 0; k < HC_R + 2; ++k) {
+                        bool used = false;
+#pragma unroll
+                        for (int li = 0; li < HC_R; ++li)
+#pragma unroll
+                            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk)
+                                    if (hc_pos(a, d, kk) == k - 1 - li) used = true;
+                        if (used) raw[d][k] = hc_ldg16(zq + rowoff[k] + (long long)(d * 3) * g.ntot);
+                    }
+                float2 acc[HC_R][2][NP];
+#pragma unroll
+                for (int li = 0; li < HC_R; ++li)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int e = 0; e < NP; ++e) acc[li][a][e] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int k = 0; k < HC_R + 2; ++k) {
+                        bool used = false;
+#pragma unroll
+                        for (int li = 0; li < HC_R; ++li)
+#pragma unroll
+                            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk)
+                                    if (hc_pos(a, d, kk) == k - 1 - li) used = true;
+                        if (!used) continue;
+                        float2 f[NP];
+                        HcPairs<T>::unpack(raw[d][k], f);
+#pragma unroll
+                        for (int li = 0; li < HC_R; ++li)
+#pragma unroll
+                            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk)
+                                    if (hc_pos(a, d, kk) == k - 1 - li) {
+                                        const float2 wgt = sWr[((li * 2 + a) * 3 + d) * 2 + kk];
+#pragma unroll
+                                        for (int e = 0; e < NP; ++e) acc[li][a][e] = vk_fma2(wgt, f[e], acc[li][a][e]);
+                                    }
+                    }
+#pragma unroll
+                for (int li = 0; li < HC_R; ++li)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        float* dst = sV + ((((li * 2 + a) * 3 + dx) * HC_QL + ql)) * cw;
+#pragma unroll
+                        for (int e = 0; e < NP; e += 2)
+                            *reinterpret_cast<float4*>(dst + hc_plane(cv, 2 * e, cvn)) =
+                                make_float4(acc[li][a][e].x, acc[li][a][e].y, acc[li][a][e + 1].x, acc[li][a][e + 1].y);
+                    }
+            }
         }
-        const T* zb = z + (long long)b * g.h * g.w * g.ld_z + hd.col0;
-        const int items = HC_QL * 3 * cvn;
-        for (int item = threadIdx.x; item < items; item += blockDim.x) {
-            const int cv = item % cvn;
-            const int t3 = item / cvn;
-            const int dx = t3 % 3;
-            const int ql = t3 / 3;
-            int q = j0 - 1 + ql;
-            q = q < 0 ? 0 : (q > g.w - 1 ? g.w - 1 : q);
-            float acc[HC_R][2][V];
+        __syncthreads();
+        // ---------------- phase 2: one warp per (row, low-res column): its two output pixels (column parity 0 / 1) together
+        for (int unit = warp; unit < HC_R * 2 * HC_TJ; unit += (blockDim.x >> 5)) {
+            const int jl = unit % HC_TJ;
+            const int la = unit / HC_TJ;               // li * 2 + a
+            const int i = i0 + (la >> 1), j = j0 + jl;
+            if (i >= g.h || j >= g.w) continue;
+            int qm = j - 1, qp = j + 1;
+            qm = qm < 0 ? 0 : qm;
+            qp = qp > g.w - 1 ? g.w - 1 : qp;
+            const int col[3] = {qm - (j0 - 1), jl + 1, qp - (j0 - 1)};
+            float2 c0[NVL][NP], c1[NVL][NP];
 #pragma unroll
-            for (int li = 0; li < HC_R; ++li)
+            for (int jj = 0; jj < NVL; ++jj) {
+                const int cvi = lane + 32 * jj;
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
-#pragma unroll
-                    for (int e = 0; e < V; ++e) acc[li][a][e] = 0.f;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const T* zt = zb + (long long)(d * 3 + dx) * g.ntot + cv * V;
-#pragma unroll
-                for (int k = 0; k < HC_R + 2; ++k) {
-                    // which accumulators read source row k (offset k - 1 - li from output row li)?  (compile-time)
-                    bool used = false;
-#pragma unroll
-                    for (int li = 0; li < HC_R; ++li)
-#pragma unroll
-                        for (int a = 0; a < 2; ++a)
-#pragma unroll
-                            for (int kk = 0; kk < 2; ++kk)
-                                if (hc_pos(a, d, kk) == k - 1 - li) used = true;
-                    if (!used) continue;
-                    VkVec<T> v;
-                    v.load(zt + ((long long)rk[k] * g.w + q) * g.ld_z);
-                    float f[V];
-                    v.unpack(f);
-#pragma unroll
-                    for (int li = 0; li < HC_R; ++li)
-#pragma unroll
-                        for (int a = 0; a < 2; ++a)
-#pragma unroll
-                            for (int kk = 0; kk < 2; ++kk)
-                                if (hc_pos(a, d, kk) == k - 1 - li) {
-                                    const float2 w2 = sWr[(li * 2 + a) * 3 + d];
-                                    const float wgt = kk ? w2.y : w2.x;
-#pragma unroll
-                                    for (int e = 0; e < V; ++e) acc[li][a][e] = fmaf(wgt, f[e], acc[li][a][e]);
-                                }
+                for (int e = 0; e < NP; e += 2) {
+                    const float4 bv = cvi < cvn ? *reinterpret_cast<const float4*>(sBias + hc_plane(cvi, 2 * e, cvn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    c0[jj][e] = c1[jj][e] = make_float2(bv.x, bv.y);
+                    c0[jj][e + 1] = c1[jj][e + 1] = make_float2(bv.z, bv.w);
                 }
             }
 #pragma unroll
-            for (int li = 0; li < HC_R; ++li)
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    float* dst = sV + ((long long)(((li * 2 + a) * 3 + dx) * HC_QL + ql)) * cw;
-#pragma unroll
-                    for (int e = 0; e < V; e += 4)
-                        *reinterpret_cast<float4*>(dst + hc_plane(cv, e, cvn)) =
-                            make_float4(acc[li][a][e], acc[li][a][e + 1], acc[li][a][e + 2], acc[li][a][e + 3]);
-                }
-        }
-        __syncthreads();
-        // ---------------- phase 2: one warp per output pixel: combine the three tap columns, then the head tail
-        for (int pi = warp; pi < HC_R * 2 * HC_TJ * 2; pi += (blockDim.x >> 5)) {
-            const int b2 = pi & 1;
-            const int jl = (pi >> 1) % HC_TJ;
-            const int la = (pi >> 1) / HC_TJ;          // li * 2 + a
-            const int li = la >> 1, a = la & 1;
-            const int i = i0 + li, j = j0 + jl;
-            if (i >= g.h || j >= g.w) continue;
-            float c[NVL][V];
-#pragma unroll
-            for (int jj = 0; jj < NVL; ++jj)
-#pragma unroll
-                for (int e = 0; e < V; ++e) c[jj][e] = tp.cb[jj][e];
-#pragma unroll
             for (int d = 0; d < 3; ++d) {
-                const float2 wc = sWc[(jl * 2 + b2) * 3 + d];
+                const float2 w0 = sWc[(jl * 2 + 0) * 3 + d], w1 = sWc[(jl * 2 + 1) * 3 + d];
+                const float* base = sV + ((la * 3 + d) * HC_QL) * cw;
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const float wgt = kk ? wc.y : wc.x;
-                    int q = j + hc_pos(b2, d, kk);
-                    q = q < 0 ? 0 : (q > g.w - 1 ? g.w - 1 : q);
-                    const int ql = q - (j0 - 1);
-                    const float* src = sV + ((long long)((la * 3 + d) * HC_QL + ql)) * cw;
+                for (int pp = 0; pp < 3; ++pp) {       // column offsets -1, 0, +1
+                    // which of the two pixels read this column for tap d?  (compile-time)
+                    float u0 = 0.f, u1 = 0.f;
+                    bool r0 = false, r1 = false;
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        if (hc_pos(0, d, kk) == pp - 1) { r0 = true; u0 = kk ? w0.y : w0.x; }
+                        if (hc_pos(1, d, kk) == pp - 1) { r1 = true; u1 = kk ? w1.y : w1.x; }
+                    }
+                    if (!r0 && !r1) continue;
+                    const float2 u02 = vk_splat2(u0), u12 = vk_splat2(u1);
+                    const float* src = base + col[pp] * cw;
 #pragma unroll
                     for (int jj = 0; jj < NVL; ++jj) {
                         const int cvi = lane + 32 * jj;
                         if (cvi < cvn) {
 #pragma unroll
-                            for (int e = 0; e < V; e += 4) {
-                                const float4 v = *reinterpret_cast<const float4*>(src + hc_plane(cvi, e, cvn));
-                                c[jj][e] = fmaf(wgt, v.x, c[jj][e]);
-                                c[jj][e + 1] = fmaf(wgt, v.y, c[jj][e + 1]);
-                                c[jj][e + 2] = fmaf(wgt, v.z, c[jj][e + 2]);
-                                c[jj][e + 3] = fmaf(wgt, v.w, c[jj][e + 3]);
+                            for (int e = 0; e < NP; e += 2) {
+                                const float4 v = *reinterpret_cast<const float4*>(src + hc_plane(cvi, 2 * e, cvn));
+                                const float2 va = make_float2(v.x, v.y), vb = make_float2(v.z, v.w);
+                                if (r0) { c0[jj][e] = vk_fma2(u02, va, c0[jj][e]); c0[jj][e + 1] = vk_fma2(u02, vb, c0[jj][e + 1]); }
+                                if (r1) { c1[jj][e] = vk_fma2(u12, va, c1[jj][e]); c1[jj][e + 1] = vk_fma2(u12, vb, c1[jj][e + 1]); }
                             }
                         }
                     }
                 }
             }
-#pragma unroll
-            for (int jj = 0; jj < NVL; ++jj)
-#pragma unroll
-                for (int e = 0; e < V; ++e)
-                    if ((lane + 32 * jj) * V + e >= hd.inner) c[jj][e] = 0.f;
-            const int y = 2 * i + a, x = 2 * j + b2;
+            // pad channels of the last vector: the weights' pad rows are zero, so Z and the bias are zero there already
+            const int y = 2 * i + (la & 1), x = 2 * j;
             const long long rem = (long long)y * g.W + x;
             if (conv) {
                 T* cr = conv + ((long long)b * ppi + rem) * ld_conv + hd.col0;
 #pragma unroll
                 for (int jj = 0; jj < NVL; ++jj) {
-                    const int c0 = (lane + 32 * jj) * V;
-                    if (c0 < hd.inner) {
-                        VkVec<T> vo;
-                        vo.pack(c[jj]);
-                        vo.store(cr + c0);
+                    const int ch0 = (lane + 32 * jj) * V;
+                    if (ch0 < hd.inner) {
+                        *reinterpret_cast<uint4*>(cr + ch0) = HcPairs<T>::pack(c0[jj]);
+                        *reinterpret_cast<uint4*>(cr + ld_conv + ch0) = HcPairs<T>::pack(c1[jj]);
                     }
                 }
             }
-            hc_tail<NVL, V, O>(c, tp, lane, hd.inner, hd.softplus, hd.out + (long long)b * O * ppi + rem, ppi);
+            float* o0 = hd.out + (long long)b * O * ppi + rem;
+            hc_tail2<NVL, NP, O>(c0, c1, tp, lane, hd.inner, hd.softplus, o0, o0 + 1, ppi);
         }
         __syncthreads();
     }
@@ -487,40 +677,69 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
 // ------------------------------------------------------------------------------------------------ factor 2, 3x3: adjoint
 // dZ_{dy,dx}[p, q] = sum_{o, o'} R[2p-1+o, p] C[2q-1+o', q] dconv[2p - dy + o, 2q - dx + o'],  o, o' in 0..3 (the four
 // up-sampled rows / columns whose interpolation reads source p / q), terms outside the grids dropped.  Separable: a block
-// first reduces the rows of a dconv tile to E[pl][dy][column] in shared memory, then every (pixel, tap) combines four E's.
-constexpr int HB_TQ = 6;                 // low-res columns per tile  -> 2 (TQ + 2) = 16 hi-res columns of dconv
+// first reduces the rows of a dconv tile to E[pl][dy][column] in shared memory (one thread per (column, channel vector),
+// its eight rows prefetched into registers while the previous tile is finished), then one thread per (pixel, channel
+// vector) combines six E columns into the nine taps.
+constexpr int HB_TQ = 8;                 // low-res columns per tile  -> 2 (TQ + 2) = 20 hi-res columns of dconv
 constexpr int HB_R = 2;                  // low-res rows per tile     -> 2 (R + 2)  =  8 hi-res rows of dconv
-constexpr int HB_SL = 2 * (HB_TQ + 2);   // 16
+constexpr int HB_SL = 2 * (HB_TQ + 2);   // 20
+constexpr int HB_ROWS = 2 * (HB_R + 2);  // 8
 constexpr int HB_CVL = 16;               // channel vectors per chunk
+constexpr int HB_THREADS = HB_SL * HB_CVL;   // 320: phase 1 uses all, phase 2 the first R * TQ * CVL = 256
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(HB_THREADS, 2)
 hc_bwd_2x3_kernel(const T* __restrict__ dc, long long ld_dc, Geom g, int width, T* __restrict__ dz, int tiles_q, int tiles_p,
                   int chunks, long long nwork) {
     constexpr int V = VkVec<T>::N;
+    constexpr int NP = HcPairs<T>::NP;
     constexpr int CH = HB_CVL * V;
     extern __shared__ float4 hc_smem4[];
     float* sE = reinterpret_cast<float*>(hc_smem4);            // [R][3][SL][CH]
     float* cE = sE + HB_R * 3 * HB_SL * CH;                     // [R][3][4] row coefficients
     float* cC = cE + HB_R * 3 * 4;                              // [TQ][3][4] column coefficients
-    for (long long work = blockIdx.x; work < nwork; work += gridDim.x) {
+    const int sl = threadIdx.x / HB_CVL, cvl = threadIdx.x % HB_CVL;
+    struct Work { int b, p0, q0, c0; };
+    auto decode = [&](long long work) {
+        Work wk;
         const int ch = (int)(work % chunks);
         long long t2 = work / chunks;
         const int qt = (int)(t2 % tiles_q);
         t2 /= tiles_q;
         const int pt = (int)(t2 % tiles_p);
-        const int b = (int)(t2 / tiles_p);
-        const int p0 = pt * HB_R, q0 = qt * HB_TQ, c0 = ch * CH;
+        wk.b = (int)(t2 / tiles_p);
+        wk.p0 = pt * HB_R; wk.q0 = qt * HB_TQ; wk.c0 = ch * CH;
+        return wk;
+    };
+    uint4 raw[HB_ROWS];
+    auto prefetch = [&](const Work& wk) {
+        const int s = 2 * (wk.q0 - 1) + sl;
+        const int c = wk.c0 + cvl * V;
+        const bool ok = s >= 0 && s < g.W && c < width;
+        const T* db = dc + ((long long)wk.b * g.H * g.W + (ok ? s : 0)) * ld_dc + (ok ? c : 0);
+#pragma unroll
+        for (int rr = 0; rr < HB_ROWS; ++rr) {
+            const int r = 2 * (wk.p0 - 1) + rr;
+            raw[rr] = (ok && r >= 0 && r < g.H) ? hc_ldg16(db + (long long)r * g.W * ld_dc) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    long long work = blockIdx.x;
+    Work wk{0, 0, 0, 0};
+    if (work < nwork) {
+        wk = decode(work);
+        prefetch(wk);
+    }
+    for (; work < nwork; work += gridDim.x) {
         if (threadIdx.x < HB_R * 3 * 4) {
             const int o = threadIdx.x & 3, dy = (threadIdx.x >> 2) % 3, pl = threadIdx.x / 12;
-            const int p = p0 + pl, Y = 2 * p - 1 + o, yy = Y - dy + 1;
+            const int p = wk.p0 + pl, Y = 2 * p - 1 + o, yy = Y - dy + 1;
             float cf = 0.f;
             if (p < g.h && Y >= 0 && Y < g.H && yy >= 0 && yy < g.H) cf = hc_weight_of(Y, p, g.h, g.H, g.mode);
             cE[threadIdx.x] = cf;
         } else if (threadIdx.x >= 32 && threadIdx.x < 32 + HB_TQ * 3 * 4) {
             const int t = threadIdx.x - 32;
             const int o = t & 3, dx = (t >> 2) % 3, ql = t / 12;
-            const int q = q0 + ql, X = 2 * q - 1 + o, xx = X - dx + 1;
+            const int q = wk.q0 + ql, X = 2 * q - 1 + o, xx = X - dx + 1;
             float cf = 0.f;
             if (q < g.w && X >= 0 && X < g.W && xx >= 0 && xx < g.W) cf = hc_weight_of(X, q, g.w, g.W, g.mode);
             cC[t] = cf;
@@ -528,81 +747,84 @@ hc_bwd_2x3_kernel(const T* __restrict__ dc, long long ld_dc, Geom g, int width, 
         __syncthreads();
         // ---------------- phase 1: E[pl][dy][sl][c] = sum_o cE[pl][dy][o] dconv[2 p - dy + o, s, c]
         {
-            const int sl = threadIdx.x / HB_CVL, cvl = threadIdx.x % HB_CVL;
-            const int s = 2 * (q0 - 1) + sl;
-            const int c = c0 + cvl * V;
-            float acc[HB_R][3][V];
+            float2 acc[HB_R][3][NP];
 #pragma unroll
             for (int pl = 0; pl < HB_R; ++pl)
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
 #pragma unroll
-                    for (int e = 0; e < V; ++e) acc[pl][d][e] = 0.f;
-            if (s >= 0 && s < g.W && c < width) {
-                const T* db = dc + ((long long)b * g.H * g.W + s) * ld_dc + c;
+                    for (int e = 0; e < NP; ++e) acc[pl][d][e] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int rr = 0; rr < 2 * (HB_R + 2); ++rr) {
-                    const int r = 2 * (p0 - 1) + rr;
-                    if (r < 0 || r >= g.H) continue;
-                    VkVec<T> v;
-                    v.load(db + (long long)r * g.W * ld_dc);
-                    float f[V];
-                    v.unpack(f);
+            for (int rr = 0; rr < HB_ROWS; ++rr) {
+                float2 f[NP];
+                HcPairs<T>::unpack(raw[rr], f);
 #pragma unroll
-                    for (int pl = 0; pl < HB_R; ++pl)
+                for (int pl = 0; pl < HB_R; ++pl)
 #pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            const int o = rr - 2 * pl - (2 - d);    // r = 2 p - d + o
-                            if (o >= 0 && o < 4) {
-                                const float cf = cE[(pl * 3 + d) * 4 + o];
+                    for (int d = 0; d < 3; ++d) {
+                        const int o = rr - 2 * pl - (2 - d);    // r = 2 p - d + o
+                        if (o >= 0 && o < 4) {
+                            const float2 cf = vk_splat2(cE[(pl * 3 + d) * 4 + o]);
 #pragma unroll
-                                for (int e = 0; e < V; ++e) acc[pl][d][e] = fmaf(cf, f[e], acc[pl][d][e]);
-                            }
+                            for (int e = 0; e < NP; ++e) acc[pl][d][e] = vk_fma2(cf, f[e], acc[pl][d][e]);
                         }
-                }
+                    }
             }
 #pragma unroll
             for (int pl = 0; pl < HB_R; ++pl)
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    float* dst = sE + ((long long)((pl * 3 + d) * HB_SL + sl)) * CH;
+                    float* dst = sE + ((pl * 3 + d) * HB_SL + sl) * CH;
 #pragma unroll
-                    for (int e = 0; e < V; e += 4)
-                        *reinterpret_cast<float4*>(dst + hc_plane(cvl, e, HB_CVL)) =
-                            make_float4(acc[pl][d][e], acc[pl][d][e + 1], acc[pl][d][e + 2], acc[pl][d][e + 3]);
+                    for (int e = 0; e < NP; e += 2)
+                        *reinterpret_cast<float4*>(dst + hc_plane(cvl, 2 * e, HB_CVL)) =
+                            make_float4(acc[pl][d][e].x, acc[pl][d][e].y, acc[pl][d][e + 1].x, acc[pl][d][e + 1].y);
                 }
         }
         __syncthreads();
+        // the next tile's rows travel while this tile's taps are combined and stored
+        const Work cur = wk;
+        if (work + gridDim.x < nwork) {
+            wk = decode(work + gridDim.x);
+            prefetch(wk);
+        }
         // ---------------- phase 2: dZ_{dy,dx}[p, q, c] = sum_o cC[ql][dx][o] E[pl][dy][2 ql + 2 - dx + o][c]
-        for (int item = threadIdx.x; item < HB_R * HB_TQ * 9 * HB_CVL; item += blockDim.x) {
-            const int cvl = item % HB_CVL;
-            int t3 = item / HB_CVL;
-            const int tap = t3 % 9;
-            t3 /= 9;
-            const int ql = t3 % HB_TQ;
-            const int pl = t3 / HB_TQ;
-            const int p = p0 + pl, q = q0 + ql, c = c0 + cvl * V;
-            if (p >= g.h || q >= g.w || c >= width) continue;
-            const int dy = tap / 3, dx = tap - dy * 3;
-            float acc[V];
+        if (threadIdx.x < HB_R * HB_TQ * HB_CVL) {
+            const int pix = threadIdx.x / HB_CVL;
+            const int pl = pix / HB_TQ, ql = pix % HB_TQ;
+            const int p = cur.p0 + pl, q = cur.q0 + ql, c = cur.c0 + cvl * V;
+            if (p < g.h && q < g.w && c < width) {
+                float2 cf[3][4];
 #pragma unroll
-            for (int e = 0; e < V; ++e) acc[e] = 0.f;
+                for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const float cf = cC[(ql * 3 + dx) * 4 + o];
-                const float* src = sE + ((long long)((pl * 3 + dy) * HB_SL + 2 * ql + 2 - dx + o)) * CH;
+                    for (int o = 0; o < 4; ++o) cf[dx][o] = vk_splat2(cC[(ql * 3 + dx) * 4 + o]);
+                T* dst = dz + (((long long)cur.b * g.h + p) * g.w + q) * g.ld_z + c;
 #pragma unroll
-                for (int e = 0; e < V; e += 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(src + hc_plane(cvl, e, HB_CVL));
-                    acc[e] = fmaf(cf, v.x, acc[e]);
-                    acc[e + 1] = fmaf(cf, v.y, acc[e + 1]);
-                    acc[e + 2] = fmaf(cf, v.z, acc[e + 2]);
-                    acc[e + 3] = fmaf(cf, v.w, acc[e + 3]);
+                for (int dy = 0; dy < 3; ++dy) {
+                    float2 ev[6][NP];
+                    const float* src = sE + ((pl * 3 + dy) * HB_SL + 2 * ql) * CH;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+#pragma unroll
+                        for (int e = 0; e < NP; e += 2) {
+                            const float4 v = *reinterpret_cast<const float4*>(src + k * CH + hc_plane(cvl, 2 * e, HB_CVL));
+                            ev[k][e] = make_float2(v.x, v.y);
+                            ev[k][e + 1] = make_float2(v.z, v.w);
+                        }
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        float2 acc[NP];
+#pragma unroll
+                        for (int e = 0; e < NP; ++e) acc[e] = vk_mul2(cf[dx][0], ev[2 - dx][e]);
+#pragma unroll
+                        for (int o = 1; o < 4; ++o)
+#pragma unroll
+                            for (int e = 0; e < NP; ++e) acc[e] = vk_fma2(cf[dx][o], ev[2 - dx + o][e], acc[e]);
+                        *reinterpret_cast<uint4*>(dst + (long long)(dy * 3 + dx) * g.ntot) = HcPairs<T>::pack(acc);
+                    }
                 }
             }
-            VkVec<T> ov;
-            ov.pack(acc);
-            ov.store(dz + (((long long)b * g.h + p) * g.w + q) * g.ld_z + (long long)tap * g.ntot + c);
         }
         __syncthreads();
     }
@@ -617,7 +839,7 @@ int hc_launch_fwd(const void* z, const Geom& g, const HeadArgs& hd, void* conv, 
     if (fast) {
         const int cvn = (hd.inner + V - 1) / V;
         const int cw = cvn * V;
-        const size_t smem = (size_t)HC_R * 2 * 3 * HC_QL * cw * sizeof(float) + (HC_R * 2 * 3 + HC_TJ * 2 * 3) * sizeof(float2);
+        const size_t smem = ((size_t)HC_R * 2 * 3 * HC_QL * cw + cw) * sizeof(float) + (HC_R * 2 * 3 * 2 + HC_TJ * 2 * 3) * sizeof(float2);
         if (smem <= 200 * 1024) {
             const int tiles_j = vk_cdiv(g.w, HC_TJ), tiles_i = vk_cdiv(g.h, HC_R);
             const long long ntiles = (long long)g.B * tiles_i * tiles_j;
@@ -725,13 +947,13 @@ int vkocr_head_combine_bwd(int dtype, const void* dconv, long long ld_dc, int B,
         const int tiles_q = vk_cdiv(w, HB_TQ), tiles_p = vk_cdiv(h, HB_R), chunks = vk_cdiv(width, CH);
         const long long nwork = (long long)B * tiles_p * tiles_q * chunks;
         const size_t smem = ((size_t)HB_R * 3 * HB_SL * CH + HB_R * 3 * 4 + HB_TQ * 3 * 4) * sizeof(float);
-        long long blocks = (long long)vkocr_sm_count() * 4;
+        long long blocks = (long long)vkocr_sm_count() * 2;
         if (blocks > nwork) blocks = nwork;
 #define VK_HC_BWD(T)                                                                                                             \
     do {                                                                                                                         \
         cudaError_t e = cudaFuncSetAttribute(hc_bwd_2x3_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "head_combine_bwd: smem %zu: %s", smem, cudaGetErrorString(e));           \
-        hc_bwd_2x3_kernel<T><<<(unsigned)blocks, 256, smem, s>>>(reinterpret_cast<const T*>(dconv), ld_dc, g, width,             \
+        hc_bwd_2x3_kernel<T><<<(unsigned)blocks, HB_THREADS, smem, s>>>(reinterpret_cast<const T*>(dconv), ld_dc, g, width,             \
                                                                  reinterpret_cast<T*>(dz), tiles_q, tiles_p, chunks, nwork);     \
     } while (0)
         if (dtype == VKOCR_BF16) VK_HC_BWD(__nv_bfloat16);
