@@ -13,9 +13,12 @@ with torchrun (one rank per GPU, NCCL); the gradient all-reduce is bucketed and 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event timed, max over ranks.  `e2e`: the same step
 through the public API from pinned HOST buffers (per step one H2D copy of both batches, issued on a copy stream one step
 ahead like a training input pipeline, and a D2H read of both losses; all inside the timed region).
-`roofline`: the dominant kernel (the tcgen05 implicit-GEMM 3x3 convolution of the precise head group), algorithmic
-FLOPs / CUDA-event duration measured inside the timed region, against MEASURED_PEAKS.json.  `cpu_baseline`: the oracle
-(port of the reference algorithm, plain fp32 PyTorch) on the host cores over a bounded sample.
+`roofline`: the C-ABI call with the largest share of the timed region (every call is bracketed with CUDA events), its
+ALGORITHMIC FLOPs or bytes over the measured duration against MEASURED_PEAKS.json (tensor peak for the tcgen05 GEMMs, HBM
+bandwidth for the streaming kernels).  `cpu_baseline`: the oracle (port of the reference algorithm, plain fp32 PyTorch) on
+the host cores over a bounded sample.  `gpu_eager_baseline`: the same oracle under stock PyTorch eager on the SAME GPU
+(fp32 TF32-off and autocast bf16).  `extra`: the other BASELINE configurations (FPN neck, ConvNeXt backbone only, 2048^2
+rough inference) and the step with the fused clip + AdamW tail, each timed like `value` with fewer steps.
 """
 import argparse
 import json
@@ -50,6 +53,8 @@ def parse_args():
                     'by CUDA events and write the per-kernel table to gpurun_out/kernel_table_<workload>.json')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the FPN / optimizer / config #2 / config #5 side measurements')
+    ap.add_argument('--no-eager-baseline', action='store_true', help='skip the stock-PyTorch-eager arm on the same GPU')
     return ap.parse_args()
 
 
@@ -181,15 +186,313 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ stock-eager GPU arm
+def gpu_eager_baseline(neck: str, batch: int, size: int, dev, steps: int = 2):
+    """The reference algorithm (the oracle's stock torch ops: cuDNN / cuBLAS / ATen eager) on the SAME B200 and the same
+    step: fp32 with TF32 off (the reference's own arithmetic) and under torch.autocast(bfloat16).  A
+    reported baseline beside the CPU arm; falls back to a smaller batch when the fp32 autograd tape does not fit."""
+    import torch
+    from oracle import loss as ol
+    from oracle import model as om
+    from oracle import synth
+    from vkit_ocr_model_adaptive_scaling_b200.training import PRECISE_KEYS, ROUGH_KEYS
+    out = {'kind': 'port', 'what': 'oracle (reference algorithm, stock PyTorch eager ops) on the same GPU, same step'}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = synth.synth_state_dict('tiny', neck, seed=133)
+        params = {k: v.to(dev).requires_grad_(True) for k, v in sd.items()}
+        for b in (batch, batch // 2, batch // 4):
+            try:
+                rb, pb = make_batches(b, size, 133)
+                to = lambda d: {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+                rb, pb = to(rb), to(pb)
+
+                def step(autocast: bool):
+                    for p in params.values():
+                        p.grad = None
+                    with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+                        m, h = om.forward_rough(params, rb['image'])
+                    (ol.rough_loss(m.float(), h.float(), *(rb[k] for k in ROUGH_KEYS)) / 2).backward()
+                    del m, h
+                    with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+                        outs = om.forward_precise(params, pb['image'])
+                    (ol.precise_loss(None, *(o.float() for o in outs), *(pb[k] for k in PRECISE_KEYS)) / 2).backward()
+
+                for name, autocast in (('fp32', False), ('autocast_bf16', True)):
+                    step(autocast)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        step(autocast)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / steps
+                    out[name] = {'value': b / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'batch': b}
+                break
+            except torch.cuda.OutOfMemoryError:
+                for p in params.values():
+                    p.grad = None
+                torch.cuda.empty_cache()
+                out['note'] = f'batch {b} did not fit beside the fp32 autograd tape; halved'
+    except Exception as exc:   # a baseline must never take the headline number down with it
+        out['error'] = f'{type(exc).__name__}: {exc}'[:300]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm
+class Workload:
+    """One benchmark workload: model, device / pinned-host inputs and the step closure."""
+
+
+def build_workload(vk, workload: str, neck: str, batch: int, size: int, dev, rank: int, world: int, with_optimizer: bool = False):
+    import torch
+    from vkit_ocr_model_adaptive_scaling_b200.parallel import DataParallel
+    from vkit_ocr_model_adaptive_scaling_b200.training import FusedAdamW, batch_to_device, train_step
+    from oracle import synth  # synthetic weights / batches only (test infrastructure generating inputs, never on the timed path)
+    M, LF = vk.model, vk.loss_function
+    w = Workload()
+    cfg = M.AdaptiveScalingConfig(size=M.AdaptiveScalingSize.TINY, neck_head_type=M.AdaptiveScalingNeckHeadType(neck))
+    torch.manual_seed(133)
+    model = M.AdaptiveScaling(cfg)
+    model.load_state_dict(synth.synth_state_dict('tiny', neck, seed=133), strict=True)
+    model.to(dev)
+    rough_fn = LF.AdaptiveScalingRoughLossFunction(LF.AdaptiveScalingRoughLossFunctionConifg())
+    precise_fn = LF.AdaptiveScalingPreciseLossFunction(LF.AdaptiveScalingPreciseLossFunctionConifg())
+    w.model, w.dp = model, None
+    w.rb_host, w.pb_host, w.rb, w.pb, w.h2d = {}, {}, {}, {}, 0
+    if workload != 'infer':
+        rb_host, pb_host = make_batches(batch, size, 133 + rank)
+        pin = lambda d: {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+        w.rb_host, w.pb_host = pin(rb_host), pin(pb_host)
+        w.rb, w.pb = batch_to_device(w.rb_host, dev), batch_to_device(w.pb_host, dev)
+        w.h2d = tensor_bytes(w.rb_host) + tensor_bytes(w.pb_host)
+    if workload == 'train':
+        model.train()   # stochastic depth active, as in the reference loop (train.py:396)
+        # flat gradient buckets also on one GPU: begin_step() zeroes 5 buffers instead of ~300 tensors, and for N > 1 the
+        # bucketed all-reduce overlaps the backward passes
+        dp = DataParallel(model, flatten_params=with_optimizer)
+        w.dp = dp
+        opt = FusedAdamW(dp.buckets, lr=8e-4, weight_decay=0.01, max_grad_norm=2.5) if with_optimizer else None
+
+        def step(rbatch, pbatch):
+            losses = train_step(model, rough_fn, precise_fn, rbatch, pbatch, dp)
+            if opt is not None:     # clip_grad_norm_(2.5) + AdamW (train.py:468-478): outside BASELINE's metric, reported in `extra`
+                opt.step()
+            return losses
+        w.images_per_step = batch
+        w.text = (f'adaptive-scaling TINY/{neck.upper()} two-pass training step (fwd+bwd+loss'
+                  f'{"+bucketed NCCL grad all-reduce" if world > 1 else ""}{"+clip+AdamW" if with_optimizer else ""}), '
+                  f'batch {batch}/GPU, {size}x{size}, {POINTS} label points')
+        w.metric, w.unit = METRIC, UNIT
+    elif workload == 'backbone':
+        model.train()
+        backbone = model.backbone
+
+        def step(rbatch, pbatch):
+            for p in backbone.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+            feats = backbone(rbatch['image'])
+            loss = sum(f.float().square().mean() for f in feats)
+            loss.backward()
+            return loss.detach(), loss.detach()
+        w.images_per_step = batch
+        w.text = f'ConvNeXt-T backbone forward/backward, batch {batch}/GPU, {size}x{size}'
+        w.metric, w.unit = 'ConvNeXt backbone fwd+bwd images/sec @640x640', UNIT
+    else:
+        # config #5: uint8 page -> pad/ingest -> forward_rough -> thresholded uint8 mask + cleaned fp32 height map
+        # (inferencing/adaptive_scaling.py:92-188, tensor side), independent replicas
+        from vkit_ocr_model_adaptive_scaling_b200.inferencing import rough_infer_tensors
+        model.eval()
+        g = torch.Generator().manual_seed(133 + rank)
+        pages_host = torch.randint(0, 256, (batch, size, size, 3), generator=g, dtype=torch.uint8).pin_memory()
+        w.rb_host, w.pb_host = {'image_u8': pages_host}, {}
+        w.rb, w.pb = {'image_u8': pages_host.to(dev)}, {}
+        w.h2d = tensor_bytes(w.rb_host)
+
+        def step(rbatch, pbatch):
+            mask, hmap, _ = rough_infer_tensors(model, rbatch['image_u8'])
+            return mask, hmap
+        w.images_per_step = batch * size * size / 1e6          # the metric is MPix/s
+        w.text = f'rough inference (uint8 page -> text mask + char-height map), batch {batch}/GPU, {size}x{size}, replicas'
+        w.metric, w.unit = 'infer MPix/s', 'MPix/s'
+    w.step = step
+    w.workload, w.neck, w.batch, w.size = workload, neck, batch, size
+    return w
+
+
+def release(w) -> None:
+    import gc
+    import torch
+    if w.dp is not None:
+        w.dp.close()
+    for k in list(vars(w)):
+        delattr(w, k)
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def time_device_resident(w, steps: int, warmup: int, dev, rank: int, world: int, local_rank: int, sample_clocks: bool = True):
+    """W >= 3 warm-up steps, then exactly `steps` steps on device-resident inputs between barriers, CUDA events on the
+    launching stream, max over ranks; every C-ABI call of the timed region is bracketed with events (per-kernel table)."""
+    import torch
+    import torch.distributed as dist
+    from vkit_ocr_model_adaptive_scaling_b200 import _lib as L
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None   # before the warm-up: nvidia-smi needs ~0.5 s
+    for _ in range(max(warmup, 3)):
+        w.step(w.rb, w.pb)
+    barrier()
+    launches0 = L.LIB.vkocr_launch_count()
+    L.LIB.start_profile()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        losses = w.step(w.rb, w.pb)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    prof = L.LIB.stop_profile()
+    launches = (L.LIB.vkocr_launch_count() - launches0) // max(steps, 1)
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    return ms, losses, int(launches), prof.summary(), clocks
+
+
+def time_end_to_end(w, steps: int, dev, rank: int, world: int, local_rank: int):
+    """The same step through the public API from pinned HOST buffers: per step one H2D copy of the inputs (issued on a
+    copy stream one step ahead, like a training input pipeline) and a D2H read of the result, all inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    # Two device-side staging sets, allocated once (an input pipeline's double buffer): no allocator traffic inside the
+    # timed loop -- fresh side-stream allocations every step made the caching allocator fall back to cudaMalloc now and then.
+    like = lambda d: {k: (torch.empty_like(v, device=dev) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    bufs = [(like(w.rb_host), like(w.pb_host)) for _ in range(2)]
+    consumed = [None, None]                 # main-stream event: the step that read set k has finished
+    turn = [0]
+
+    def stage():
+        k = turn[0]
+        turn[0] ^= 1
+        with torch.cuda.stream(copy_stream):
+            if consumed[k] is not None:
+                copy_stream.wait_event(consumed[k])
+            for d_dev, d_host in zip(bufs[k], (w.rb_host, w.pb_host)):
+                for name, v in d_host.items():
+                    if isinstance(v, torch.Tensor):
+                        d_dev[name].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return bufs[k][0], bufs[k][1], ev, k
+
+    def mark_consumed(k):
+        consumed[k] = torch.cuda.Event()
+        consumed[k].record(main_stream)
+
+    for _ in range(2):
+        r, p_, ev, k = stage()
+        main_stream.wait_event(ev)
+        w.step(r, p_)
+        mark_consumed(k)
+    result_host, d2h = None, 8
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        time.sleep(0.6)                                 # let nvidia-smi come up (before the barrier: every rank starts together)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    nxt = stage()                                       # step 0's copy is exposed; every later copy overlaps a step
+    for i in range(steps):
+        rdev, pdev, ev, k = nxt
+        main_stream.wait_event(ev)
+        if i + 1 < steps:
+            nxt = stage()
+        a, b = w.step(rdev, pdev)
+        mark_consumed(k)
+        if w.workload == 'infer':                       # the caller reads the uint8 mask and the height map
+            if result_host is None:
+                result_host = (torch.empty(a.shape, dtype=a.dtype).pin_memory(), torch.empty(b.shape, dtype=b.dtype).pin_memory())
+            result_host[0].copy_(a, non_blocking=True)
+            result_host[1].copy_(b, non_blocking=True)
+            d2h = a.numel() * a.element_size() + b.numel() * b.element_size()
+        else:
+            loss_host.copy_(torch.stack([a.float().reshape(()), b.float().reshape(())]), non_blocking=True)
+        main_stream.synchronize()                       # the caller reads the step's losses (train.py:415,453)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {'value': w.images_per_step * world / (ms / 1e3), 'unit': w.unit, 'h2d_bytes_per_step': w.h2d, 'd2h_bytes_per_step': d2h,
+            'ms_per_step': ms, 'clocks': clocks}
+
+
+def roofline_of(table, steps: int, step_ms: float, peaks):
+    """The C-ABI call (entry point + shape) with the largest share of the timed region, against the roofline that bounds it:
+    tensor FLOP/s for the tcgen05 GEMMs, HBM GB/s for everything else.  FLOPs / bytes are ALGORITHMIC (true channel counts,
+    each operand read once and each result written once), the duration is measured here with CUDA events."""
+    rows = {k: r for k, r in table.items() if r['flops'] > 0 or r['bytes'] > 0}
+    if not rows:
+        return None
+    label, row = max(rows.items(), key=lambda kv: kv[1]['ms'])
+    per_launch_ms = row['ms'] / row['calls']
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            ent = json.load(f).get(label)      # DRAM bytes of this very call from the committed ncu --set full capture
+            traffic = ent.get('dram_bytes_per_call') if isinstance(ent, dict) else ent
+    except OSError:
+        pass
+    gemm = {k: r for k, r in table.items() if r['flops'] > 0 and r['entry'].startswith('vkocr_gemm')}
+    common = {'kernel': f'{row["entry"]} [{label}]', 'launch_ms': per_launch_ms, 'share_of_step': row['ms'] / steps / step_ms,
+              'traffic': traffic,
+              'all_gemm_share_of_step': sum(r['ms'] for r in gemm.values()) / steps / step_ms if gemm else 0.0,
+              'all_gemm_tflops': (sum(r['flops'] for r in gemm.values()) / sum(r['ms'] for r in gemm.values()) / 1e9) if gemm else 0.0}
+    if row['flops'] > 0 and row['entry'].startswith('vkocr_gemm'):
+        achieved = row['flops'] / row['calls'] / (per_launch_ms * 1e-3) / 1e12
+        return dict(bound='tensor', achieved=achieved, peak=peaks['tflops_sustained'], unit='TFLOP/s', frac=achieved / peaks['tflops_sustained'],
+                    algorithmic_flops=row['flops'] / row['calls'],
+                    peak_source=f'{peaks["source"]} sustained bf16 (kernel timed inside a long step)', **common)
+    achieved = row['bytes'] / row['calls'] / (per_launch_ms * 1e-3) / 1e9
+    return dict(bound='hbm', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s', frac=achieved / peaks['hbm_gbs'],
+                algorithmic_bytes=row['bytes'] / row['calls'], peak_source=f'{peaks["source"]} HBM copy bandwidth', **common)
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
     import vkit_ocr_model_adaptive_scaling_b200 as vk
     from vkit_ocr_model_adaptive_scaling_b200 import _lib as L
-    from vkit_ocr_model_adaptive_scaling_b200.parallel import DataParallel
-    from vkit_ocr_model_adaptive_scaling_b200.training import batch_to_device, train_step
-    from oracle import synth  # synthetic weights / batches only (test infrastructure generating inputs, never on the timed path)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -204,219 +507,62 @@ def run_ours(args) -> None:
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
     vk.set_compute_dtype(dtype)
 
-    M, LF = vk.model, vk.loss_function
     size = args.size or (2048 if args.workload == 'infer' else 640)
     batch = args.batch or (8 if args.workload == 'infer' else 32)
-    cfg = M.AdaptiveScalingConfig(size=M.AdaptiveScalingSize.TINY, neck_head_type=M.AdaptiveScalingNeckHeadType(args.neck))
-    torch.manual_seed(133)
-    model = M.AdaptiveScaling(cfg)
-    model.load_state_dict(synth.synth_state_dict('tiny', args.neck, seed=133), strict=True)
-    model.to(dev)
-    rough_fn = LF.AdaptiveScalingRoughLossFunction(LF.AdaptiveScalingRoughLossFunctionConifg())
-    precise_fn = LF.AdaptiveScalingPreciseLossFunction(LF.AdaptiveScalingPreciseLossFunctionConifg())
+    w = build_workload(vk, args.workload, args.neck, batch, size, dev, rank, world)
+    ms, losses, launches, table, clocks = time_device_resident(w, args.steps, args.warmup, dev, rank, world, local_rank)
+    value = w.images_per_step * world / (ms / 1e3)
+    e2e = None if args.no_e2e else time_end_to_end(w, args.steps, dev, rank, world, local_rank)
+    loss_values = [float(x.float().sum()) for x in losses]
 
-    rb_host, pb_host, rb, pb, h2d = {}, {}, {}, {}, 0
-    if args.workload != 'infer':
-        rb_host, pb_host = make_batches(batch, size, 133 + rank)
-        pin = lambda d: {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
-        rb_host, pb_host = pin(rb_host), pin(pb_host)
-        rb, pb = batch_to_device(rb_host, dev), batch_to_device(pb_host, dev)
-        h2d = tensor_bytes(rb_host) + tensor_bytes(pb_host)
-
-    dp = None
-    if args.workload == 'train':
-        model.train()   # stochastic depth active, as in the reference loop (train.py:396)
-        # flat gradient buckets also on one GPU: begin_step() zeroes 5 buffers instead of ~300 tensors, and for N > 1 the
-        # bucketed all-reduce overlaps the backward passes
-        dp = DataParallel(model)
-
-        def step(rbatch, pbatch):
-            return train_step(model, rough_fn, precise_fn, rbatch, pbatch, dp)
-        images_per_step = batch
-        workload = (f'adaptive-scaling TINY/{args.neck.upper()} two-pass training step (fwd+bwd+loss'
-                    f'{"+bucketed NCCL grad all-reduce" if world > 1 else ""}), batch {batch}/GPU, {size}x{size}, {POINTS} label points')
-    elif args.workload == 'backbone':
-        model.train()
-        backbone = model.backbone
-
-        def step(rbatch, pbatch):
-            for p in backbone.parameters():
-                if p.grad is not None:
-                    p.grad.zero_()
-            feats = backbone(rbatch['image'])
-            loss = sum(f.float().square().mean() for f in feats)
-            loss.backward()
-            return loss.detach(), loss.detach()
-        images_per_step = batch
-        workload = f'ConvNeXt-T backbone forward/backward, batch {batch}/GPU, {size}x{size}'
-    else:
-        # config #5: uint8 page -> pad/ingest -> forward_rough (head tails in the GEMM epilogue) -> thresholded uint8 mask +
-        # cleaned fp32 height map (inferencing/adaptive_scaling.py:92-188, tensor side), independent replicas
-        from vkit_ocr_model_adaptive_scaling_b200.inferencing import rough_infer_tensors
-        model.eval()
-        g = torch.Generator().manual_seed(133 + rank)
-        pages_host = torch.randint(0, 256, (batch, size, size, 3), generator=g, dtype=torch.uint8).pin_memory()
-        rb_host, pb_host = {'image_u8': pages_host}, {}
-        rb, pb = {'image_u8': pages_host.to(dev)}, {}
-        h2d = tensor_bytes(rb_host)
-
-        def step(rbatch, pbatch):
-            mask, hmap, _ = rough_infer_tensors(model, rbatch['image_u8'])
-            return mask, hmap
-        images_per_step = batch * size * size / 1e6          # the metric is MPix/s
-        workload = f'rough inference (uint8 page -> text mask + char-height map), batch {batch}/GPU, {size}x{size}, replicas'
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None     # started before the warm-up: nvidia-smi needs ~0.5 s to come up
-    for _ in range(max(args.warmup, 3)):
-        step(rb, pb)
-    barrier()
-
-    # ---- timed region: device-resident inputs, CUDA events on the launching (current) stream, GEMM launches bracketed
-    launches0 = L.LIB.vkocr_launch_count()
-    L.LIB.start_profile(only={'vkocr_gemm_nt', 'vkocr_gemm_nt_heads', 'vkocr_gemm_tn'})
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        losses = step(rb, pb)
-    e1.record()
-    barrier()
-    t1 = time.time()
-    prof = L.LIB.stop_profile()
-    launches = (L.LIB.vkocr_launch_count() - launches0) // max(args.steps, 1)
-    ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    clocks = sampler.stop(t0, t1) if sampler is not None else None
-    value = images_per_step * world / (ms / 1e3)
-    metric, unit = {'train': (METRIC, UNIT), 'backbone': ('ConvNeXt backbone fwd+bwd images/sec @640x640', UNIT),
-                    'infer': ('infer MPix/s', 'MPix/s')}[args.workload]
-    gemm_table = prof.summary()
-
-    # ---- e2e: host (pinned) -> device copies of both batches + device -> host read of both losses, every step
-    e2e = None
-    if not args.no_e2e:
-        loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
-        copy_stream = torch.cuda.Stream(device=dev)
-        main_stream = torch.cuda.current_stream(dev)
-
-        # Two device-side staging sets, allocated once (an input pipeline's double buffer): no allocator traffic inside
-        # the timed loop -- fresh side-stream allocations every step made the caching allocator fall back to cudaMalloc
-        # now and then (tens of ms per step, intermittently).
-        like = lambda d: {k: (torch.empty_like(v, device=dev) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
-        bufs = [(like(rb_host), like(pb_host)) for _ in range(2)]
-        consumed = [None, None]                 # main-stream event: the step that read set k has finished
-        turn = [0]
-
-        def stage():
-            """H2D copy of one step's rough + precise batch on the copy stream (the input pipeline of a training loop:
-            the next step's batch is in flight while the current step computes)."""
-            k = turn[0]
-            turn[0] ^= 1
-            with torch.cuda.stream(copy_stream):
-                if consumed[k] is not None:
-                    copy_stream.wait_event(consumed[k])
-                for d_dev, d_host in zip(bufs[k], (rb_host, pb_host)):
-                    for name, v in d_host.items():
-                        if isinstance(v, torch.Tensor):
-                            d_dev[name].copy_(v, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return bufs[k][0], bufs[k][1], ev, k
-
-        def mark_consumed(k):
-            consumed[k] = torch.cuda.Event()
-            consumed[k].record(main_stream)
-
-        for _ in range(2):
-            r, p_, ev, k = stage()
-            main_stream.wait_event(ev)
-            a, b = step(r, p_)
-            mark_consumed(k)
-        result_host, d2h = None, 8
-        sampler2 = ClockSampler(local_rank) if rank == 0 else None
-        if sampler2 is not None:
-            time.sleep(0.6)                                 # let nvidia-smi come up (before the barrier: every rank starts together)
-        barrier()
-        t0e = time.time()
-        e0.record()
-        nxt = stage()                                       # step 0's copy is exposed; every later copy overlaps a step
-        for i in range(args.steps):
-            rdev, pdev, ev, k = nxt
-            main_stream.wait_event(ev)
-            if i + 1 < args.steps:
-                nxt = stage()
-            a, b = step(rdev, pdev)
-            mark_consumed(k)
-            if args.workload == 'infer':                    # the caller reads the uint8 mask and the height map
-                if result_host is None:
-                    result_host = (torch.empty(a.shape, dtype=a.dtype).pin_memory(), torch.empty(b.shape, dtype=b.dtype).pin_memory())
-                result_host[0].copy_(a, non_blocking=True)
-                result_host[1].copy_(b, non_blocking=True)
-                d2h = a.numel() * a.element_size() + b.numel() * b.element_size()
-            else:
-                loss_host.copy_(torch.stack([a.float().reshape(()), b.float().reshape(())]), non_blocking=True)
-            main_stream.synchronize()                       # the caller reads the step's losses (train.py:415,453)
-        e1.record()
-        barrier()
-        t1e = time.time()
-        clocks_e2e = sampler2.stop(t0e, t1e) if sampler2 is not None else None
-        ms_e2e = e0.elapsed_time(e1) / args.steps
-        if world > 1:
-            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
-        e2e = {'value': images_per_step * world / (ms_e2e / 1e3), 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-               'ms_per_step': ms_e2e, 'clocks': clocks_e2e}
-
-    # ---- optional: full per-kernel table (one extra step, every C-ABI call bracketed)
+    # ---- optional: full per-kernel table of the timed region
     if args.profile and rank == 0:
-        L.LIB.start_profile()
-        step(rb, pb)
-        torch.cuda.synchronize()
-        table = L.LIB.stop_profile().summary()
         rows = sorted(table.items(), key=lambda kv: -kv[1]['ms'])
-        total = sum(r['ms'] for _, r in rows)
+        total = sum(r['ms'] for _, r in rows) / args.steps
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
         with open(os.path.join(ROOT, 'gpurun_out', f'kernel_table_{args.workload}_{args.neck}.json'), 'w') as f:
-            json.dump({'step_ms_sum_of_calls': total, 'rows': [dict(label=k, **v) for k, v in rows]}, f, indent=1)
-        print(f'# per-call device time, one step: {total:.2f} ms over {sum(r["calls"] for _, r in rows)} C-ABI calls', file=sys.stderr)
+            json.dump({'step_ms': ms, 'step_ms_sum_of_calls': total, 'steps': args.steps,
+                       'rows': [dict(label=k, calls=v['calls'] / args.steps, ms=v['ms'] / args.steps, flops=v['flops'] / args.steps,
+                                     bytes=v['bytes'] / args.steps, entry=v['entry']) for k, v in rows]}, f, indent=1)
+        print(f'# per-call device time per step: {total:.2f} ms of {ms:.2f} ms', file=sys.stderr)
         for k, r in rows[:70]:
             tf = r['flops'] / (r['ms'] * 1e-3) / 1e12 if r['flops'] else 0.0
             gb = r['bytes'] / (r['ms'] * 1e-3) / 1e9 if r['bytes'] else 0.0
-            print(f'#  {r["ms"]:9.3f} ms {100 * r["ms"] / total:5.1f}%  x{r["calls"]:<4d} {tf:7.1f} TF/s {gb:7.0f} GB/s  {k}', file=sys.stderr)
+            print(f'#  {r["ms"] / args.steps:9.3f} ms {100 * r["ms"] / args.steps / total:5.1f}%  x{r["calls"] // args.steps:<4d} {tf:7.1f} TF/s {gb:7.0f} GB/s  {k}',
+                  file=sys.stderr)
 
+    workload_text, metric, unit, h2d = w.text, w.metric, w.unit, w.h2d
+    release(w)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the GEMM label with the largest share of the timed region
-    roofline = None
-    if gemm_table:
-        label, row = max(gemm_table.items(), key=lambda kv: kv[1]['ms'])
-        per_launch_ms = row['ms'] / row['calls']
-        achieved = row['flops'] / row['calls'] / (per_launch_ms * 1e-3) / 1e12
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
-                traffic = json.load(f).get(label)      # DRAM bytes per launch from the committed ncu --set full capture
-        except OSError:
-            pass
-        roofline = {'bound': 'tensor', 'kernel': f'vkocr_gemm_tc_kernel [{label}]', 'achieved': achieved,
-                    'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops_sustained'],
-                    'traffic': traffic, 'peak_source': f'{peaks["source"]} sustained bf16 (kernel timed inside a long step)',
-                    'launch_ms': per_launch_ms, 'share_of_step': row['ms'] / args.steps / ms,
-                    'all_gemm_share_of_step': sum(r['ms'] for r in gemm_table.values()) / args.steps / ms,
-                    'all_gemm_tflops': sum(r['flops'] for r in gemm_table.values()) / sum(r['ms'] for r in gemm_table.values()) / 1e9}
+    roofline = roofline_of(table, args.steps, ms, peaks)
+
+    # ---- the other BASELINE configurations and the optimizer tail, observed by the same run (N = 1 only)
+    extra = None
+    if world == 1 and args.workload == 'train' and not args.no_extras:
+        extra = {}
+        for key, (wl, neck, b, sz, opt) in {
+                'fpn_train': ('train', 'fpn' if args.neck == 'upernext' else 'upernext', batch, size, False),
+                'with_optimizer': ('train', args.neck, batch, size, True),
+                'backbone_config2': ('backbone', args.neck, 32, 640, False),
+                'infer_config5': ('infer', 'upernext', 8, 2048, False)}.items():
+            try:
+                wx = build_workload(vk, wl, neck, b, sz, dev, 0, 1, with_optimizer=opt)
+                msx, _, lx, _, _ = time_device_resident(wx, 5, 3, dev, 0, 1, local_rank, sample_clocks=False)
+                extra[key] = {'workload': wx.text, 'value': wx.images_per_step / (msx / 1e3), 'unit': wx.unit, 'ms_per_step': msx,
+                              'gpu_launches': lx}
+                release(wx)
+            except Exception as exc:
+                extra[key] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
+                torch.cuda.empty_cache()
+
+    gpu_eager = None
+    if world == 1 and args.workload == 'train' and not args.no_eager_baseline:
+        gpu_eager = gpu_eager_baseline(args.neck, batch, size, dev)
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     if not args.no_cpu_baseline and args.workload == 'train':
@@ -429,10 +575,10 @@ def run_ours(args) -> None:
         'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if dtype == torch.bfloat16 else 'f32', 'data': 'synthetic',
-        'config': {'workload': workload, 'global_batch': batch * world, 'image_size': size, 'label_points': POINTS,
+        'config': {'workload': workload_text, 'global_batch': batch * world, 'image_size': size, 'label_points': POINTS,
                    'parallelism': f'dp{world}', 'l2': f'inputs per step ({h2d / 1e6:.0f} MB) and every activation exceed the 126 MB L2'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline,
-        'losses': [float(x.float().sum()) for x in losses],
+        'gpu_eager_baseline': gpu_eager, 'extra': extra, 'losses': loss_values,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

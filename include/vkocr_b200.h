@@ -209,7 +209,10 @@ int vkocr_head_tail_bwd(int dtype, const void* x, long long ld_x, int inner, int
  *   floats, coef[0] = loss.
  * vkocr_precise_loss_*: AdaptiveScalingPreciseLossFunction.__call__ (:181-346): masked pos / neg L2 of sigmoid(prob) in
  *   the core box + label-point gather (:167-179) terms; `factors` = 7 device floats {pos_l2, neg_l2, offset_l1,
- *   distance_regulation, angle_ce, corner_distance, loss_factor}.  sums: 8 zeroed doubles; coef: 3 floats. */
+ *   distance_regulation, angle_ce, corner_distance, loss_factor}.  sums: 8 zeroed doubles; coef: 3 floats.  Label points
+ *   are (B, P) int64 with negative indices wrapped like torch's advanced indexing; a point outside the map (the reference
+ *   raises IndexError) makes the loss NaN and is skipped by both passes -- nothing is read or written out of bounds.
+ *   gt_off: the (B, P, 2) offsets as fp32 (the dataset emits int64; the caller converts). */
 int vkocr_rough_loss_fwd(const float* logit, const float* height, const float* gt_mask, const float* gt_score, int B, int H,
                          int W, int up, int left, int CH, int CW, float height_min, float score_min, float focal_factor,
                          float dice_factor, float l1_factor, double* sums, float* coef, void* stream);
@@ -218,11 +221,11 @@ int vkocr_rough_loss_bwd(const float* logit, const float* height, const float* g
                          const float* grad_out, float* dlogit, float* dheight, void* stream);
 int vkocr_precise_loss_fwd(const float* prob, const float* off, const float* ang, const float* dist, const float* gt_score,
                            const float* gt_mask, int B, int H, int W, int up, int left, int CH, int CW, const long long* py,
-                           const long long* px, const long long* gt_off, const float* gt_ang, const float* gt_dist, int P,
+                           const long long* px, const float* gt_off, const float* gt_ang, const float* gt_dist, int P,
                            float beta, const float* factors, double* sums, float* coef, void* stream);
 int vkocr_precise_loss_bwd(const float* prob, const float* off, const float* ang, const float* dist, const float* gt_score,
                            const float* gt_mask, int B, int H, int W, int up, int left, int CH, int CW, const long long* py,
-                           const long long* px, const long long* gt_off, const float* gt_ang, const float* gt_dist, int P,
+                           const long long* px, const float* gt_off, const float* gt_ang, const float* gt_dist, int P,
                            float beta, const float* factors, const float* coef, const float* grad_out, float* dprob,
                            float* doff, float* dang, float* ddist, void* stream);
 

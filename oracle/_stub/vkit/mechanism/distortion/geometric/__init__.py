@@ -1,0 +1,1 @@
+"""Import-only stand-in (see vkit/element.py)."""

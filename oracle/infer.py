@@ -1,10 +1,20 @@
-"""Oracle (test infrastructure): numpy/torch restatement of the tensor-side operations of the reference's rough inference
-pass.  Citations are ``file:line`` into ``/root/reference``.  Parity unpinned by golden vectors of the reference itself:
-``vkit_open_model.inferencing`` imports ``vkit`` / ``iolite`` (absent), so these few lines are restated from source."""
+"""Oracle (test infrastructure): numpy/torch restatement of the tensor-side operations of the reference's inference passes.
+Citations are ``file:line`` into ``/root/reference``.  Pinned: ``tests/golden/inference_tensor_ops.npz`` holds the outputs of
+the UNMODIFIED reference (``inferencing/opt.py`` and ``AdaptiveScalingInferencing.rough_infer`` / ``.precise_infer``, run by
+``oracle/make_golden.py`` with import-only stand-ins for the absent ``vkit`` / ``iolite`` packages and a stand-in model
+that returns seeded network outputs) together with the reference's own test vectors (tests/test_evaluation.py:15-22);
+``tests/test_oracle_golden.py`` holds these functions to them bit for bit.  ``peak_mask`` restates :477-491, whose only
+arithmetic is the reference's own dependency ``scipy.ndimage.maximum_filter`` (called here as the reference calls it)."""
 import math
 
 import numpy as np
 import torch
+
+
+def pad_length_to_make_divisible(length: int, downsampling_factor: int):
+    """vkit_open_model/inferencing/opt.py:16-18."""
+    padded_length = math.ceil(length / downsampling_factor) * downsampling_factor
+    return padded_length, padded_length - length
 
 
 def pad_mat_to_make_divisible(mat: np.ndarray, downsampling_factor: int) -> np.ndarray:

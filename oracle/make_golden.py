@@ -176,9 +176,83 @@ def neck_head_units():
     np.savez_compressed(os.path.join(OUT, 'neck_head_units.npz'), **out)
 
 
+def inference_tensor_ops():
+    """The tensor side of the reference's inference passes, run UNMODIFIED: ``pad_length_to_make_divisible`` /
+    ``pad_mat_to_make_divisible`` (inferencing/opt.py:16-41), ``AdaptiveScalingInferencing.rough_infer`` (inferencing/
+    adaptive_scaling.py:92-188) and ``.precise_infer`` (:295-396) with a stand-in ``model_jit`` that returns seeded network
+    outputs (the network itself is pinned by the other fixtures), on images that need bottom / right / no padding."""
+    from vkit.element import Image
+    from vkit_open_model.inferencing import adaptive_scaling as ref_inf
+    from vkit_open_model.inferencing.opt import pad_length_to_make_divisible, pad_mat_to_make_divisible
+
+    out = {}
+    lengths = [(6, 3), (7, 3), (1, 32), (32, 32), (33, 32), (720, 32), (721, 32), (2048, 32)]
+    out['pad_length_cases'] = np.array(lengths, dtype=np.int64)
+    out['pad_length_results'] = np.array([pad_length_to_make_divisible(a, b) for a, b in lengths], dtype=np.int64)
+
+    class FakeJit:
+        """forward_rough / forward_precise of a scripted model: seeded outputs at (H / 2, W / 2) of the padded input."""
+
+        def __init__(self, seed):
+            self.g = torch.Generator().manual_seed(seed)
+            self.last = None
+
+        def forward_rough(self, x):
+            _, _, H, W = x.shape
+            mask = torch.randn(1, 1, H // 2, W // 2, generator=self.g) * 3
+            height = torch.rand(1, 1, H // 2, W // 2, generator=self.g) * 8
+            self.last = (x.clone(), mask.clone(), height.clone())
+            return mask, height
+
+        def forward_precise(self, x):
+            _, _, H, W = x.shape
+            shape = (H // 2, W // 2)
+            feats = (torch.randn(1, 1, *shape, generator=self.g) * 3, torch.randn(1, 2, *shape, generator=self.g) * 10,
+                     torch.randn(1, 4, *shape, generator=self.g) * 2, torch.rand(1, 4, *shape, generator=self.g) * 30)
+            self.last = (x.clone(),) + tuple(f.clone() for f in feats)
+            return feats
+
+    cfg = ref_inf.AdaptiveScalingInferencingConfig(model_jit='unused')
+    rng = np.random.default_rng(133)
+    sizes = [(64, 96), (70, 101), (33, 64), (96, 33), (1, 1)]
+    out['sizes'] = np.array(sizes, dtype=np.int64)
+    for idx, (H, W) in enumerate(sizes):
+        img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        out[f'image{idx}'] = img
+        out[f'padded{idx}'] = pad_mat_to_make_divisible(img, 32)
+        inf = object.__new__(ref_inf.AdaptiveScalingInferencing)       # __init__ only loads the TorchScript file
+        inf.config = cfg
+        inf.model_jit = FakeJit(1000 + idx)
+        with torch.no_grad():
+            r = inf.rough_infer(Image(mat=img))
+        x, mask_f, height_f = inf.model_jit.last
+        out[f'rough{idx}_input'] = _np(x)
+        out[f'rough{idx}_mask_feature'] = _np(mask_f)
+        out[f'rough{idx}_height_feature'] = _np(height_f)
+        out[f'rough{idx}_mask'] = r.rough_char_mask.mat
+        out[f'rough{idx}_height_map'] = r.rough_char_height_score_map.mat
+        out[f'rough{idx}_resized_shape'] = np.array(r.resized_shape, dtype=np.int64)
+        inf.model_jit = FakeJit(2000 + idx)
+        with torch.no_grad():
+            p = inf.precise_infer(Image(mat=img))
+        feats = inf.model_jit.last
+        for name, t in zip(('input', 'prob_feature', 'offset_feature', 'angle_feature', 'distance_feature'), feats):
+            out[f'precise{idx}_{name}'] = _np(t)
+        out[f'precise{idx}_prob_map'] = p.precise_char_prob_score_map.mat
+        out[f'precise{idx}_offset'] = p.precise_np_char_up_left_corner_offset
+        out[f'precise{idx}_angle'] = p.precise_np_char_corner_angle_distribution
+        out[f'precise{idx}_distance'] = p.precise_np_char_corner_distance
+    np.savez_compressed(os.path.join(OUT, 'inference_tensor_ops.npz'), **out)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == 'inference':
+        inference_tensor_ops()
+        print('inference fixture written to', OUT)
+        sys.exit(0)
+    inference_tensor_ops()
     primitive_losses()
     backbone_features()
     neck_head_units()

@@ -13,6 +13,47 @@ def vk():
     return vk
 
 
+def test_inference_tensor_ops_against_reference_fixture(vk, golden_dir):
+    """The device kernels against the outputs of the UNMODIFIED reference inference code (tests/golden/
+    inference_tensor_ops.npz, written by oracle/make_golden.py from inferencing/opt.py:16-41 and inferencing/
+    adaptive_scaling.py:92-188,295-396), fed the same network outputs: uint8 ingest and the rough mask / height map
+    bit-exact, the precise post-ops to fp32 rounding of sigmoid / softmax."""
+    import math
+    import os
+    from vkit_ocr_model_adaptive_scaling_b200 import _lib as L
+    g = np.load(os.path.join(golden_dir, 'inference_tensor_ops.npz'))
+    for (length, factor), want in zip(g['pad_length_cases'], g['pad_length_results']):
+        assert vk.inferencing.pad_length_to_make_divisible(int(length), int(factor)) == (int(want[0]), int(want[1]))
+    dev = torch.device('cuda')
+    for idx, (H, W) in enumerate(g['sizes']):
+        H, W = int(H), int(W)
+        x = vk.inferencing.ingest_images(torch.from_numpy(g[f'image{idx}']).to(dev), 32)
+        assert torch.equal(x.cpu(), torch.from_numpy(g[f'rough{idx}_input']))
+        logit, height = (torch.from_numpy(g[f'rough{idx}_{n}_feature']).to(dev) for n in ('mask', 'height'))
+        _, _, h, w = logit.shape
+        mask = torch.empty((1, h, w), dtype=torch.uint8, device=dev)
+        hmap = torch.empty((1, h, w), dtype=torch.float32, device=dev)
+        L.check(L.LIB.vkocr_rough_postprocess(L.ptr(logit), L.ptr(height), 1, h, w, math.ceil(H / 2), math.ceil(W / 2), 0.5, 3.0,
+                                              L.ptr(mask), L.ptr(hmap), L.stream_ptr()), 'rough_postprocess')
+        want_mask = g[f'rough{idx}_mask']
+        sure = np.abs(g[f'rough{idx}_mask_feature'][0, 0]) > 1e-6          # sigmoid(x) >= 0.5 <=> x >= 0, up to rounding at x ~ 0
+        assert np.array_equal(mask[0].cpu().numpy()[sure], want_mask[sure])
+        assert np.array_equal(hmap[0].cpu().numpy(), g[f'rough{idx}_height_map'])
+        feats = [torch.from_numpy(g[f'precise{idx}_{n}_feature']).to(dev) for n in ('prob', 'offset', 'angle', 'distance')]
+        prob = torch.empty((1, h, w), dtype=torch.float32, device=dev)
+        offs = torch.empty((1, h, w, 2), dtype=torch.float32, device=dev)
+        angs = torch.empty((1, h, w, 4), dtype=torch.float32, device=dev)
+        dists = torch.empty((1, h, w, 4), dtype=torch.float32, device=dev)
+        L.check(L.LIB.vkocr_precise_postprocess(*(L.ptr(f) for f in feats), 1, h, w, 4, math.ceil(H / 2), math.ceil(W / 2), L.ptr(prob),
+                                                L.ptr(offs), L.ptr(angs), L.ptr(dists), L.stream_ptr()), 'precise_postprocess')
+        assert np.array_equal(offs[0].cpu().numpy(), g[f'precise{idx}_offset'])
+        assert np.array_equal(dists[0].cpu().numpy(), g[f'precise{idx}_distance'])
+        assert np.allclose(prob[0].cpu().numpy(), g[f'precise{idx}_prob_map'], rtol=1e-6, atol=1e-7)
+        assert np.allclose(angs[0].cpu().numpy(), g[f'precise{idx}_angle'], rtol=1e-5, atol=1e-7)
+        zero = g[f'precise{idx}_prob_map'] == 0.0
+        assert np.array_equal(prob[0].cpu().numpy() == 0.0, zero)                # the padding is forced to exactly 0
+
+
 @pytest.mark.parametrize('hw', [(64, 96), (70, 101), (33, 32), (1, 1)])
 def test_ingest_matches_reference_padding(vk, hw):
     from oracle import infer as oi

@@ -246,3 +246,35 @@ def test_larger_configs_against_oracle(vk, size, neck, dtype):
     assert abs(float(pl) - float(pl_ref)) <= tol * abs(float(pl_ref)), (float(pl), float(pl_ref))
     # bf16: the 40-layer SMALL / 1024-channel BASE chains are deeper than TINY's; same yardstick rule as the step test
     compare_grads(model, params, dtype, f'{size}/{neck} step', yardstick=4e-2 if dtype == torch.bfloat16 else None)
+
+
+def test_frozen_parameters_get_no_gradient(vk):
+    """requires_grad_(False) on the backbone (fine-tuning the necks / heads): the backward kernels leave the frozen
+    parameters without a .grad, and every other gradient equals the unfrozen run's."""
+    from oracle import synth
+    dev = torch.device('cuda')
+    M, LF = vk.model, vk.loss_function
+    model = M.AdaptiveScaling(M.AdaptiveScalingConfig(size=M.AdaptiveScalingSize.TINY, neck_head_type=M.AdaptiveScalingNeckHeadType.UPERNEXT))
+    model.load_state_dict(synth.synth_state_dict('tiny', 'upernext', seed=7), strict=True)
+    model.to(dev).eval()
+    rb = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in synth.synth_rough_batch(1, 64, 96, seed=3, inset=4).items()}
+    fn = LF.AdaptiveScalingRoughLossFunction(LF.AdaptiveScalingRoughLossFunctionConifg())
+    rk = ('downsampled_mask', 'downsampled_score_map', 'downsampled_shape', 'downsampled_core_box')
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        with vk.precision(torch.float32):
+            m, h = model.forward_rough(rb['image'])
+            fn(rough_char_mask_feature=m, rough_char_height_feature=h, **{k: rb[k] for k in rk}).backward()
+        torch.cuda.synchronize()
+        return {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}
+
+    full = run()
+    for p in model.backbone.parameters():
+        p.requires_grad_(False)
+    frozen = run()
+    for n, g in frozen.items():
+        if n.startswith('backbone.'):
+            assert g is None, f'{n}: a frozen parameter received a gradient'
+        elif n.startswith('rough_'):
+            assert g is not None and torch.allclose(g, full[n], rtol=1e-5, atol=1e-8), n

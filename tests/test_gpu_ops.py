@@ -328,6 +328,61 @@ def test_precise_loss(vk, B, H, W, inset, P):
         assert_close(ours[i].grad, refs[i].grad, 1e-4, f'd precise / d {name}')
 
 
+def test_precise_loss_guards(vk):
+    """Label points outside the map (the reference's advanced indexing raises IndexError, :167-179) give a NaN loss and touch
+    no memory outside the maps; negative indices wrap like torch; float offsets promote like F.smooth_l1_loss (no truncation);
+    label tensors of another batch size are rejected; changed primitive hyper-parameters are refused, not ignored."""
+    from oracle import loss as ol
+    dev = torch.device('cuda')
+    B, H, W, P = 2, 24, 32, 6
+    _, pb = _loss_inputs(B, H, W, 3, P, 81, dev)
+    g = torch.Generator().manual_seed(5)
+    maps = [(torch.randn(B, c, H, W, generator=g)).to(dev) for c in (1, 2, 4, 4)]
+    fn = vk.loss_function.AdaptiveScalingPreciseLossFunction(vk.loss_function.AdaptiveScalingPreciseLossFunctionConifg())
+    keys = ('downsampled_char_prob_score_map', 'downsampled_char_mask', 'downsampled_shape', 'downsampled_core_box',
+            'downsampled_label_point_y', 'downsampled_label_point_x', 'char_up_left_offsets', 'char_corner_angles',
+            'char_corner_distances')
+
+    def run(batch, maps_in):
+        ours = [m.clone().requires_grad_(True) for m in maps_in]
+        loss = fn(None, *ours, **{k: batch[k] for k in keys})
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss, ours
+
+    base, base_maps = run(pb, maps)
+    # negative indices wrap (y - H addresses the same pixel)
+    wrapped = dict(pb)
+    wrapped['downsampled_label_point_y'] = pb['downsampled_label_point_y'] - H
+    loss_w, maps_w = run(wrapped, maps)
+    assert float(loss_w) == float(base)
+    assert all(torch.equal(a.grad, b.grad) for a, b in zip(maps_w, base_maps))
+    # float offsets with fractional parts: the oracle (F.smooth_l1_loss) promotes, so must we
+    frac = dict(pb)
+    frac['char_up_left_offsets'] = pb['char_up_left_offsets'].float() + 0.4
+    loss_f, _ = run(frac, maps)
+    ref = ol.precise_loss(None, *maps, *(frac[k] for k in keys))
+    assert abs(float(loss_f) - float(ref)) <= 1e-4 * abs(float(ref)), (float(loss_f), float(ref))
+    assert abs(float(loss_f) - float(base)) > 1e-4
+    # a point outside the map: NaN loss, finite gradients that ignore the point
+    bad = dict(pb)
+    y = pb['downsampled_label_point_y'].clone()
+    y[1, 2] = H + 5
+    bad['downsampled_label_point_y'] = y
+    loss_b, maps_b = run(bad, maps)
+    assert torch.isnan(loss_b)
+    assert all(torch.isfinite(m.grad).all() for m in maps_b)
+    # batch mismatch
+    short = dict(pb)
+    short['char_corner_angles'] = pb['char_corner_angles'][:1]
+    with pytest.raises(RuntimeError):
+        run(short, maps)
+    # hyper-parameters of the primitives are compiled into the fused kernels
+    fn.char_corner_distance_l1.smooth_beta = 1.0
+    with pytest.raises(NotImplementedError):
+        run(pb, maps)
+
+
 def test_precise_loss_optional_terms(vk):
     """Off-by-default terms: masked focal on the optional char-mask head, prob smooth-L1, WAHR (reference :272-307)."""
     from oracle import loss as ol

@@ -108,3 +108,34 @@ def test_full_model_forward_loss_backward(golden_dir, neck):
     for key in g.files:
         if key.startswith('precise_grad::'):
             _close(by_name[key.split('::', 1)[1]], g[key], rtol=2e-3, atol=1e-5)
+
+
+def test_inference_tensor_ops_against_reference_fixture(golden_dir):
+    """oracle/infer.py against the outputs of the UNMODIFIED reference inference code (inferencing/opt.py:16-41,
+    inferencing/adaptive_scaling.py:92-188,295-396; fixture written by oracle/make_golden.py) and the reference's own test
+    vectors (tests/test_evaluation.py:15-22): bit-exact."""
+    from oracle import infer as oi
+    g = _load(golden_dir, 'inference_tensor_ops.npz')
+    assert oi.pad_length_to_make_divisible(6, 3) == (6, 0)          # tests/test_evaluation.py:16-18
+    assert oi.pad_length_to_make_divisible(7, 3) == (9, 2)          # tests/test_evaluation.py:20-22
+    for (length, factor), want in zip(g['pad_length_cases'], g['pad_length_results']):
+        assert oi.pad_length_to_make_divisible(int(length), int(factor)) == (int(want[0]), int(want[1]))
+    for idx, (H, W) in enumerate(g['sizes']):
+        H, W = int(H), int(W)
+        img = g[f'image{idx}']
+        padded = oi.pad_mat_to_make_divisible(img, 32)
+        assert padded.dtype == np.uint8 and np.array_equal(padded, g[f'padded{idx}'])
+        x = oi.network_input(img, 32)
+        assert x.dtype == torch.float32 and np.array_equal(x.numpy(), g[f'rough{idx}_input'])
+        assert np.array_equal(x.numpy(), g[f'precise{idx}_input'])
+        Hp, Wp = padded.shape[:2]
+        mask, hmap, shape = oi.rough_postprocess(torch.from_numpy(g[f'rough{idx}_mask_feature'])[0, 0],
+                                                 torch.from_numpy(g[f'rough{idx}_height_feature'])[0, 0], H, W, Hp, Wp)
+        assert mask.dtype == np.uint8 and np.array_equal(mask, g[f'rough{idx}_mask'])
+        assert hmap.dtype == np.float32 and np.array_equal(hmap, g[f'rough{idx}_height_map'])
+        assert tuple(shape) == tuple(int(v) for v in g[f'rough{idx}_resized_shape'])
+        feats = [torch.from_numpy(g[f'precise{idx}_{n}_feature']) for n in ('prob', 'offset', 'angle', 'distance')]
+        prob, off, ang, dist = oi.precise_postprocess(*feats, H, W, Hp, Wp)
+        for got, name in ((prob, 'prob_map'), (off, 'offset'), (ang, 'angle'), (dist, 'distance')):
+            want = g[f'precise{idx}_{name}']
+            assert got.dtype == np.float32 and got.shape == want.shape and np.array_equal(got, want), (idx, name)

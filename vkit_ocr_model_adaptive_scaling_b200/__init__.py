@@ -17,3 +17,4 @@ from . import parallel  # noqa: F401
 __all__ = ['model', 'loss_function', 'ops', 'parallel', 'runtime', 'set_compute_dtype', 'compute_dtype', 'precision']
 from . import training  # noqa: F401
 from . import inferencing  # noqa: F401
+from . import checkpoint  # noqa: F401

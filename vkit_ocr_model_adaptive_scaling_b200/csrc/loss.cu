@@ -143,7 +143,7 @@ precise_dense_reduce_kernel(const float* __restrict__ logit, const float* __rest
 __global__ void __launch_bounds__(256)
 precise_points_reduce_kernel(const float* __restrict__ off, const float* __restrict__ ang, const float* __restrict__ dist,
                              const long long* __restrict__ py, const long long* __restrict__ px,
-                             const long long* __restrict__ gt_off, const float* __restrict__ gt_ang,
+                             const float* __restrict__ gt_off, const float* __restrict__ gt_ang,
                              const float* __restrict__ gt_dist, int B, int P, int H, int W, float beta, double* __restrict__ sums) {
     __shared__ float scratch[33];
     float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -154,9 +154,15 @@ precise_points_reduce_kernel(const float* __restrict__ off, const float* __restr
         long long y = py[i], x = px[i];
         if (y < 0) y += H;   // torch advanced indexing wraps negative indices
         if (x < 0) x += W;
+        if (y < 0 || y >= H || x < 0 || x >= W) {
+            // the reference's advanced indexing raises IndexError here; without a host sync the loud failure is a NaN loss
+            // (see precise_finalize_kernel), and nothing is read or (in the backward) written out of bounds
+            v[0] = v[1] = v[2] = v[3] = __int_as_float(0x7fc00000);
+            continue;
+        }
         const long long pix = y * W + x;
         const float o0 = off[((long long)b * 2 + 0) * hw + pix], o1 = off[((long long)b * 2 + 1) * hw + pix];
-        v[0] += smooth_l1(o0 - (float)gt_off[i * 2 + 0], beta) + smooth_l1(o1 - (float)gt_off[i * 2 + 1], beta);
+        v[0] += smooth_l1(o0 - gt_off[i * 2 + 0], beta) + smooth_l1(o1 - gt_off[i * 2 + 1], beta);
         float a[4], d[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -186,6 +192,7 @@ __global__ void precise_finalize_kernel(const double* __restrict__ sums, double 
     if (f[4] > 0.f) loss += f[4] * sums[6] / bp;
     if (f[5] > 0.f) loss += f[5] * sums[7] / (bp * 3.0);
     loss *= f[6];
+    if (sums[4] != sums[4] || sums[5] != sums[5] || sums[6] != sums[6] || sums[7] != sums[7]) loss = sums[4] + sums[5] + sums[6] + sums[7];   // a label point outside the map
     coef[0] = (float)loss;
     coef[1] = f[0] > 0.f ? (float)(f[6] * f[0] / (sums[1] + (double)EPS)) : 0.f;
     coef[2] = f[1] > 0.f ? (float)(f[6] * f[1] / (sums[3] + (double)EPS)) : 0.f;
@@ -216,7 +223,7 @@ precise_dense_bwd_kernel(const float* __restrict__ logit, const float* __restric
 __global__ void __launch_bounds__(256)
 precise_points_bwd_kernel(const float* __restrict__ off, const float* __restrict__ ang, const float* __restrict__ dist,
                           const long long* __restrict__ py, const long long* __restrict__ px,
-                          const long long* __restrict__ gt_off, const float* __restrict__ gt_ang,
+                          const float* __restrict__ gt_off, const float* __restrict__ gt_ang,
                           const float* __restrict__ gt_dist, int B, int P, int H, int W, float beta, const float* __restrict__ f,
                           const float* __restrict__ gout, float* __restrict__ doff, float* __restrict__ dang,
                           float* __restrict__ ddist) {
@@ -228,6 +235,7 @@ precise_points_bwd_kernel(const float* __restrict__ off, const float* __restrict
     long long y = py[i], x = px[i];
     if (y < 0) y += H;
     if (x < 0) x += W;
+    if (y < 0 || y >= H || x < 0 || x >= W) return;   // see the forward: the loss is NaN, nothing is scattered
     const long long pix = y * W + x;
     const float g = gout[0] * f[6];
     const float bp = (float)total;
@@ -241,8 +249,8 @@ precise_points_bwd_kernel(const float* __restrict__ off, const float* __restrict
     float g0 = 0.f, g1 = 0.f, gd0 = 0.f;
     if (f[2] > 0.f) {
         const float k = g * f[2] / (bp * 2.f);
-        g0 += k * smooth_l1_grad(o0 - (float)gt_off[i * 2 + 0], beta);
-        g1 += k * smooth_l1_grad(o1 - (float)gt_off[i * 2 + 1], beta);
+        g0 += k * smooth_l1_grad(o0 - gt_off[i * 2 + 0], beta);
+        g1 += k * smooth_l1_grad(o1 - gt_off[i * 2 + 1], beta);
     }
     if (f[3] > 0.f) {
         const float nrm = sqrtf(o0 * o0 + o1 * o1);
@@ -324,7 +332,7 @@ int vkocr_rough_loss_bwd(const float* logit, const float* height, const float* g
 // factors: 7 device floats (see precise_finalize_kernel); sums: 8 doubles zeroed by the caller; coef: 3 floats.
 int vkocr_precise_loss_fwd(const float* prob, const float* off, const float* ang, const float* dist, const float* gt_score,
                            const float* gt_mask, int B, int H, int W, int up, int left, int CH, int CW, const long long* py,
-                           const long long* px, const long long* gt_off, const float* gt_ang, const float* gt_dist, int P,
+                           const long long* px, const float* gt_off, const float* gt_ang, const float* gt_dist, int P,
                            float beta, const float* factors, double* sums, float* coef, void* stream) {
     VK_REQUIRE(prob && off && ang && dist && gt_score && gt_mask && factors && sums && coef, VKOCR_BAD_ARGUMENT,
                "precise_loss_fwd: null argument");
@@ -350,7 +358,7 @@ int vkocr_precise_loss_fwd(const float* prob, const float* off, const float* ang
 // dprob is fully written; doff/dang/ddist must be zero-initialised by the caller (scatter-add).
 int vkocr_precise_loss_bwd(const float* prob, const float* off, const float* ang, const float* dist, const float* gt_score,
                            const float* gt_mask, int B, int H, int W, int up, int left, int CH, int CW, const long long* py,
-                           const long long* px, const long long* gt_off, const float* gt_ang, const float* gt_dist, int P,
+                           const long long* px, const float* gt_off, const float* gt_ang, const float* gt_dist, int P,
                            float beta, const float* factors, const float* coef, const float* grad_out, float* dprob, float* doff,
                            float* dang, float* ddist, void* stream) {
     VK_REQUIRE(prob && off && ang && dist && gt_score && gt_mask && factors && coef && grad_out && dprob && doff && dang && ddist,

@@ -40,6 +40,13 @@ def _crop(feature: torch.Tensor, box) -> torch.Tensor:
     return feature[:, 0, box.up:box.down + 1, box.left:box.right + 1]
 
 
+def _require(cond: bool, what: str) -> None:
+    if not cond:
+        raise NotImplementedError(
+            'vkocr_b200 fused loss kernels are built for the reference\'s hyper-parameters; ' + what +
+            ' (changing the primitive objects on the composite loss has no effect on the fused path)')
+
+
 def _check_box(box, shape: Tuple[int, int], gt: torch.Tensor) -> Tuple[int, int]:
     ch, cw = box.down - box.up + 1, box.right - box.left + 1
     assert 0 <= box.up and box.down < shape[0] and 0 <= box.left and box.right < shape[1], 'core box outside the map'
@@ -81,6 +88,12 @@ class AdaptiveScalingRoughLossFunction:
         box = downsampled_core_box
         _check_box(box, tuple(downsampled_shape), downsampled_mask)
         cfg = self.config
+        assert downsampled_mask.shape == downsampled_score_map.shape
+        assert downsampled_mask.shape[0] == rough_char_mask_feature.shape[0], 'ground-truth batch differs from the prediction batch'
+        # the fused kernel (csrc/loss.cu) compiles in the hyper-parameters of the reference's primitives (:42-51)
+        fo, l1 = self.focal_with_logits, self.l1
+        _require(abs(fo.alpha - 0.25) < 1e-12 and abs(fo.gamma - 2) < 1e-12, f'focal alpha {fo.alpha} gamma {fo.gamma} != 0.25 / 2')
+        _require(l1.smooth and abs(l1.smooth_beta - 1.0) < 1e-12, f'rough smooth-L1 beta {l1.smooth_beta} != 1.0')
         loss = ops.RoughLossFn.apply(
             rough_char_mask_feature, rough_char_height_feature, downsampled_mask, downsampled_score_map,
             int(box.up), int(box.left), float(cfg.char_height_feature_min), float(cfg.downsampled_score_map_min),
@@ -154,6 +167,9 @@ class AdaptiveScalingPreciseLossFunction:
         assert precise_char_up_left_corner_offset_feature.shape[1] == 2
         assert precise_char_corner_angle_feature.shape[1] == 4 and precise_char_corner_distance_feature.shape[1] == 4
 
+        for prim in (self.char_up_left_offset_l1, self.char_up_left_distance_regulation_l1, self.char_corner_distance_l1):
+            _require(prim.smooth and abs(prim.smooth_beta - self.LABEL_POINT_SMOOTH_BETA) < 1e-12,
+                     f'label-point smooth-L1 beta {prim.smooth_beta} != {self.LABEL_POINT_SMOOTH_BETA}')
         factors = (cfg.char_prob_pos_l2_factor, cfg.char_prob_neg_l2_factor, cfg.char_up_left_offset_l1_factor,
                    cfg.char_up_left_distance_regulation_l1_factor, cfg.char_corner_angle_cross_entropy_factor,
                    cfg.char_corner_distance_l1_factor, cfg.loss_factor)

@@ -66,8 +66,23 @@ def geom(x: Tensor) -> Tuple[int, int, int, int, int]:
     return B, H, W, C, x.stride(3)
 
 
+_FROZEN_SCRATCH: Dict[Tuple, Tensor] = {}
+
+
 def grad_buffer(p: Tensor) -> Tensor:
-    """fp32 ``.grad`` of a parameter, created zeroed on first use; kernels accumulate into it."""
+    """fp32 ``.grad`` of a parameter, created zeroed on first use; kernels accumulate into it.
+
+    The backward nodes write parameter gradients here themselves and return ``None`` for them to autograd (that is what
+    lets the gradients land in the flat data-parallel buckets without a copy), so ``torch.autograd.grad``, tensor hooks
+    and ``create_graph`` do not see parameter gradients — use ``loss.backward()`` and read ``param.grad``.  A frozen
+    parameter (``requires_grad_(False)``, e.g. backbone fine-tuning) gets no ``.grad``: its kernels accumulate into a
+    shared scratch buffer that nothing reads."""
+    if not p.requires_grad:
+        key = (p.numel(), str(p.device))
+        buf = _FROZEN_SCRATCH.get(key)
+        if buf is None:
+            buf = _FROZEN_SCRATCH[key] = torch.zeros(p.numel(), dtype=torch.float32, device=p.device)
+        return buf.view(p.shape)
     if p.grad is None:
         p.grad = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
     g = p.grad
@@ -274,18 +289,21 @@ COMBINE_ALGO = 0    # tests set this to 1 to force the generic gather kernels of
 SIMT_BACKEND = 0  # tests set this to 1 to route bf16 GEMMs through the SIMT kernel (cross-check of the tcgen05 path)
 
 
-def gemm_nt(x: Tensor, B: int, H: int, W: int, C: int, ld_x: int, ks: int, wp: Tensor, c_pad: int, N: int, ep: L.Epilogue) -> None:
+def gemm_nt(x: Tensor, B: int, H: int, W: int, C: int, ld_x: int, ks: int, wp: Tensor, c_pad: int, N: int, ep: L.Epilogue,
+            alg_kn: Optional[int] = None) -> None:
+    """``alg_kn``: the algorithmic K*N of the contraction when C / N carry layout padding (profile bookkeeping only)."""
     if L.PROFILE.active:
         M = B * H * W
-        L.PROFILE.note(f'gemm_nt ks{ks} M{M} K{ks * ks * C} N{N}', 2.0 * M * ks * ks * C * N)
+        L.PROFILE.note(f'gemm_nt ks{ks} M{M} K{ks * ks * C} N{N}', 2.0 * M * (ks * ks * C * N if alg_kn is None else alg_kn))
     g = L.ConvGeom(B, H, W, ks, C, ld_x, c_pad)
     L.check(L.LIB.vkocr_gemm_nt(_tag(x.dtype), SIMT_BACKEND, L.ptr(x), ctypes.byref(g), L.ptr(wp), N, ctypes.byref(ep), _s()), 'gemm_nt')
 
 
-def gemm_tn(p: Tensor, B: int, H: int, W: int, I: int, ld_p: int, ks: int, q: Tensor, J: int, ld_q: int, ep: L.Epilogue) -> None:
+def gemm_tn(p: Tensor, B: int, H: int, W: int, I: int, ld_p: int, ks: int, q: Tensor, J: int, ld_q: int, ep: L.Epilogue,
+            alg_ij: Optional[int] = None) -> None:
     if L.PROFILE.active:
         M = B * H * W
-        L.PROFILE.note(f'gemm_tn ks{ks} M{M} I{I} J{J}', 2.0 * M * ks * ks * I * J)
+        L.PROFILE.note(f'gemm_tn ks{ks} M{M} I{I} J{J}', 2.0 * M * (ks * ks * I * J if alg_ij is None else alg_ij))
     g = L.ConvGeom(B, H, W, ks, I, ld_p, 0)
     L.check(L.LIB.vkocr_gemm_tn(_tag(p.dtype), SIMT_BACKEND, L.ptr(p), ctypes.byref(g), L.ptr(q), J, ld_q, ctypes.byref(ep), _s()), 'gemm_tn')
 
@@ -813,12 +831,14 @@ class HeadGroupFn(torch.autograd.Function):
             wz, c_pad, nz = packed_tapsplit_fwd([hd[0] for hd in heads], dt, slot)
             m_low = B * h * w
             z = torch.empty((m_low, nz), dtype=dt, device=dev)
-            gemm_nt(x, 1, 1, m_low, C, ld, 1, wz, c_pad, nz, _epilogue(z, nz))
+            gemm_nt(x, 1, 1, m_low, C, ld, 1, wz, c_pad, nz, _epilogue(z, nz), alg_kn=C * T * sum(inners))
             conv = alloc_nhwc(B, H, W, ntot, dt, dev) if train else None
             ht = head_tail()
             if L.PROFILE.active:
+                # algorithmic bytes: the heads' real channels of Z read once, the conv output written once, the fp32 maps
                 L.PROFILE.note(f'head_combine_fwd {B}x{h}x{w} x{factor} ks{ks} N{ntot}', 0.0,
-                               (m_low * nz + (M * ntot if train else 0)) * z.element_size() + 4.0 * M * sum(int(hd[4].shape[0]) for hd in heads))
+                               (m_low * T + (M if train else 0)) * sum(inners) * z.element_size()
+                               + 4.0 * M * sum(int(hd[4].shape[0]) for hd in heads))
             L.check(L.LIB.vkocr_head_combine_fwd(_tag(dt), L.ptr(z), nz, B, h, w, factor, mode, ks, ntot, L.ptr(bias), ctypes.byref(ht),
                                                  L.ptr(conv), 0 if conv is None else conv.stride(3), COMBINE_ALGO, _s()),
                     'head_combine_fwd')
@@ -882,7 +902,7 @@ class HeadGroupFn(torch.autograd.Function):
                 dout = torch.zeros_like(outs[i])
             dout = dout.contiguous().float()
             if L.PROFILE.active:
-                L.PROFILE.note(f'head_tail_bwd rows{M} inner{inner} O{O}', 0.0, M * (2 * slot * conv.element_size() + 8 * O))
+                L.PROFILE.note(f'head_tail_bwd rows{M} inner{inner} O{O}', 0.0, M * (2 * inner * conv.element_size() + 8 * O))
             L.check(L.LIB.vkocr_head_tail_bwd(_tag(dt), L.ptr(conv[:, i * slot:(i + 1) * slot]), conv.stride(3), inner, slot,
                                               L.ptr(hd[2].detach()), L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), O,
                                               int(softplus[i]), L.ptr(outs[i]), L.ptr(dout), H * W, M,
@@ -897,12 +917,14 @@ class HeadGroupFn(torch.autograd.Function):
             nz = T * ntot
             dz = torch.empty((m_low, nz), dtype=dt, device=dev)
             if L.PROFILE.active:
-                L.PROFILE.note(f'head_combine_bwd {B}x{h}x{w} x{factor} ks{ks} N{ntot}', 0.0, (M * ntot + m_low * nz) * dz.element_size())
+                inner_sum = sum(int(hd[0].shape[0]) for hd in heads)
+                L.PROFILE.note(f'head_combine_bwd {B}x{h}x{w} x{factor} ks{ks} N{ntot}', 0.0, (M + m_low * T) * inner_sum * dz.element_size())
             L.check(L.LIB.vkocr_head_combine_bwd(_tag(dt), L.ptr(dconv), dconv.stride(3), B, h, w, factor, mode, ks, ntot, L.ptr(dz), nz,
                                                  COMBINE_ALGO, _s()), 'head_combine_bwd')
             del dconv
             gw = _zeros_f32(nz * C, dev)
-            gemm_tn(dz, 1, 1, m_low, nz, nz, 1, x, C, ld, _epilogue(gw, C, out_f32=True, accumulate=True, tn=(0, C, 1)))
+            gemm_tn(dz, 1, 1, m_low, nz, nz, 1, x, C, ld, _epilogue(gw, C, out_f32=True, accumulate=True, tn=(0, C, 1)),
+                    alg_ij=C * T * sum(int(hd[0].shape[0]) for hd in heads))
             for i, hd in enumerate(heads):
                 inner = int(hd[0].shape[0])
                 # gw[(tap * ntot + i * slot + n) * C + c]  ->  grad[(n * C + c) * T + tap]
@@ -911,7 +933,8 @@ class HeadGroupFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 wd, k_pad = packed_tapsplit_dgrad([hd[0] for hd in heads], dt, slot)
                 dx = alloc_nhwc(B, h, w, C, dt, dev)
-                gemm_nt(dz, 1, 1, m_low, nz, nz, 1, wd, k_pad, C, _epilogue(dx, dx.stride(3)))
+                gemm_nt(dz, 1, 1, m_low, nz, nz, 1, wd, k_pad, C, _epilogue(dx, dx.stride(3)),
+                        alg_kn=C * T * sum(int(hd[0].shape[0]) for hd in heads))
         else:
             # weight gradient of all heads in one pass over (dconv, up): G[n_total, C, T] in OIHW order, then per-head slices
             gw = _zeros_f32(ntot * C * T, dev)
@@ -1009,8 +1032,16 @@ class PreciseLossFn(torch.autograd.Function):
                 factors: Tuple[float, ...]) -> Tensor:
         prob_c, off_c, ang_c, dist_c = _f32c(prob), _f32c(off), _f32c(ang), _f32c(dist)
         gt_score, gt_mask = _f32c(gt_score), _f32c(gt_mask)
-        py, px, gt_off = _i64c(py), _i64c(px), _i64c(gt_off)
-        gt_ang, gt_dist = _f32c(gt_ang), _f32c(gt_dist)
+        py, px = _i64c(py), _i64c(px)
+        gt_off, gt_ang, gt_dist = _f32c(gt_off), _f32c(gt_ang), _f32c(gt_dist)   # int64 offsets (the dataset's) promote like F.smooth_l1_loss
+        B, _, H, W = prob_c.shape
+        P = int(py.shape[1]) if py.dim() == 2 else -1
+        if not (py.shape == px.shape == (B, P) and tuple(gt_off.shape) == (B, P, 2) and tuple(gt_ang.shape) == (B, P, 4)
+                and tuple(gt_dist.shape) == (B, P, 3) and off_c.shape[0] == ang_c.shape[0] == dist_c.shape[0] == gt_score.shape[0]
+                == gt_mask.shape[0] == B):
+            raise L.VkocrError(f'precise loss: label tensors do not match the prediction batch {B} / point count {P}: '
+                               f'y {tuple(py.shape)} x {tuple(px.shape)} offsets {tuple(gt_off.shape)} angles {tuple(gt_ang.shape)} '
+                               f'distances {tuple(gt_dist.shape)} score map {tuple(gt_score.shape)} mask {tuple(gt_mask.shape)}')
         B, _, H, W = prob_c.shape
         _, CH, CW = gt_mask.shape
         P = int(py.shape[1])

@@ -65,6 +65,8 @@ class GradientBuckets:
                  flatten_params: bool = False) -> None:
         plan = bucket_plan(model) if plan is None else plan
         params = dict(model.named_parameters())
+        self.ordered_params: List[nn.Parameter] = [p for _, p in model.named_parameters()]   # model.parameters() order
+        self.frozen: List[str] = [n for n, p in params.items() if not p.requires_grad]
         self.names: List[str] = []
         self.flat: List[Tensor] = []
         self.flat_params: List[Tensor] = []     # only with flatten_params: param.data of every member aliases a slice
@@ -137,6 +139,8 @@ class DataParallel:
             for p in model.parameters():
                 dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
                                group=process_group)
+            # an in-place write through .data does not move the version counters the packed-weight cache is keyed on
+            ops.PACK.bump()
         ops.set_grad_ready_hook(self._on_ready)
 
     # ------------------------------------------------------------------------------------------------ step protocol

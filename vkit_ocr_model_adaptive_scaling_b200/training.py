@@ -67,6 +67,9 @@ class FusedAdamW:
         self.buckets = buckets
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
+        if buckets.frozen:
+            raise ValueError('FusedAdamW steps whole flat buckets; parameters with requires_grad=False are not supported: '
+                             + ', '.join(buckets.frozen[:4]))
         self.exp_avg = [torch.zeros_like(t) for t in buckets.flat_params]
         self.exp_avg_sq = [torch.zeros_like(t) for t in buckets.flat_params]
         self.steps = 0
@@ -75,6 +78,58 @@ class FusedAdamW:
     def zero_grad(self) -> None:
         self.buckets.reattach()
         self.buckets.zero()
+
+    # ---- checkpointing in torch.optim.AdamW's layout (the reference saves / restores ``optimizer.state_dict()``,
+    # experiment/adaptive_scaling/train.py:94-96,307-322,597-603): parameters are numbered in ``model.parameters()`` order
+    def _param_slices(self):
+        """(bucket index, offset, parameter) in the model's own parameter order."""
+        where = {}
+        for b, members in enumerate(self.buckets.members):
+            offset = 0
+            for p in members:
+                where[id(p)] = (b, offset)
+                offset += p.numel()
+        return [(where[id(p)][0], where[id(p)][1], p) for p in self.buckets.ordered_params if id(p) in where]
+
+    def state_dict(self) -> Dict[str, object]:
+        state = {}
+        for idx, (b, off, p) in enumerate(self._param_slices()):
+            n = p.numel()
+            state[idx] = {'step': torch.tensor(float(self.steps)),
+                          'exp_avg': self.exp_avg[b][off:off + n].view(p.shape).detach().clone(),
+                          'exp_avg_sq': self.exp_avg_sq[b][off:off + n].view(p.shape).detach().clone()}
+        group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': self.weight_decay, 'amsgrad': False,
+                 'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None,
+                 'decoupled_weight_decay': True, 'params': list(range(len(state)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, state_dict: Dict[str, object]) -> None:
+        """Accepts ``torch.optim.AdamW.state_dict()`` of an optimizer built over ``model.parameters()`` (the reference's,
+        train.py:287-292) or this class's own."""
+        slices = self._param_slices()
+        state = state_dict['state']
+        groups = state_dict['param_groups']
+        if len(groups) != 1 or len(groups[0]['params']) != len(slices):
+            raise ValueError('FusedAdamW.load_state_dict expects one parameter group covering every model parameter')
+        g = groups[0]
+        self.lr, self.betas, self.eps, self.weight_decay = float(g['lr']), tuple(g['betas']), float(g['eps']), float(g['weight_decay'])
+        steps = set()
+        for idx, (b, off, p) in zip(g['params'], slices):
+            n = p.numel()
+            if idx not in state:          # torch creates the per-parameter state lazily at the first step
+                self.exp_avg[b][off:off + n].zero_()
+                self.exp_avg_sq[b][off:off + n].zero_()
+                steps.add(0)
+                continue
+            ent = state[idx]
+            if tuple(ent['exp_avg'].shape) != tuple(p.shape):
+                raise ValueError(f'optimizer state {idx}: shape {tuple(ent["exp_avg"].shape)} vs parameter {tuple(p.shape)}')
+            self.exp_avg[b][off:off + n].copy_(ent['exp_avg'].reshape(-1))
+            self.exp_avg_sq[b][off:off + n].copy_(ent['exp_avg_sq'].reshape(-1))
+            steps.add(int(float(ent['step'])))
+        if len(steps) > 1:
+            raise ValueError(f'FusedAdamW keeps ONE step counter; the state holds several: {sorted(steps)}')
+        self.steps = steps.pop() if steps else 0
 
     def grad_norm(self) -> Tensor:
         """Global L2 norm of the gradients as seen by the last ``step`` (device tensor)."""
