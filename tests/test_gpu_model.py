@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from _util import GRAD_TOL, NEGLIGIBLE, PER_TENSOR_GRAD_TOL, TOL, assert_close, compare_grads, oracle_params, rel_err
+from _util import (GRAD_TOL, NEGLIGIBLE, PER_TENSOR_GRAD_TOL, SMALL_SHAPE_BF16_GRAD_TOL, TOL, assert_close, compare_grads,
+                   oracle_params, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -135,11 +136,10 @@ def test_training_step_against_oracle(vk, neck, dtype):
     assert abs(float(pl) - float(pl_ref)) <= tol * abs(float(pl_ref)), (float(pl), float(pl_ref))
     autocast_err = None
     if dtype == torch.bfloat16:
-        # Yardstick for the bf16 mode: the reference's own algorithm (the oracle's torch ops) under stock
-        # torch.autocast(bfloat16) on this device, measured against the same fp64 result.  Through 18 backbone layers, the
-        # neck and the heads the gradient that reaches the stem (87 % of the gradient norm: the images are raw 0..255)
-        # carries every bf16 rounding of the chain; the bound on our gradient is the north-star 2e-2 or the error the
-        # reference itself shows in bf16, whichever is larger.
+        # For the record (not a relaxation): the reference's own algorithm (the oracle's torch ops) under stock
+        # torch.autocast(bfloat16) on this device against the same fp64 result.  Through 18 backbone layers, the neck and
+        # the heads the gradient that reaches the stem (87 % of the gradient norm: the images are raw 0..255) carries every
+        # bf16 rounding of the chain; the product must also be at least as accurate as this run.
         p32 = {k: v.detach().float().requires_grad_(True) for k, v in params.items()}
         f32 = lambda d: {k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in d.items()}
         rb32, pb32 = f32(rb), f32(pb)
@@ -153,7 +153,10 @@ def test_training_step_against_oracle(vk, neck, dtype):
         den = sum(float(params[k].grad.square().sum()) for k in params if params[k].grad is not None)
         autocast_err = (num / den) ** 0.5
         print(f'[{neck} step] reference algorithm under torch.autocast(bfloat16): global gradient rel L2 error {autocast_err:.3e}')
-    compare_grads(model, params, dtype, f'{neck} step', yardstick=autocast_err)
+    explicit = SMALL_SHAPE_BF16_GRAD_TOL.get(f'tiny/{neck}') if dtype == torch.bfloat16 else None
+    err = compare_grads(model, params, dtype, f'{neck} step', grad_tol=explicit)
+    if autocast_err is not None:
+        assert err <= autocast_err, f'{neck}: product gradient error {err:.3e} above stock autocast\'s {autocast_err:.3e}' 
 
 
 def test_train_mode_stochastic_depth_matches_reference_rng(vk):
@@ -244,8 +247,9 @@ def test_larger_configs_against_oracle(vk, size, neck, dtype):
     tol = TOL[dtype]
     assert abs(float(rl) - float(rl_ref)) <= tol * abs(float(rl_ref)), (float(rl), float(rl_ref))
     assert abs(float(pl) - float(pl_ref)) <= tol * abs(float(pl_ref)), (float(pl), float(pl_ref))
-    # bf16: the 40-layer SMALL / 1024-channel BASE chains are deeper than TINY's; same yardstick rule as the step test
-    compare_grads(model, params, dtype, f'{size}/{neck} step', yardstick=4e-2 if dtype == torch.bfloat16 else None)
+    # bf16: the 40-layer SMALL / 1024-channel BASE chains on ONE 64x96 image: the stated small-shape bound of _util.py
+    explicit = SMALL_SHAPE_BF16_GRAD_TOL[f'{size}/{neck}'] if dtype == torch.bfloat16 else None
+    compare_grads(model, params, dtype, f'{size}/{neck} step', grad_tol=explicit)
 
 
 def test_frozen_parameters_get_no_gradient(vk):
@@ -277,4 +281,5 @@ def test_frozen_parameters_get_no_gradient(vk):
         if n.startswith('backbone.'):
             assert g is None, f'{n}: a frozen parameter received a gradient'
         elif n.startswith('rough_'):
-            assert g is not None and torch.allclose(g, full[n], rtol=1e-5, atol=1e-8), n
+            assert g is not None, n
+            assert_close(g, full[n], 1e-5, f'{n} (fp32 atomics reorder sums run to run)', atol=1e-7)

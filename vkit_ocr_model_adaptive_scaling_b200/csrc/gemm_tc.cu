@@ -56,6 +56,25 @@ __device__ __forceinline__ void fd_divmod(uint32_t n, const FastDiv& f, uint32_t
     *r = n - *q * f.d;
 }
 
+// Compile-time description of a staged epilogue; RT = decide everything at run time.  The kernel is instantiated once
+// per kind (template parameter EPI): with every feature decided by run-time tests inside the 32-column chunk loop the
+// epilogue warps' code was ~1900 SASS instructions of mostly-untaken branches, and the plain bf16 store of a K = 384 GEMM
+// stalled on instruction fetch (ncu: stall_no_inst / branch_resolving on every flag test) -- 5.3 ms of epilogue against
+// 3.6 ms of MMA + TMA for [819200, 384] x [384, 7488].
+template <int ACT_, bool BIAS_, bool CS_, bool RES_, bool PRE_, bool RT_>
+struct EpiKind {
+    static constexpr int ACT = ACT_;
+    static constexpr bool BIAS = BIAS_, CS = CS_, RES = RES_, PRE = PRE_, RT = RT_;
+};
+template <int EPI> struct KindOf { using type = EpiKind<0, false, false, false, false, true>; };          // 0: run-time flags
+template <> struct KindOf<1> { using type = EpiKind<0, false, false, false, false, false>; };            // plain store
+template <> struct KindOf<2> { using type = EpiKind<0, true, false, false, false, false>; };             // + bias
+template <> struct KindOf<3> { using type = EpiKind<3, true, false, false, true, false>; };              // bias, GELU, gelu' side channel
+template <> struct KindOf<4> { using type = EpiKind<1, true, false, false, false, false>; };             // bias, GELU
+template <> struct KindOf<5> { using type = EpiKind<0, true, true, true, false, false>; };               // bias, layer scale, residual
+template <> struct KindOf<6> { using type = EpiKind<4, false, false, false, false, false>; };            // * aux (gelu' side channel)
+constexpr int NUM_EPI = 7;
+
 struct TcParams {
     int mode;                // 0 NT, 1 TN
     int batch, H, W;
@@ -76,6 +95,7 @@ struct TcParams {
     int M;                   // NT plain GEMM: number of rows
     long long units;
     int head_mode;           // NT: fused head tail epilogue (ht valid)
+    int epi_kind;            // which instance of the kernel (template parameter EPI) matches ep; 0 = the general one
     FastDiv fd_n, fd_x, fd_y, fd_i, fd_taps, fd_rpg;   // n_tiles, tiles_x, tiles_y, i_tiles, ks*ks, rows_per_group
     VkocrEpilogue ep;
     VkocrHeadTail ht;
@@ -261,7 +281,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo1
 // ------------------------------------------------------------------------------------------------- kernel
 // CTA2: compile-time, because every tcgen05 instruction of a kernel must name the same cta_group (and a kernel that uses
 // cta_group::2 can only be launched as clusters of two).
-template <bool CTA2>
+template <bool CTA2, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const __grid_constant__ TcParams p) {
@@ -555,6 +575,224 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
             const bool vec_ok = (p.mode == 0) && (!ep.out_f32) && ((ep.ldo & 7) == 0) && (!ep.out_pre || (ep.ld_pre & 7) == 0) &&
                                 (!ep.residual || (ep.ld_res & 7) == 0) && (ep.act != 2 || (ep.ld_aux & 7) == 0) && ep.act <= 2;
+            auto staged_tile = [&](auto kind) {
+                using K = decltype(kind);
+                // ---- fast path, one 32-column chunk at a time: each lane finishes its row in registers (bias, GELU / GELU',
+                // layer scale, drop-path mask, residual), the warp's 32 x 32 tile is staged in shared memory (64-byte rows,
+                // XOR-swizzled: conflict-free both ways) and leaves as coalesced 64-byte row segments, 8 rows per store
+                // instruction.  Residual / GELU' operands come in the same way, transposed through the tile.
+                const uint32_t wb = epi_base + (uint32_t)(warp - 4) * (uint32_t)EPI_TILE_BYTES;
+                const uint32_t my_row = wb + (uint32_t)lane * 64u;
+                const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+                const int r0 = q * 32;
+                const int act = K::RT ? ep.act : K::ACT;
+                const bool has_bias = K::RT ? (ep.bias != nullptr) : K::BIAS;
+                const bool has_cs = K::RT ? (ep.col_scale != nullptr) : K::CS;
+                const bool has_res = K::RT ? (ep.residual != nullptr) : K::RES;
+                const bool has_pre = K::RT ? (ep.out_pre != nullptr) : K::PRE;
+                const bool uses_extra = has_res || act == 2 || act == 4;
+                const __nv_bfloat16* esrc = has_res ? reinterpret_cast<const __nv_bfloat16*>(ep.residual)
+                                                    : ((act == 2 || act == 4) ? reinterpret_cast<const __nv_bfloat16*>(ep.aux) : nullptr);
+                const long long eld = has_res ? ep.ld_res : ep.ld_aux;
+                const float rs = (ep.row_scale && row_ok) ? __ldg(ep.row_scale + fd_div((uint32_t)row, p.fd_rpg)) : 1.f;
+                // global pixel index of the 4 staged rows this lane moves (rows 8*i + lane/4 of the warp's quarter)
+                int pix[4];
+                unsigned okmask = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = r0 + 8 * i + (lane >> 2);
+                    const int yy = t.y0 + (rl >> p.bw_shift), xx = t.x0 + (rl & (p.BW - 1));
+                    pix[i] = (t.b * p.H + yy) * p.W + xx;
+                    if (yy < p.H && xx < p.W) okmask |= 1u << i;
+                }
+                const int seg = lane & 3;
+                const int col_end = (t.n0 + BN < p.N) ? t.n0 + BN : p.N;   // 8-column groups are all-or-nothing
+                // Prefetch of the residual / aux tile of chunk cc of tile tt into the warp's second staging tile (same
+                // swizzled layout).  A synchronous load here exposes a full DRAM round trip per chunk, which bounded the
+                // K <= 384 GEMMs; the copy for the next chunk (or the next tile's first chunk) now flies during this one.
+                const uint32_t pwb = pre_base + (uint32_t)(warp - 4) * (uint32_t)EPI_TILE_BYTES;
+                auto issue_prefetch = [&](const Unit& tt, int cc) {
+                    const int ce = (tt.n0 + BN < p.N) ? tt.n0 + BN : p.N;
+                    const int pc = tt.n0 + cc * 32 + seg * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = 8 * i + (lane >> 2);
+                        const int rl = r0 + rr;
+                        const int yy = tt.y0 + (rl >> p.bw_shift), xx = tt.x0 + (rl & (p.BW - 1));
+                        const bool ok = yy < p.H && xx < p.W && pc < ce && cc < chunks;
+                        const long long px = (long long)((tt.b * p.H + yy) * p.W + xx);
+                        const void* src = ok ? static_cast<const void*>(esrc + px * eld + pc) : static_cast<const void*>(esrc);
+                        const int nbytes = ok ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pwb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4)),
+                                     "l"(src), "r"(nbytes) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                const bool prefetch = p.prefetch_extra && esrc != nullptr;
+                if (prefetch && !pf_issued) issue_prefetch(t, cpart);
+                pf_issued = false;
+                for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
+                    const int cb = c * 32;
+                    const int nb = t.n0 + cb;
+                    if (nb >= col_end || (p.skip_tma & 16)) break;   // debug bit 4: epilogue = barrier traffic only
+                    const int col = nb + seg * 8;
+                    uint4 extra[4];
+                    if (uses_extra && prefetch) {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) extra[j] = lds128(pwb + (uint32_t)lane * 64u + (((uint32_t)j ^ sw) << 4));
+                        __syncwarp();
+                        const int cn = c + EPI_WARPS / 4;
+                        if (cn < chunks && t.n0 + cn * 32 < col_end) {
+                            issue_prefetch(t, cn);
+                        } else if (w + wstride < wcount) {
+                            issue_prefetch(decode(unit_of(w + wstride)), cpart);
+                            pf_issued = true;
+                        }
+                    } else if (uses_extra) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = 8 * i + (lane >> 2);
+                            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                            if ((okmask & (1u << i)) && col < col_end)
+                                val = __ldg(reinterpret_cast<const uint4*>(esrc + (long long)pix[i] * eld + col));
+                            sts128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4), val);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) extra[j] = lds128(my_row + (((uint32_t)j ^ sw) << 4));
+                        __syncwarp();
+                    }
+                    // stage the lane's 32 finished values and write the warp's tile out as coalesced row segments
+                    auto store_packed = [&](const uint4 (&pk)[4], void* base, long long ld) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pk[j]);
+                        __syncwarp();
+                        if (col < col_end && !(p.skip_tma & 8)) {   // debug bit 3: no global stores
+                            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(base);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int rr = 8 * i + (lane >> 2);
+                                if (okmask & (1u << i)) {
+                                    const uint4 val = lds128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4));
+                                    *reinterpret_cast<uint4*>(obase + (long long)pix[i] * ld + col) = val;
+                                }
+                            }
+                        }
+                        __syncwarp();      // the tile is free again
+                    };
+                    auto store_tile = [&](const float* vals, void* base, long long ld) {
+                        uint4 pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pk[j] = pack8(vals + 8 * j);
+                        store_packed(pk, base, ld);
+                    };
+                    float v[32];
+                    {
+                        uint32_t acc[32];
+                        tc_ld32(taddr + (uint32_t)cb, acc);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                    }
+                    const bool full = nb + 32 <= p.N;
+                    if (has_bias && vec_in_smem && full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_vec + nb + j);
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else if (has_bias) {
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(ep.bias + nb + j) : 0.f;
+                        }
+                    }
+                    if (act == 3) {
+                        // GELU and its derivative share all transcendental work: the derivative is what the backward
+                        // needs (second output), the pre-activation itself is never read again
+                        uint4 pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float dg[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) vk_gelu_both(v[8 * j + e], &v[8 * j + e], &dg[e]);
+                            if (ep.row_scale) {       // stochastic-depth mask: side channel = m_b * gelu', dropped samples' activation = 0
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    dg[e] *= rs;
+                                    v[8 * j + e] = rs != 0.f ? v[8 * j + e] : 0.f;
+                                }
+                            }
+                            pk[j] = pack8_f16(dg);
+                        }
+                        if (has_pre) store_packed(pk, ep.out_pre, ep.ld_pre);
+                    } else {
+                        if (has_pre) store_tile(v, ep.out_pre, ep.ld_pre);      // pre-activation copy (acc + bias)
+                        if (act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
+                        } else if (act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float f[8];
+                                unpack8(extra[j], f);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
+                            }
+                        } else if (act == 4) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float f[8];
+                                unpack8_f16(extra[j], f);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[8 * j + e] *= f[e];
+                            }
+                        }
+                    }
+                    if (has_cs && vec_in_smem && full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(s_vec + 896 + nb + j);
+                            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+                        }
+                    } else if (has_cs) {
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nb + j));
+                                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= (nb + j < p.N) ? __ldg(ep.col_scale + nb + j) : 0.f;
+                        }
+                    }
+                    if (ep.row_scale && act != 3) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= rs;
+                    }
+                    if (has_res) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float f[8];
+                            unpack8(extra[j], f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
+                        }
+                    }
+                    store_tile(v, ep.out, ep.ldo);
+                }
+            };
+            if constexpr (EPI != 0) {
+                staged_tile(typename KindOf<EPI>::type{});
+            } else
             if (p.head_mode) {
                 // ---- fused head tail (one head per N tile): conv bias -> [conv output stored for the backward] ->
                 // LayerNorm over the head's `inner` columns -> exact GELU -> projection to O <= 4 maps (-> Softplus), all
@@ -702,212 +940,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 // the exchange buffers are rewritten only after the next tile's phase 1, which every warp of the quarter
                 // reaches after this point; the cpart-0 reader above is ordered by the next tile's first named barrier
             } else if (p.staged_store) {
-                // ---- fast path, one 32-column chunk at a time: each lane finishes its row in registers (bias, GELU / GELU',
-                // layer scale, drop-path mask, residual), the warp's 32 x 32 tile is staged in shared memory (64-byte rows,
-                // XOR-swizzled: conflict-free both ways) and leaves as coalesced 64-byte row segments, 8 rows per store
-                // instruction.  Residual / GELU' operands come in the same way, transposed through the tile.
-                const uint32_t wb = epi_base + (uint32_t)(warp - 4) * (uint32_t)EPI_TILE_BYTES;
-                const uint32_t my_row = wb + (uint32_t)lane * 64u;
-                const uint32_t sw = (uint32_t)((lane >> 1) & 3);
-                const int r0 = q * 32;
-                const __nv_bfloat16* esrc = ep.residual ? reinterpret_cast<const __nv_bfloat16*>(ep.residual)
-                                                        : ((ep.act == 2 || ep.act == 4) ? reinterpret_cast<const __nv_bfloat16*>(ep.aux) : nullptr);
-                const long long eld = ep.residual ? ep.ld_res : ep.ld_aux;
-                const float rs = (ep.row_scale && row_ok) ? __ldg(ep.row_scale + fd_div((uint32_t)row, p.fd_rpg)) : 1.f;
-                // global pixel index of the 4 staged rows this lane moves (rows 8*i + lane/4 of the warp's quarter)
-                int pix[4];
-                unsigned okmask = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rl = r0 + 8 * i + (lane >> 2);
-                    const int yy = t.y0 + (rl >> p.bw_shift), xx = t.x0 + (rl & (p.BW - 1));
-                    pix[i] = (t.b * p.H + yy) * p.W + xx;
-                    if (yy < p.H && xx < p.W) okmask |= 1u << i;
-                }
-                const int seg = lane & 3;
-                const int col_end = (t.n0 + BN < p.N) ? t.n0 + BN : p.N;   // 8-column groups are all-or-nothing
-                // Prefetch of the residual / aux tile of chunk cc of tile tt into the warp's second staging tile (same
-                // swizzled layout).  A synchronous load here exposes a full DRAM round trip per chunk, which bounded the
-                // K <= 384 GEMMs; the copy for the next chunk (or the next tile's first chunk) now flies during this one.
-                const uint32_t pwb = pre_base + (uint32_t)(warp - 4) * (uint32_t)EPI_TILE_BYTES;
-                auto issue_prefetch = [&](const Unit& tt, int cc) {
-                    const int ce = (tt.n0 + BN < p.N) ? tt.n0 + BN : p.N;
-                    const int pc = tt.n0 + cc * 32 + seg * 8;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rr = 8 * i + (lane >> 2);
-                        const int rl = r0 + rr;
-                        const int yy = tt.y0 + (rl >> p.bw_shift), xx = tt.x0 + (rl & (p.BW - 1));
-                        const bool ok = yy < p.H && xx < p.W && pc < ce && cc < chunks;
-                        const long long px = (long long)((tt.b * p.H + yy) * p.W + xx);
-                        const void* src = ok ? static_cast<const void*>(esrc + px * eld + pc) : static_cast<const void*>(esrc);
-                        const int nbytes = ok ? 16 : 0;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pwb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4)),
-                                     "l"(src), "r"(nbytes) : "memory");
-                    }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                };
-                const bool prefetch = p.prefetch_extra && esrc != nullptr;
-                if (prefetch && !pf_issued) issue_prefetch(t, cpart);
-                pf_issued = false;
-                for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
-                    const int cb = c * 32;
-                    const int nb = t.n0 + cb;
-                    if (nb >= col_end || (p.skip_tma & 16)) break;   // debug bit 4: epilogue = barrier traffic only
-                    const int col = nb + seg * 8;
-                    uint4 extra[4];
-                    if (prefetch) {
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) extra[j] = lds128(pwb + (uint32_t)lane * 64u + (((uint32_t)j ^ sw) << 4));
-                        __syncwarp();
-                        const int cn = c + EPI_WARPS / 4;
-                        if (cn < chunks && t.n0 + cn * 32 < col_end) {
-                            issue_prefetch(t, cn);
-                        } else if (w + wstride < wcount) {
-                            issue_prefetch(decode(unit_of(w + wstride)), cpart);
-                            pf_issued = true;
-                        }
-                    } else if (esrc) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int rr = 8 * i + (lane >> 2);
-                            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                            if ((okmask & (1u << i)) && col < col_end)
-                                val = __ldg(reinterpret_cast<const uint4*>(esrc + (long long)pix[i] * eld + col));
-                            sts128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4), val);
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) extra[j] = lds128(my_row + (((uint32_t)j ^ sw) << 4));
-                        __syncwarp();
-                    }
-                    // stage the lane's 32 finished values and write the warp's tile out as coalesced row segments
-                    auto store_packed = [&](const uint4 (&pk)[4], void* base, long long ld) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pk[j]);
-                        __syncwarp();
-                        if (col < col_end && !(p.skip_tma & 8)) {   // debug bit 3: no global stores
-                            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(base);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int rr = 8 * i + (lane >> 2);
-                                if (okmask & (1u << i)) {
-                                    const uint4 val = lds128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4));
-                                    *reinterpret_cast<uint4*>(obase + (long long)pix[i] * ld + col) = val;
-                                }
-                            }
-                        }
-                        __syncwarp();      // the tile is free again
-                    };
-                    auto store_tile = [&](const float* vals, void* base, long long ld) {
-                        uint4 pk[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) pk[j] = pack8(vals + 8 * j);
-                        store_packed(pk, base, ld);
-                    };
-                    float v[32];
-                    {
-                        uint32_t acc[32];
-                        tc_ld32(taddr + (uint32_t)cb, acc);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                    }
-                    const bool full = nb + 32 <= p.N;
-                    if (ep.bias && vec_in_smem && full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(s_vec + nb + j);
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
-                    } else if (ep.bias) {
-                        if (full) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
-                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(ep.bias + nb + j) : 0.f;
-                        }
-                    }
-                    if (ep.act == 3) {
-                        // GELU and its derivative share all transcendental work: the derivative is what the backward
-                        // needs (second output), the pre-activation itself is never read again
-                        uint4 pk[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float dg[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) vk_gelu_both(v[8 * j + e], &v[8 * j + e], &dg[e]);
-                            if (ep.row_scale) {       // stochastic-depth mask: side channel = m_b * gelu', dropped samples' activation = 0
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    dg[e] *= rs;
-                                    v[8 * j + e] = rs != 0.f ? v[8 * j + e] : 0.f;
-                                }
-                            }
-                            pk[j] = pack8_f16(dg);
-                        }
-                        if (ep.out_pre) store_packed(pk, ep.out_pre, ep.ld_pre);
-                    } else {
-                        if (ep.out_pre) store_tile(v, ep.out_pre, ep.ld_pre);      // pre-activation copy (acc + bias)
-                        if (ep.act == 1) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
-                        } else if (ep.act == 2) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float f[8];
-                                unpack8(extra[j], f);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) v[8 * j + e] *= vk_gelu_grad(f[e]);
-                            }
-                        } else if (ep.act == 4) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float f[8];
-                                unpack8_f16(extra[j], f);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) v[8 * j + e] *= f[e];
-                            }
-                        }
-                    }
-                    if (ep.col_scale && vec_in_smem && full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(s_vec + 896 + nb + j);
-                            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-                        }
-                    } else if (ep.col_scale) {
-                        if (full) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nb + j));
-                                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= (nb + j < p.N) ? __ldg(ep.col_scale + nb + j) : 0.f;
-                        }
-                    }
-                    if (ep.row_scale && ep.act != 3) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= rs;
-                    }
-                    if (ep.residual) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float f[8];
-                            unpack8(extra[j], f);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
-                        }
-                    }
-                    store_tile(v, ep.out, ep.ldo);
-                }
+                staged_tile(typename KindOf<0>::type{});
             } else
             for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
                 uint32_t acc[32];
@@ -1084,16 +1117,35 @@ void pick_box(int W, int H, int pixels, int* bw_out, int* bh_out) {
     }
 }
 
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams);
+template <int... I>
+struct KernelTable {
+    static TcKernel get(bool cta2, int epi) {
+        static const TcKernel one[] = {vkocr_gemm_tc_kernel<false, I>...};
+        static const TcKernel two[] = {vkocr_gemm_tc_kernel<true, I>...};
+        return cta2 ? two[epi] : one[epi];
+    }
+};
+using Kernels = KernelTable<0, 1, 2, 3, 4, 5, 6>;
+static_assert(NUM_EPI == 7, "KernelTable lists every epilogue kind");
+
 int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaStream_t stream) {
     static bool attr_set = false;
     const int smem = MAX_SMEM + 1024 + EPI_WARPS * EPI_TILE_BYTES + HEAD_PAR_BYTES + HEAD_XCH_BYTES + 256;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(vkocr_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(vkocr_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d, pair): %s", smem, cudaGetErrorString(e));
+        for (int c2 = 0; c2 < 2; ++c2)
+            for (int e = 0; e < NUM_EPI; ++e) {
+                cudaError_t err = cudaFuncSetAttribute(reinterpret_cast<const void*>(Kernels::get(c2 != 0, e)),
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                VK_REQUIRE(err == cudaSuccess, VKOCR_CUDA_ERROR, "cudaFuncSetAttribute(smem=%d, pair %d, kind %d): %s", smem, c2, e,
+                           cudaGetErrorString(err));
+            }
         attr_set = true;
     }
+    // the specialised instances only hold the staged NT epilogue
+    if (!(p.mode == 0 && p.staged_store && !p.head_mode) || p.epi_kind < 0 || p.epi_kind >= NUM_EPI) p.epi_kind = 0;
+    if (const char* e = getenv("VKOCR_EPI_GENERIC")) { if (atoi(e)) p.epi_kind = 0; }
+    const TcKernel kernel = Kernels::get(p.cta2 != 0, p.epi_kind);
     VK_REQUIRE(p.units < (1LL << 31), VKOCR_BAD_SHAPE, "gemm_tc: %lld work units", p.units);
     p.fd_n = make_fastdiv((uint32_t)p.n_tiles);
     p.fd_x = make_fastdiv((uint32_t)(p.tiles_x > 0 ? p.tiles_x : 1));
@@ -1126,14 +1178,14 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaSt
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, vkocr_gemm_tc_kernel<true>, mapA, mapB, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, mapA, mapB, p);
         VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaLaunchKernelEx(cluster 2): %s", cudaGetErrorString(e));
         VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
         return VKOCR_OK;
     }
     const int grid = (int)(p.units < sms ? p.units : sms);
     if (grid <= 0) return VKOCR_OK;
-    vkocr_gemm_tc_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, p);
+    kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, p);
     VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
     return VKOCR_OK;
 }
@@ -1200,6 +1252,17 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
     p.prefetch_extra = p.staged_store && (ep->residual || ep->act == 2 || ep->act == 4) && !p.head_mode &&
                        g->ks * g->ks * p.kb_per_tap <= 12 && (MAX_SMEM - PREFETCH_BYTES) / p.stage_bytes >= 2;
     if (const char* e = getenv("VKOCR_NO_PREFETCH")) { if (atoi(e)) p.prefetch_extra = 0; }
+    {
+        const bool b = ep->bias != nullptr, cs = ep->col_scale != nullptr, res = ep->residual != nullptr, pre = ep->out_pre != nullptr;
+        const bool rsc = ep->row_scale != nullptr;
+        p.epi_kind = 0;
+        if (ep->act == 0 && !b && !cs && !res && !pre && !rsc) p.epi_kind = 1;
+        else if (ep->act == 0 && b && !cs && !res && !pre && !rsc) p.epi_kind = 2;
+        else if (ep->act == 3 && b && !cs && !res && pre) p.epi_kind = 3;
+        else if (ep->act == 1 && b && !cs && !res && !pre && !rsc) p.epi_kind = 4;
+        else if (ep->act == 0 && b && cs && res && !pre) p.epi_kind = 5;
+        else if (ep->act == 4 && !b && !cs && !res && !pre && !rsc) p.epi_kind = 6;
+    }
     return launch(mapA, mapB, p, stream);
 }
 
