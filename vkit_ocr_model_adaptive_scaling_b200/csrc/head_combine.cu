@@ -886,7 +886,7 @@ int vkocr_head_combine_fwd(int dtype, const void* z, long long ld_z, int B, int 
     VK_REQUIRE(factor >= 1 && factor <= 8 && (mode == 0 || mode == 1) && (ks == 1 || ks == 3 || ks == 5), VKOCR_BAD_SHAPE,
                "head_combine_fwd: factor %d mode %d kernel %d", factor, mode, ks);
     const int V = dtype == VKOCR_F32 ? 4 : 8;
-    VK_REQUIRE(heads->num_heads >= 1 && heads->num_heads <= VKOCR_MAX_HEADS && heads->slot % 16 == 0 && heads->slot <= 256 &&
+    VK_REQUIRE(heads->num_heads >= 1 && heads->num_heads <= VKOCR_MAX_HEADS && heads->slot % 8 == 0 && heads->slot <= 256 &&
                    ntot == heads->num_heads * heads->slot,
                VKOCR_BAD_SHAPE, "head_combine_fwd: %d heads x slot %d vs ntot %d", heads->num_heads, heads->slot, ntot);
     VK_REQUIRE(ld_z % V == 0 && ld_z >= (long long)ks * ks * ntot && (reinterpret_cast<uintptr_t>(z) & 15) == 0, VKOCR_BAD_ALIGN,

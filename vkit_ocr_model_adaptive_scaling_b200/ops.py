@@ -802,7 +802,10 @@ class HeadGroupFn(torch.autograd.Function):
         H, W = h * factor, w * factor
         inners = [int(hd[0].shape[0]) for hd in heads]
         ks = int(heads[0][0].shape[2])
-        slot = _ceil_to(max(inners), 16)
+        tapsplit = factor > 1 and TAPSPLIT and nh <= L.MAX_HEADS and max(inners) <= 256 and max(int(hd[4].shape[0]) for hd in heads) <= 4
+        # columns per head: the convolve-first path only needs whole 16-byte vectors (4 x 200 instead of 4 x 208 columns for
+        # the precise group: 4 % less Z / dZ traffic and GEMM work); the fused-epilogue GEMM needs a multiple of the UMMA N step
+        slot = _ceil_to(max(inners), 8 if tapsplit else 16)
         ntot = slot * nh
         bias = torch.zeros(ntot, dtype=torch.float32, device=dev)
         for i, hd in enumerate(heads):
@@ -821,7 +824,6 @@ class HeadGroupFn(torch.autograd.Function):
                 ht.inner[i], ht.out_channels[i], ht.softplus[i] = inners[i], int(hd[4].shape[0]), int(softplus[i])
             return ht
 
-        tapsplit = factor > 1 and TAPSPLIT and nh <= L.MAX_HEADS and slot <= 256 and max(int(hd[4].shape[0]) for hd in heads) <= 4
         up = None
         if tapsplit:
             # convolve first, resample after (csrc/head_combine.cu): Z = X . W_tap^T on the LOW-resolution map -- factor^2
