@@ -20,6 +20,8 @@
 // Z to per-output-row partial sums V in shared memory (every Z element is loaded and converted once per block), then
 // every output pixel combines six V entries.
 #include "gemm_common.cuh"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -300,7 +302,6 @@ hc_bwd_generic_kernel(const T* __restrict__ dc, long long ld_dc, Geom g, int wid
 // the two output pixels of a (row, low-res column) run together (shared V loads, interleaved dependency chains), and the
 // warp reductions keep only half of the values per butterfly round.
 constexpr int HC_TJ = 8;            // low-res columns per tile
-constexpr int HC_R = 2;             // low-res rows per tile
 constexpr int HC_QL = HC_TJ + 2;    // columns of V kept per tile (one halo column each side)
 __device__ __forceinline__ constexpr int hc_pos(int a, int d, int k) {   // offset of the k-th source row of (parity a, tap d)
     // a=0: (-1,0) (-1,0) (0,1);  a=1: (-1,0) (0,1) (0,1)
@@ -483,8 +484,8 @@ __device__ __forceinline__ void hc_tail2(const float2 (&c0)[NVL][NP], const floa
     }
 }
 
-template <typename T, int NVL, int O>
-__global__ void __launch_bounds__(256, 2)
+template <typename T, int NVL, int O, int HC_R, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ conv, long long ld_conv, int cw, int tiles_j,
                   int tiles_i, long long ntiles) {
     constexpr int V = VkVec<T>::N;
@@ -839,19 +840,32 @@ int hc_launch_fwd(const void* z, const Geom& g, const HeadArgs& hd, void* conv, 
     if (fast) {
         const int cvn = (hd.inner + V - 1) / V;
         const int cw = cvn * V;
-        const size_t smem = ((size_t)HC_R * 2 * 3 * HC_QL * cw + cw) * sizeof(float) + (HC_R * 2 * 3 * 2 + HC_TJ * 2 * 3) * sizeof(float2);
-        if (smem <= 200 * 1024) {
-            const int tiles_j = vk_cdiv(g.w, HC_TJ), tiles_i = vk_cdiv(g.h, HC_R);
+        int variant = 0;     // 0: 2 rows x 256 threads x 2 blocks/SM; 1: 1 row x 128 threads x 4 blocks/SM; 2: 2 rows x 384 threads x 2 blocks/SM
+        if (const char* e = getenv("VKOCR_HC_VARIANT")) variant = atoi(e);
+        auto run = [&](auto rtag, auto ttag, auto btag) -> int {
+            constexpr int R = decltype(rtag)::value, THREADS = decltype(ttag)::value, MINB = decltype(btag)::value;
+            const size_t smem = ((size_t)R * 2 * 3 * HC_QL * cw + cw) * sizeof(float) + (R * 2 * 3 * 2 + HC_TJ * 2 * 3) * sizeof(float2);
+            if (smem > 200 * 1024) return -1;
+            const int tiles_j = vk_cdiv(g.w, HC_TJ), tiles_i = vk_cdiv(g.h, R);
             const long long ntiles = (long long)g.B * tiles_i * tiles_j;
-            cudaError_t e = cudaFuncSetAttribute(hc_fwd_2x3_kernel<T, NVL, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            auto kern = hc_fwd_2x3_kernel<T, NVL, O, R, THREADS, MINB>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return 2;
-            const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+            int per_sm = (int)((220 * 1024) / (smem + 1024));
+            if (per_sm > MINB) per_sm = MINB;
+            if (per_sm < 1) per_sm = 1;
             long long blocks = (long long)vkocr_sm_count() * per_sm;
             if (blocks > ntiles) blocks = ntiles;
-            hc_fwd_2x3_kernel<T, NVL, O><<<(unsigned)blocks, 256, smem, s>>>(reinterpret_cast<const T*>(z), g, hd, reinterpret_cast<T*>(conv),
-                                                                             ld_conv, cw, tiles_j, tiles_i, ntiles);
+            kern<<<(unsigned)blocks, THREADS, smem, s>>>(reinterpret_cast<const T*>(z), g, hd, reinterpret_cast<T*>(conv), ld_conv, cw, tiles_j,
+                                                         tiles_i, ntiles);
             return 0;
-        }
+        };
+        using std::integral_constant;
+        int rc;
+        if (variant == 1) rc = run(integral_constant<int, 1>{}, integral_constant<int, 128>{}, integral_constant<int, 4>{});
+        else if (variant == 2) rc = run(integral_constant<int, 2>{}, integral_constant<int, 384>{}, integral_constant<int, 2>{});
+        else rc = run(integral_constant<int, 2>{}, integral_constant<int, 256>{}, integral_constant<int, 2>{});
+        if (rc >= 0) return rc;
     }
     long long blocks = (rows + 7) / 8;
     const long long cap = (long long)vkocr_sm_count() * 8;
