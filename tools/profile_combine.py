@@ -1,8 +1,8 @@
 """GPU: the 'convolve first, resample after' head path of the precise head group at the full B=32 / 640x640 shapes, one
 C-ABI call per line (for CUDA-event timing and as the target of ncu captures):
-  Z GEMM        [819200, 384] x [384, 9*832]              (vkocr_gemm_nt)
+  Z GEMM        [819200, 384] x [384, 9*800]              (vkocr_gemm_nt)
   combine fwd   Z -> 4 heads' conv outputs + prediction maps   (vkocr_head_combine_fwd)
-  combine bwd   d(conv) [3276800, 832] -> dZ                   (vkocr_head_combine_bwd)
+  combine bwd   d(conv) [3276800, 800] -> dZ                   (vkocr_head_combine_bwd)
   dgrad / wgrad GEMMs on (dZ, x)
 python tools/profile_combine.py [reps] [what ...]   what: z fwd bwd dgrad wgrad (default all)"""
 import ctypes
@@ -23,7 +23,7 @@ inners, outs_c, soft = (192, 193, 194, 194), (1, 2, 4, 4), (0, 0, 0, 1)
 if os.environ.get('ROUGH'):
     inners, outs_c, soft = (192, 192), (1, 1), (0, 1)
 nh = len(inners)
-slot = (max(inners) + 15) // 16 * 16
+slot = (max(inners) + 7) // 8 * 8       # the product's slot width on the convolve-first path (ops.HeadGroupFn)
 ntot, T = slot * nh, 9
 nz = T * ntot
 H, W = 2 * h, 2 * w
@@ -45,7 +45,8 @@ for i in range(nh):
     ht.gamma[i], ht.beta[i], ht.w2[i], ht.b2[i] = (t.data_ptr() for t in par[i])
     ht.out[i] = outs[i].data_ptr()
     ht.inner[i], ht.out_channels[i], ht.softplus[i] = inners[i], outs_c[i], soft[i]
-wd = (torch.randn(C, nz, device=dev) * 0.05).to(BF)
+k_pad = (nz + 63) // 64 * 64
+wd = (torch.randn(C, k_pad, device=dev) * 0.05).to(BF)
 gw = torch.zeros(nz * C, device=dev)
 dx = ops.alloc_nhwc(B, h, w, C, BF, dev)
 s = ops._s
@@ -75,7 +76,7 @@ for r in range(reps):
         timed('combine bwd', lambda: L.check(L.LIB.vkocr_head_combine_bwd(1, L.ptr(dconv), ntot, B, h, w, 2, 0, 3, ntot, L.ptr(dz), nz, algo, s())),
               0.0, 2.0 * (m_low * nz + M * ntot))
     if 'dgrad' in what:
-        timed('dgrad gemm', lambda: ops.gemm_nt(dz, 1, 1, m_low, nz, nz, 1, wd, nz, C, ops._epilogue(dx, dx.stride(3))), 2.0 * m_low * C * nz,
+        timed('dgrad gemm', lambda: ops.gemm_nt(dz, 1, 1, m_low, nz, nz, 1, wd, k_pad, C, ops._epilogue(dx, dx.stride(3))), 2.0 * m_low * C * nz,
               2.0 * m_low * (C + nz))
     if 'wgrad' in what:
         timed('wgrad gemm', lambda: ops.gemm_tn(dz, 1, 1, m_low, nz, nz, 1, x, C, x.stride(3),

@@ -27,7 +27,7 @@ fi
 
 if [ "$WHAT" = ncu ]; then
     # launch list of the bench command (the same command exited 0 without ncu in the `bench` pass)
-    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1700 --csv --log-file $O/launches_${TAG}.csv \
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3900 -c 1400 --csv --log-file $O/launches_${TAG}.csv \
         python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras --no-eager-baseline > $O/${TAG}_ncu_bench.log 2>&1
     capture() {   # name, kernel regex, launches to skip, launches to capture, command...
         local name=$1 regex=$2 skip=$3 count=$4; shift 4
