@@ -663,8 +663,8 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
                 for (int jj = 0; jj < NVL; ++jj) {
                     const int ch0 = (lane + 32 * jj) * V;
                     if (ch0 < hd.inner) {
-                        *reinterpret_cast<uint4*>(cr + ch0) = HcPairs<T>::pack(c0[jj]);
-                        *reinterpret_cast<uint4*>(cr + ld_conv + ch0) = HcPairs<T>::pack(c1[jj]);
+                        __stcs(reinterpret_cast<uint4*>(cr + ch0), HcPairs<T>::pack(c0[jj]));
+                        __stcs(reinterpret_cast<uint4*>(cr + ld_conv + ch0), HcPairs<T>::pack(c1[jj]));
                     }
                 }
             }
@@ -822,7 +822,7 @@ hc_bwd_2x3_kernel(const T* __restrict__ dc, long long ld_dc, Geom g, int width, 
                         for (int o = 1; o < 4; ++o)
 #pragma unroll
                             for (int e = 0; e < NP; ++e) acc[e] = vk_fma2(cf[dx][o], ev[2 - dx + o][e], acc[e]);
-                        *reinterpret_cast<uint4*>(dst + (long long)(dy * 3 + dx) * g.ntot) = HcPairs<T>::pack(acc);
+                        __stcs(reinterpret_cast<uint4*>(dst + (long long)(dy * 3 + dx) * g.ntot), HcPairs<T>::pack(acc));   // write-once stream: keep L2 for the dconv halo rows
                     }
                 }
             }
