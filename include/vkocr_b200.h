@@ -271,6 +271,11 @@ int vkocr_scatter_add_f32(const float* g, long long g0, long long g1, long long 
                           long long y1, long long y2, void* stream);
 int vkocr_scale_rows(int dtype, const void* x, long long ld_x, void* y, long long ld_y, long long rows, int C,
                      const float* scale, int rows_per_group, void* stream);
+/* x[row, col0] = first, x[row, col0+1 .. col0+ncols) = 0: the constant column appended to the LayerNorm output so that the
+ * weight-gradient GEMM of the MLP up-projection (model/convnext.py:33) also delivers its bias gradient. */
+int vkocr_set_columns(int dtype, void* x, long long ld, long long rows, int col0, int ncols, float first, void* stream);
+/* Asynchronous zero fill of caller memory on `stream` (atomic-accumulate workspaces, gradient buckets). */
+int vkocr_zero(void* p, long long bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ optimizer tail
  * Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step over ~300 tensors

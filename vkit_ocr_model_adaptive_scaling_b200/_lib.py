@@ -113,6 +113,8 @@ _SIGNATURES = {
     'vkocr_mlp2_grad_finalize': [c_void_p, c_ll, c_float, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p],
     'vkocr_accumulate_f32': [c_void_p, c_void_p, c_ll, c_void_p],
+    'vkocr_set_columns': [c_int, c_void_p, c_ll, c_ll, c_int, c_int, c_float, c_void_p],
+    'vkocr_zero': [c_void_p, c_ll, c_void_p],
     'vkocr_scale_rows': [c_int, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p],
     'vkocr_ingest_image_u8': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     'vkocr_rough_postprocess': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],

@@ -398,8 +398,24 @@ def _ones_tail(dtype: torch.dtype, device) -> Tensor:
     return _ONES_TAIL[key]
 
 
+import os as _os
+_TORCH_ZERO = _os.environ.get('VKOCR_TORCH_ZERO') == '1'   # A/B switch for experiments
+
+
+def zero_(t: Tensor) -> Tensor:
+    """Asynchronous zero fill on the current stream through the C ABI (no eager PyTorch kernel on the hot path)."""
+    if _TORCH_ZERO:
+        return t.zero_()
+    L.check(L.LIB.vkocr_zero(L.ptr(t), t.numel() * t.element_size(), _s()), 'zero')
+    return t
+
+
 def _zeros_f32(n: int, device) -> Tensor:
-    return torch.zeros(n, dtype=torch.float32, device=device)
+    return zero_(torch.empty(n, dtype=torch.float32, device=device))
+
+
+def _zeros(n: int, dtype: torch.dtype, device) -> Tensor:
+    return zero_(torch.empty(n, dtype=dtype, device=device))
 
 
 def _needs_grad(ctx) -> bool:
@@ -498,7 +514,7 @@ class ConvNextLayerFn(torch.autograd.Function):
             # gradient of the up-projection (column sums of dH) as column C of its product, for 8 % more J instead of a
             # separate pass over the (M, 4C) gradient
             lnbuf = torch.empty((B, H, W, C + 8), dtype=dt, device=dev)
-            lnbuf[..., C:] = _ones_tail(dt, dev)
+            L.check(L.LIB.vkocr_set_columns(_tag(dt), L.ptr(lnbuf), C + 8, M, C, 8, 1.0, _s()), 'set_columns')
             lnout = lnbuf[..., :C].permute(0, 3, 1, 2)
         else:
             lnout = alloc_nhwc(B, H, W, C, dt, dev)
@@ -561,9 +577,9 @@ class ConvNextLayerFn(torch.autograd.Function):
         if ldl == C + 8:          # LN_out carries the ones channel (see forward): dW1 and db1 from one GEMM
             gwb = _zeros_f32(hid * (C + 8), dev)
             gemm_tn(dh, 1, 1, M, hid, hid, 1, lnout, C + 8, ldl, _epilogue(gwb, C + 8, out_f32=True, accumulate=True, tn=(0, C + 8, 1)))
-            gwb = gwb.view(hid, C + 8)
-            grad_buffer(w1).add_(gwb[:, :C])
-            grad_buffer(b1).add_(gwb[:, C])
+            L.check(L.LIB.vkocr_scatter_add_f32(L.ptr(gwb), C + 8, 0, 1, hid, 1, C, L.ptr(grad_buffer(w1)), C, 0, 1, _s()), 'scatter_add_f32')
+            L.check(L.LIB.vkocr_scatter_add_f32(ctypes.c_void_p(gwb.data_ptr() + 4 * C), C + 8, 0, 0, hid, 1, 1, L.ptr(grad_buffer(b1)), 1, 0, 0,
+                                                _s()), 'scatter_add_f32')
         else:
             colsum(dh, hid, M, hid, grad_buffer(b1))
             gemm_tn(dh, 1, 1, M, hid, hid, 1, lnout, C, ldl, _epilogue(grad_buffer(w1), C, out_f32=True, accumulate=True, tn=(0, C, 1)))
@@ -807,9 +823,11 @@ class HeadGroupFn(torch.autograd.Function):
         # the precise group: 4 % less Z / dZ traffic and GEMM work); the fused-epilogue GEMM needs a multiple of the UMMA N step
         slot = _ceil_to(max(inners), 8 if tapsplit else 16)
         ntot = slot * nh
-        bias = torch.zeros(ntot, dtype=torch.float32, device=dev)
-        for i, hd in enumerate(heads):
-            bias[i * slot:i * slot + inners[i]].copy_(hd[1].detach())   # tiny staging copy of the conv biases
+        def fill_bias(buf: Tensor) -> None:
+            for i, hd in enumerate(heads):
+                _pack(hd[1].detach(), 0, 0, 1, 1, 1, inners[i], 0, None, buf, i * slot, 0, 0)
+        # the heads' conv biases side by side in slot order: a cached, kernel-written staging vector (pad columns stay 0)
+        bias = PACK.get(('head_bias', tuple(id(hd[1]) for hd in heads), slot), [hd[1] for hd in heads], (ntot,), torch.float32, fill_bias)
         train = _needs_grad(ctx)
         M = B * H * W
         outs = [torch.empty((B, int(hd[4].shape[0]), H, W), dtype=torch.float32, device=dev) for hd in heads]
@@ -988,7 +1006,7 @@ class RoughLossFn(torch.autograd.Function):
         B, _, H, W = logit_c.shape
         _, CH, CW = gt_mask.shape
         dev = logit_c.device
-        sums = torch.zeros(6, dtype=torch.float64, device=dev)
+        sums = _zeros(6, torch.float64, dev)
         coef = torch.empty(6, dtype=torch.float32, device=dev)
         L.check(L.LIB.vkocr_rough_loss_fwd(L.ptr(logit_c), L.ptr(height_c), L.ptr(gt_mask), L.ptr(gt_score), B, H, W, up, left, CH, CW,
                                            height_min, score_min, focal_factor, dice_factor, l1_factor, L.ptr(sums), L.ptr(coef), _s()),
@@ -1049,7 +1067,7 @@ class PreciseLossFn(torch.autograd.Function):
         P = int(py.shape[1])
         dev = prob_c.device
         fac = _device_factors(tuple(float(f) for f in factors), dev)
-        sums = torch.zeros(8, dtype=torch.float64, device=dev)
+        sums = _zeros(8, torch.float64, dev)
         coef = torch.empty(3, dtype=torch.float32, device=dev)
         L.check(L.LIB.vkocr_precise_loss_fwd(L.ptr(prob_c), L.ptr(off_c), L.ptr(ang_c), L.ptr(dist_c), L.ptr(gt_score), L.ptr(gt_mask),
                                              B, H, W, up, left, CH, CW, L.ptr(py), L.ptr(px), L.ptr(gt_off), L.ptr(gt_ang),
@@ -1066,9 +1084,7 @@ class PreciseLossFn(torch.autograd.Function):
         B, H, W, up, left, CH, CW, P, beta = ctx.meta
         gout = gout.contiguous().float()
         dprob = torch.empty_like(prob)
-        doff = torch.zeros_like(off)
-        dang = torch.zeros_like(ang)
-        ddist = torch.zeros_like(dist)
+        doff, dang, ddist = zero_(torch.empty_like(off)), zero_(torch.empty_like(ang)), zero_(torch.empty_like(dist))
         L.check(L.LIB.vkocr_precise_loss_bwd(L.ptr(prob), L.ptr(off), L.ptr(ang), L.ptr(dist), L.ptr(gt_score), L.ptr(gt_mask), B, H, W,
                                              up, left, CH, CW, L.ptr(py), L.ptr(px), L.ptr(gt_off), L.ptr(gt_ang), L.ptr(gt_dist), P,
                                              beta, L.ptr(ctx.fac), L.ptr(ctx.coef), L.ptr(gout), L.ptr(dprob), L.ptr(doff),

@@ -96,7 +96,10 @@ class GradientBuckets:
 
     def zero(self) -> None:
         for flat in self.flat:
-            flat.zero_()
+            if flat.is_cuda:
+                ops.zero_(flat)
+            else:
+                flat.zero_()
 
     def reattach(self) -> None:
         """Re-point ``param.grad`` at the buckets (after a ``zero_grad(set_to_none=True)``)."""
