@@ -203,6 +203,26 @@ int vkocr_head_tail_bwd(int dtype, const void* x, long long ld_x, int inner, int
                         long long rows, void* dx, long long ld_dx, float* dgamma, float* dbeta, float* dw2, float* db2,
                         float* dbias, void* stream);
 
+/* ------------------------------------------------------------------------------- label-point backward of the heads
+ * Three of the four precise heads enter the loss only through their values at the (B, P) label points
+ * (get_label_point_feature, loss_function/adaptive_scaling.py:167-179,235-260), so their upstream gradient maps are zero
+ * elsewhere and the dense backward of model/upernext.py:233-248 / model/fpn.py:193-208 multiplies zeros.  These entry points
+ * compute the SAME gradients from the E = B*P label pixels only:
+ * vkocr_points_claim: pix_index[e] = b*H*W + y*W + x for the first entry on a pixel, -1 for duplicates / outside points
+ *   (the gradient map already holds the sum of duplicates); `owner`: B*H*W ints zeroed by the caller.
+ * vkocr_head_tail_bwd_points: vkocr_head_tail_bwd over the listed pixel rows; dx = [E, ld_dx] gradient rows G.
+ * vkocr_gather_up_taps: A[e, tap*C + c] = up(x)[r_e + dy - k/2, s_e + dx - k/2, c]; then dW_tap = G^T . A_tap (vkocr_gemm_tn).
+ * vkocr_scatter_up_taps: dX += adjoint of up-sample + tap shift applied to U = G . W (vkocr_gemm_nt), atomically. */
+int vkocr_points_claim(const long long* py, const long long* px, int B, int P, int H, int W, int* owner, int* pix_index, void* stream);
+int vkocr_head_tail_bwd_points(int dtype, const void* x, long long ld_x, int inner, int slice_w, const float* gamma, const float* beta,
+                               const float* w2, int O, int softplus, const float* out, const float* dout, long long pixels_per_image,
+                               const int* row_index, long long entries, void* dx, long long ld_dx, float* dgamma, float* dbeta,
+                               float* dw2, float* db2, float* dbias, void* stream);
+int vkocr_gather_up_taps(int dtype, const void* x, long long ld_x, int B, int h, int w, int C, int factor, int mode, int ks,
+                         const int* pix_index, int E, void* a, void* stream);
+int vkocr_scatter_up_taps(int dtype, const void* u, int B, int h, int w, int C, int factor, int mode, int ks, const int* pix_index, int E,
+                          void* dx, long long ld_dx, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ fused losses
  * vkocr_rough_loss_*: AdaptiveScalingRoughLossFunction.__call__ (loss_function/adaptive_scaling.py:53-131): core-box
  *   crop, 5*focal + 1*dice + 1*masked log-space smooth-L1 (factors are arguments).  sums: 6 zeroed doubles; coef: 6

@@ -308,3 +308,47 @@ def test_rough_loss_with_hard_negative_bce_term(vk):
     assert abs(float(ref) - float(plain)) > 1e-3                       # the term is really on
     assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref)), (float(loss), float(ref))
     compare_grads(model, params, torch.float32, 'rough step with the hard-negative BCE term')
+
+
+@pytest.mark.parametrize('neck', ['upernext', 'fpn'])
+def test_label_point_backward_equals_dense_backward(vk, neck):
+    """The offset / angle / distance heads receive gradient only at the label points; their backward runs on those pixels
+    alone (csrc/head_sparse.cu).  It must reproduce the dense backward: duplicate points, points on the map border and in
+    the corners, negative (wrapped) indices, fp32 mode."""
+    from oracle import synth
+    from vkit_ocr_model_adaptive_scaling_b200 import ops
+    dev = torch.device('cuda')
+    B, H, W, P = 2, 64, 96, 12
+    model = _build(vk, neck)
+    model.load_state_dict(synth.synth_state_dict('tiny', neck, seed=17), strict=True)
+    model.to(dev).eval()
+    pb = _to(synth.synth_precise_batch(B, H, W, points=P, seed=4, inset=2), dev)
+    y, x = pb['downsampled_label_point_y'].clone(), pb['downsampled_label_point_x'].clone()
+    h2, w2 = H // 2, W // 2
+    y[0, 0], x[0, 0] = 0, 0                      # corners and borders
+    y[0, 1], x[0, 1] = h2 - 1, w2 - 1
+    y[0, 2], x[0, 2] = 0, w2 - 1
+    y[1, 0], x[1, 0] = h2 - 1, 5
+    y[1, 1], x[1, 1] = y[1, 2], x[1, 2]          # a duplicate
+    y[1, 3], x[1, 3] = y[1, 4] - h2, x[1, 4] - w2    # the same pixel again, through wrapped negative indices
+    pb['downsampled_label_point_y'], pb['downsampled_label_point_x'] = y, x
+    fn = vk.loss_function.AdaptiveScalingPreciseLossFunction(vk.loss_function.AdaptiveScalingPreciseLossFunctionConifg())
+    image = pb['image']
+    results = []
+    try:
+        for sparse in (True, False):
+            ops.SPARSE_BACKWARD = sparse
+            model.zero_grad(set_to_none=True)
+            launches0 = vk._lib.LIB.vkocr_launch_count()
+            with vk.precision(torch.float32):
+                outs = model.forward_precise(image)
+                fn(None, *outs, **{k: pb[k] for k in PRECISE_KEYS}).backward()
+            torch.cuda.synchronize()
+            results.append(({n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None},
+                            vk._lib.LIB.vkocr_launch_count() - launches0))
+    finally:
+        ops.SPARSE_BACKWARD = True
+    (gs, _), (gd, _) = results
+    assert set(gs) == set(gd)       # the backbone gradients carry the data gradient of the heads
+    for n in gd:
+        assert_close(gs[n], gd[n], 5e-5, f'grad {n}', atol=1e-7)

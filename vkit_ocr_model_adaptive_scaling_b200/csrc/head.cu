@@ -217,7 +217,9 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
                      const float* __restrict__ beta, const float* __restrict__ w2, int softplus, const float* __restrict__ out,
                      const float* __restrict__ dout, unsigned ppi, float inv_ppi, unsigned rows, T* __restrict__ dx,
                      long long ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw2,
-                     float* __restrict__ db2, float* __restrict__ dbias) {
+                     float* __restrict__ db2, float* __restrict__ dbias, const int* __restrict__ row_index) {
+    // row_index (nullable): entry e reads pixel row row_index[e] (< 0: no pixel, the entry's gradient row is zero) and writes
+    // dx row e -- the label-point form used when the upstream gradient is zero outside a short list of pixels
     constexpr int V = VkVec<T>::N;
     constexpr int P = V / 2;
     constexpr int CW = 32 * NVL * V;
@@ -263,11 +265,13 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
     const int wib = threadIdx.x >> 5;
     // issue one row: the lane's conv vectors, and (lanes < 2*O) the row's upstream gradient / saved output values
     auto issue = [&](unsigned long long rr, int sl) {
-        if (rr < rows) {
-            ring_issue<T, NVL>(ring, sl, x + (long long)rr * ld_x, lane, inner);
+        long long pr = (long long)rr;
+        if (rr < rows && row_index) pr = __ldg(row_index + rr);
+        if (rr < rows && pr >= 0) {
+            ring_issue<T, NVL>(ring, sl, x + pr * ld_x, lane, inner);
             if (lane < 2 * O && (softplus || lane < O)) {
                 unsigned b, pix;
-                split_row((unsigned)rr, ppi, inv_ppi, &b, &pix);
+                split_row((unsigned)pr, ppi, inv_ppi, &b, &pix);
                 const int o = lane < O ? lane : lane - O;
                 const long long oi = ((long long)b * O + o) * ppi + pix;
                 vk_cp_async4(dring + (sl * HT_WARPS + wib) * 2 * O + lane, (lane < O ? dout : out) + oi);
@@ -282,15 +286,22 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
         float2 f[NVL][P];
         vk_cp_async_wait<RING - 1>();
         __syncwarp();                                   // the upstream values were copied by other lanes
+        const bool live = !row_index || __ldg(row_index + r) >= 0;
         ring_fetch2<T, NVL>(ring, slot, lane, inner, f);
+        if (!live) {
+#pragma unroll
+            for (int j = 0; j < NVL; ++j)
+#pragma unroll
+                for (int i = 0; i < P; ++i) f[j][i] = make_float2(0.f, 0.f);
+        }
         // upstream gradient of the pre-softplus outputs (same value in every lane)
         float2 dpre[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) {
             const float* dr = dring + (slot * HT_WARPS + wib) * 2 * O;
-            float d = dr[o];
+            float d = live ? dr[o] : 0.f;
             if (softplus) {
-                const float y = dr[O + o];
+                const float y = live ? dr[O + o] : 0.f;
                 d *= (y > 20.f) ? 1.f : (1.f - __expf(-y));   // sigmoid(pre) = 1 - exp(-softplus(pre))
             }
             dpre[o] = vk_splat2(d);
@@ -428,7 +439,7 @@ int launch_fwd(int O, const void* x, long long ld_x, int inner, const float* gam
 template <typename T, int NVL>
 int launch_bwd(int O, const void* x, long long ld_x, int inner, int slice_w, const float* gamma, const float* beta,
                const float* w2, int softplus, const float* out, const float* dout, long long ppi, long long rows, void* dx,
-               long long ld_dx, float* dgamma, float* dbeta, float* dw2, float* db2, float* dbias, cudaStream_t s) {
+               long long ld_dx, float* dgamma, float* dbeta, float* dw2, float* db2, float* dbias, const int* row_index, cudaStream_t s) {
     constexpr int V = VkVec<T>::N;
     long long blocks = (rows + HT_WARPS - 1) / HT_WARPS;
     const long long cap = (long long)vkocr_sm_count() * ((NVL * O <= 4) ? 2 : 1);
@@ -440,7 +451,7 @@ int launch_bwd(int O, const void* x, long long ld_x, int inner, int slice_w, con
     head_tail_bwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS,                                                        \
         RING * NVL * HT_THREADS * 16 + (RING * HT_WARPS * 2 * OO + (3 + OO + (OO >= 3 ? OO : 0)) * 32 * NVL * V + OO + 1) * sizeof(float), s>>>(      \
         reinterpret_cast<const T*>(x), ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, (unsigned)ppi, inv_ppi,  \
-        (unsigned)rows, reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias)
+        (unsigned)rows, reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias, row_index)
     switch (O) {
         case 1: VK_HT_BWD(1); break;
         case 2: VK_HT_BWD(2); break;
@@ -506,13 +517,42 @@ int vkocr_head_tail_bwd(int dtype, const void* x, long long ld_x, int inner, int
     if (rows == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int rc = 0;
-#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_bwd<T, NVL>(O, x, ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, pixels_per_image, rows, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, s)))
+#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_bwd<T, NVL>(O, x, ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, pixels_per_image, rows, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, nullptr, s)))
     if (nvl == 1) VK_CALL(1);
     else if (nvl == 2) VK_CALL(2);
     else VK_CALL(4);
 #undef VK_CALL
     VK_REQUIRE(rc == 0, VKOCR_BAD_SHAPE, "head_tail_bwd: dispatch failed");
     VK_CHECK_LAUNCH("head_tail_bwd_kernel");
+    return VKOCR_OK;
+}
+
+// The same backward restricted to a list of pixels: entry e < entries reads the conv / out / dout values of pixel row
+// row_index[e] (global pixel index b * pixels_per_image + y * W + x; < 0 = no pixel) and writes the gradient row e of dx
+// ([entries, ld_dx], zeros for empty entries).  Used when d(loss)/d(out) is zero outside the label points.
+int vkocr_head_tail_bwd_points(int dtype, const void* x, long long ld_x, int inner, int slice_w, const float* gamma, const float* beta,
+                               const float* w2, int O, int softplus, const float* out, const float* dout, long long pixels_per_image,
+                               const int* row_index, long long entries, void* dx, long long ld_dx, float* dgamma, float* dbeta,
+                               float* dw2, float* db2, float* dbias, void* stream) {
+    VK_REQUIRE(x && gamma && beta && w2 && out && dout && dx && dgamma && dbeta && dw2 && db2 && dbias && row_index, VKOCR_BAD_ARGUMENT,
+               "head_tail_bwd_points: null argument");
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    VK_REQUIRE(slice_w % V == 0 && ld_x % V == 0 && ld_dx % V == 0 && slice_w >= inner, VKOCR_BAD_ALIGN, "head_tail_bwd_points: slice %d", slice_w);
+    VK_REQUIRE(O >= 1 && O <= 4, VKOCR_BAD_SHAPE, "head_tail_bwd_points: out channels %d (1..4 supported)", O);
+    VK_REQUIRE(entries < (1LL << 31) && pixels_per_image >= 1 && pixels_per_image < (1LL << 31), VKOCR_BAD_SHAPE,
+               "head_tail_bwd_points: %lld entries / %lld pixels per image out of range", entries, pixels_per_image);
+    const int nvl = pick_nvl(dtype, slice_w);
+    VK_REQUIRE(nvl > 0, VKOCR_BAD_SHAPE, "head_tail_bwd_points: inner width %d too large", slice_w);
+    if (entries == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = 0;
+#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_bwd<T, NVL>(O, x, ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, pixels_per_image, entries, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, row_index, s)))
+    if (nvl == 1) VK_CALL(1);
+    else if (nvl == 2) VK_CALL(2);
+    else VK_CALL(4);
+#undef VK_CALL
+    VK_REQUIRE(rc == 0, VKOCR_BAD_SHAPE, "head_tail_bwd_points: dispatch failed");
+    VK_CHECK_LAUNCH("head_tail_bwd_kernel(points)");
     return VKOCR_OK;
 }
 

@@ -243,6 +243,28 @@ def packed_tapsplit_dgrad(ws: Sequence[Tensor], dtype: torch.dtype, slot: int) -
     return buf, k_pad
 
 
+def packed_tapsplit_points_dgrad(ws: Sequence[Tensor], dtype: torch.dtype, slot: int) -> Tuple[Tensor, int]:
+    """Conv2d weights -> [k*k * C, k_pad] operand of U = G . W over the label-point rows (csrc/head_sparse.cu): row
+    tap * C + c, column head * slot + n."""
+    C, k = ws[0].shape[1], ws[0].shape[2]
+    T = k * k
+    k_pad = _ceil_to(slot * len(ws), 64)
+
+    def fill(b: Tensor) -> None:
+        for h, w in enumerate(ws):
+            _pack(w.detach(), T, 1, C * T, C, T, w.shape[0], 0, None, b, h * slot, k_pad, C * k_pad)
+
+    buf = PACK.get(('tapsplit_points_dgrad', tuple(id(w) for w in ws), dtype, slot), list(ws), (T * C, k_pad), dtype, fill)
+    return buf, k_pad
+
+
+# Upstream gradients that are zero outside a list of label points: data_ptr of the gradient map -> (label_y, label_x, (B, H, W)).
+# PreciseLossFn.backward registers the maps it scatters into; HeadGroupFn.backward consumes the entry of a head whose incoming
+# gradient is that very tensor (any accumulation or copy in between gives a new tensor and the dense path).
+SPARSE_GRADS: Dict[int, Tuple[Tensor, Tensor, Tuple[int, int, int]]] = {}
+SPARSE_BACKWARD = True     # tests set this to False to run the dense backward everywhere (cross-check)
+
+
 def packed_patch_fwd(w: Tensor, dtype: torch.dtype) -> Tuple[Tensor, int]:
     """Patchify conv weight (N, C, p, p), stride p -> [N, c_pad] with k = (ky*p+kx)*C + c."""
     N, C, p, _ = w.shape
@@ -914,47 +936,112 @@ class HeadGroupFn(torch.autograd.Function):
         M = B * H * W
         dt, dev = x.dtype, x.device
         ntot = slot * nh
-        dconv = alloc_nhwc(B, H, W, ntot, dt, dev)
-        for i, hd in enumerate(heads):
-            inner, O = int(hd[0].shape[0]), int(hd[4].shape[0])
+        T = ks * ks
+        dx = None
+        # heads whose incoming gradient is zero outside the label points (registered by PreciseLossFn.backward) take the
+        # label-point backward (csrc/head_sparse.cu): exact, and B * P rows of work instead of B * H * W
+        points: Dict[int, Tuple[Tensor, Tensor]] = {}
+        if tapsplit and SPARSE_BACKWARD:
+            for i in range(nh):
+                d = douts[i]
+                info = SPARSE_GRADS.pop(d.data_ptr(), None) if d is not None else None
+                if info is not None and d.dtype == torch.float32 and d.is_contiguous() and info[2] == (B, H, W) \
+                        and info[0].shape[0] == B and 8 * info[0].numel() <= M:
+                    points[i] = (info[0], info[1])
+        dense_ids = [i for i in range(nh) if i not in points]
+
+        def upstream(i: int) -> Tensor:
             dout = douts[i]
             if dout is None:
-                dout = torch.zeros_like(outs[i])
-            dout = dout.contiguous().float()
+                dout = zero_(torch.empty_like(outs[i]))
+            return dout.contiguous().float()
+
+        n_d = slot * len(dense_ids) if tapsplit else ntot
+        dconv = alloc_nhwc(B, H, W, n_d, dt, dev) if n_d > 0 else None
+        for k, i in enumerate(dense_ids):
+            hd = heads[i]
+            inner, O = int(hd[0].shape[0]), int(hd[4].shape[0])
+            dout = upstream(i)
             if L.PROFILE.active:
                 L.PROFILE.note(f'head_tail_bwd rows{M} inner{inner} O{O}', 0.0, M * (2 * inner * conv.element_size() + 8 * O))
             L.check(L.LIB.vkocr_head_tail_bwd(_tag(dt), L.ptr(conv[:, i * slot:(i + 1) * slot]), conv.stride(3), inner, slot,
                                               L.ptr(hd[2].detach()), L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), O,
                                               int(softplus[i]), L.ptr(outs[i]), L.ptr(dout), H * W, M,
-                                              L.ptr(dconv[:, i * slot:(i + 1) * slot]), dconv.stride(3),
+                                              L.ptr(dconv[:, k * slot:(k + 1) * slot]), dconv.stride(3),
                                               L.ptr(grad_buffer(hd[2])), L.ptr(grad_buffer(hd[3])), L.ptr(grad_buffer(hd[4])),
                                               L.ptr(grad_buffer(hd[5])), L.ptr(grad_buffer(hd[1])), _s()), 'head_tail_bwd')
-        T = ks * ks
-        dx = None
         if tapsplit:
-            # adjoint of the interpolate + shift + sum, then two plain GEMMs on the low-resolution grid
             m_low = B * h * w
-            nz = T * ntot
-            dz = torch.empty((m_low, nz), dtype=dt, device=dev)
-            if L.PROFILE.active:
-                inner_sum = sum(int(hd[0].shape[0]) for hd in heads)
-                L.PROFILE.note(f'head_combine_bwd {B}x{h}x{w} x{factor} ks{ks} N{ntot}', 0.0, (M + m_low * T) * inner_sum * dz.element_size())
-            L.check(L.LIB.vkocr_head_combine_bwd(_tag(dt), L.ptr(dconv), dconv.stride(3), B, h, w, factor, mode, ks, ntot, L.ptr(dz), nz,
-                                                 COMBINE_ALGO, _s()), 'head_combine_bwd')
-            del dconv
-            gw = _zeros_f32(nz * C, dev)
-            gemm_tn(dz, 1, 1, m_low, nz, nz, 1, x, C, ld, _epilogue(gw, C, out_f32=True, accumulate=True, tn=(0, C, 1)),
-                    alg_ij=C * T * sum(int(hd[0].shape[0]) for hd in heads))
-            for i, hd in enumerate(heads):
-                inner = int(hd[0].shape[0])
-                # gw[(tap * ntot + i * slot + n) * C + c]  ->  grad[(n * C + c) * T + tap]
-                L.check(L.LIB.vkocr_scatter_add_f32(ctypes.c_void_p(gw.data_ptr() + 4 * i * slot * C), C, ntot * C, 1, inner, T, C,
-                                                    L.ptr(grad_buffer(hd[0])), C * T, 1, T, _s()), 'scatter_add_f32')
-            if ctx.needs_input_grad[0]:
-                wd, k_pad = packed_tapsplit_dgrad([hd[0] for hd in heads], dt, slot)
+            if dense_ids:
+                # adjoint of the interpolate + shift + sum, then two plain GEMMs on the low-resolution grid
+                nz = T * n_d
+                inner_sum = sum(int(heads[i][0].shape[0]) for i in dense_ids)
+                dz = torch.empty((m_low, nz), dtype=dt, device=dev)
+                if L.PROFILE.active:
+                    L.PROFILE.note(f'head_combine_bwd {B}x{h}x{w} x{factor} ks{ks} N{n_d}', 0.0, (M + m_low * T) * inner_sum * dz.element_size())
+                L.check(L.LIB.vkocr_head_combine_bwd(_tag(dt), L.ptr(dconv), dconv.stride(3), B, h, w, factor, mode, ks, n_d, L.ptr(dz), nz,
+                                                     COMBINE_ALGO, _s()), 'head_combine_bwd')
+                del dconv
+                gw = _zeros_f32(nz * C, dev)
+                gemm_tn(dz, 1, 1, m_low, nz, nz, 1, x, C, ld, _epilogue(gw, C, out_f32=True, accumulate=True, tn=(0, C, 1)),
+                        alg_ij=C * T * inner_sum)
+                for k, i in enumerate(dense_ids):
+                    hd = heads[i]
+                    # gw[(tap * n_d + k * slot + n) * C + c]  ->  grad[(n * C + c) * T + tap]
+                    L.check(L.LIB.vkocr_scatter_add_f32(ctypes.c_void_p(gw.data_ptr() + 4 * k * slot * C), C, n_d * C, 1, int(hd[0].shape[0]),
+                                                        T, C, L.ptr(grad_buffer(hd[0])), C * T, 1, T, _s()), 'scatter_add_f32')
+                if ctx.needs_input_grad[0]:
+                    wd, k_pad = packed_tapsplit_dgrad([heads[i][0] for i in dense_ids], dt, slot)
+                    dx = alloc_nhwc(B, h, w, C, dt, dev)
+                    gemm_nt(dz, 1, 1, m_low, nz, nz, 1, wd, k_pad, C, _epilogue(dx, dx.stride(3)), alg_kn=C * T * inner_sum)
+                del dz
+            elif ctx.needs_input_grad[0]:
                 dx = alloc_nhwc(B, h, w, C, dt, dev)
-                gemm_nt(dz, 1, 1, m_low, nz, nz, 1, wd, k_pad, C, _epilogue(dx, dx.stride(3)),
-                        alg_kn=C * T * sum(int(hd[0].shape[0]) for hd in heads))
+                zero_(dx.permute(0, 2, 3, 1))
+            # ---- label-point heads, grouped by point list
+            groups: Dict[Tuple[int, int], List[int]] = {}
+            for i, (py, px) in points.items():
+                groups.setdefault((py.data_ptr(), px.data_ptr()), []).append(i)
+            for ids in groups.values():
+                py, px = points[ids[0]]
+                P = int(py.shape[1])
+                E = B * P
+                n_s = slot * len(ids)
+                owner = _zeros(B * H * W, torch.int32, dev)
+                pix_index = torch.empty(E, dtype=torch.int32, device=dev)
+                L.check(L.LIB.vkocr_points_claim(L.ptr(py), L.ptr(px), B, P, H, W, L.ptr(owner), L.ptr(pix_index), _s()), 'points_claim')
+                g = torch.empty((E, n_s), dtype=dt, device=dev)
+                for k, i in enumerate(ids):
+                    hd = heads[i]
+                    inner, O = int(hd[0].shape[0]), int(hd[4].shape[0])
+                    dout = upstream(i)
+                    if L.PROFILE.active:
+                        L.PROFILE.note(f'head_tail_bwd_points entries{E} inner{inner} O{O}', 0.0, E * (2 * inner * conv.element_size() + 8 * O))
+                    L.check(L.LIB.vkocr_head_tail_bwd_points(
+                        _tag(dt), L.ptr(conv[:, i * slot:(i + 1) * slot]), conv.stride(3), inner, slot, L.ptr(hd[2].detach()),
+                        L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), O, int(softplus[i]), L.ptr(outs[i]), L.ptr(dout), H * W, L.ptr(pix_index), E,
+                        ctypes.c_void_p(g.data_ptr() + k * slot * g.element_size()), n_s, L.ptr(grad_buffer(hd[2])), L.ptr(grad_buffer(hd[3])),
+                        L.ptr(grad_buffer(hd[4])), L.ptr(grad_buffer(hd[5])), L.ptr(grad_buffer(hd[1])), _s()), 'head_tail_bwd_points')
+                # weight gradient: dW_tap = G^T . A_tap with A_tap the up-sampled, tap-shifted input rows of the label pixels
+                a_pts = torch.empty((E, T * C), dtype=dt, device=dev)
+                L.check(L.LIB.vkocr_gather_up_taps(_tag(dt), L.ptr(x), ld, B, h, w, C, factor, mode, ks, L.ptr(pix_index), E, L.ptr(a_pts), _s()),
+                        'gather_up_taps')
+                gw = _zeros_f32(n_s * T * C, dev)
+                gemm_tn(g, 1, 1, E, n_s, n_s, 1, a_pts, T * C, T * C, _epilogue(gw, T * C, out_f32=True, accumulate=True, tn=(0, T * C, 1)),
+                        alg_ij=T * C * sum(int(heads[i][0].shape[0]) for i in ids))
+                for k, i in enumerate(ids):
+                    hd = heads[i]
+                    # gw[(k * slot + n) * T * C + tap * C + c]  ->  grad[(n * C + c) * T + tap]
+                    L.check(L.LIB.vkocr_scatter_add_f32(ctypes.c_void_p(gw.data_ptr() + 4 * k * slot * T * C), T * C, C, 1, int(hd[0].shape[0]),
+                                                        T, C, L.ptr(grad_buffer(hd[0])), C * T, 1, T, _s()), 'scatter_add_f32')
+                if ctx.needs_input_grad[0]:
+                    # data gradient: U = G . W per tap, then the adjoint of up-sample + shift scattered into dX
+                    wp, k_pad = packed_tapsplit_points_dgrad([heads[i][0] for i in ids], dt, slot)
+                    u = torch.empty((E, T * C), dtype=dt, device=dev)
+                    gemm_nt(g, 1, 1, E, n_s, n_s, 1, wp, k_pad, T * C, _epilogue(u, T * C),
+                            alg_kn=T * C * sum(int(heads[i][0].shape[0]) for i in ids))
+                    L.check(L.LIB.vkocr_scatter_up_taps(_tag(dt), L.ptr(u), B, h, w, C, factor, mode, ks, L.ptr(pix_index), E, L.ptr(dx),
+                                                        dx.stride(3), _s()), 'scatter_up_taps')
         else:
             # weight gradient of all heads in one pass over (dconv, up): G[n_total, C, T] in OIHW order, then per-head slices
             gw = _zeros_f32(ntot * C * T, dev)
@@ -1089,6 +1176,10 @@ class PreciseLossFn(torch.autograd.Function):
                                              up, left, CH, CW, L.ptr(py), L.ptr(px), L.ptr(gt_off), L.ptr(gt_ang), L.ptr(gt_dist), P,
                                              beta, L.ptr(ctx.fac), L.ptr(ctx.coef), L.ptr(gout), L.ptr(dprob), L.ptr(doff),
                                              L.ptr(dang), L.ptr(ddist), _s()), 'precise_loss_bwd')
+        # the offset / angle / distance gradients are zero outside the label points (they were zero-filled and scattered into)
+        SPARSE_GRADS.clear()
+        for t in (doff, dang, ddist):
+            SPARSE_GRADS[t.data_ptr()] = (py, px, (B, H, W))
         return (dprob, doff, dang, ddist) + (None,) * 11
 
 
