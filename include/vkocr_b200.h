@@ -216,8 +216,15 @@ int vkocr_head_tail_bwd(int dtype, const void* x, long long ld_x, int inner, int
 int vkocr_points_claim(const long long* py, const long long* px, int B, int P, int H, int W, int* owner, int* pix_index, void* stream);
 int vkocr_head_tail_bwd_points(int dtype, const void* x, long long ld_x, int inner, int slice_w, const float* gamma, const float* beta,
                                const float* w2, int O, int softplus, const float* out, const float* dout, long long pixels_per_image,
-                               const int* row_index, long long entries, void* dx, long long ld_dx, float* dgamma, float* dbeta,
-                               float* dw2, float* db2, float* dbias, void* stream);
+                               const int* row_index, long long entries, int x_compact, void* dx, long long ld_dx, float* dgamma,
+                               float* dbeta, float* dw2, float* db2, float* dbias, void* stream);
+/* Label-point FORWARD (opt-in, training): conv-output rows of the label pixels only, conv[e, :] = bias + A[e, :] . W^T with A
+ * from vkocr_gather_up_taps (one small vkocr_gemm_nt), then this tail writes the NCHW maps at those pixels (the rest of the map
+ * is the caller's zero fill).  The loss reads the offset / angle / distance maps at the label points alone
+ * (loss_function/adaptive_scaling.py:235-260), so loss and gradients equal the dense forward's. */
+int vkocr_head_tail_fwd_points(int dtype, const void* x, long long ld_x, int inner, int slice_w, const float* gamma, const float* beta,
+                               const float* w2, const float* b2, int O, int softplus, float* out, long long pixels_per_image,
+                               const int* row_index, long long entries, void* stream);
 int vkocr_gather_up_taps(int dtype, const void* x, long long ld_x, int B, int h, int w, int C, int factor, int mode, int ks,
                          const int* pix_index, int E, void* a, void* stream);
 int vkocr_scatter_up_taps(int dtype, const void* u, int B, int h, int w, int C, int factor, int mode, int ks, const int* pix_index, int E,

@@ -352,3 +352,44 @@ def test_label_point_backward_equals_dense_backward(vk, neck):
     assert set(gs) == set(gd)       # the backbone gradients carry the data gradient of the heads
     for n in gd:
         assert_close(gs[n], gd[n], 5e-5, f'grad {n}', atol=1e-7)
+
+
+@pytest.mark.parametrize('neck', ['upernext', 'fpn'])
+def test_label_point_forward_gives_the_dense_loss_and_gradients(vk, neck):
+    """`forward_precise(x, label_points=...)` (an extension, off by default) evaluates the offset / angle / distance heads at the
+    label pixels only.  The maps agree with the dense call AT the label points and are zero elsewhere; the precise loss and
+    every parameter gradient agree with the dense call (fp32 mode)."""
+    from oracle import synth
+    dev = torch.device('cuda')
+    B, H, W, P = 2, 64, 96, 10
+    model = _build(vk, neck)
+    model.load_state_dict(synth.synth_state_dict('tiny', neck, seed=19), strict=True)
+    model.to(dev).eval()
+    pb = _to(synth.synth_precise_batch(B, H, W, points=P, seed=6, inset=2), dev)
+    y, x = pb['downsampled_label_point_y'].clone(), pb['downsampled_label_point_x'].clone()
+    y[0, 0], x[0, 0] = 0, 0
+    y[0, 1], x[0, 1] = H // 2 - 1, W // 2 - 1
+    y[1, 1], x[1, 1] = y[1, 2], x[1, 2]
+    pb['downsampled_label_point_y'], pb['downsampled_label_point_x'] = y, x
+    fn = vk.loss_function.AdaptiveScalingPreciseLossFunction(vk.loss_function.AdaptiveScalingPreciseLossFunctionConifg())
+    results = []
+    for lp in (None, (y, x)):
+        model.zero_grad(set_to_none=True)
+        with vk.precision(torch.float32):
+            outs = model.forward_precise(pb['image']) if lp is None else model.forward_precise(pb['image'], label_points=lp)
+            loss = fn(None, *outs, **{k: pb[k] for k in PRECISE_KEYS})
+            loss.backward()
+        torch.cuda.synchronize()
+        results.append((float(loss), [o.detach().clone() for o in outs], {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    (ld, od, gd), (ls, os_, gs) = results
+    assert abs(ls - ld) <= 1e-5 * abs(ld), (ls, ld)
+    assert_close(os_[0], od[0], 1e-6, 'prob map (dense in both)')
+    bi = torch.arange(B, device=dev)[:, None]
+    for k in (1, 2, 3):
+        assert_close(os_[k][bi, :, y, x], od[k][bi, :, y, x], 2e-5, f'head {k} at the label points')
+        mask = torch.ones_like(os_[k], dtype=torch.bool)
+        mask[bi, :, y, x] = False
+        assert float(os_[k][mask].abs().max()) == 0.0
+    assert set(gs) == set(gd)
+    for n in gd:
+        assert_close(gs[n], gd[n], 5e-5, f'grad {n}', atol=1e-7)

@@ -98,7 +98,9 @@ _SIGNATURES = {
     'vkocr_head_tail_bwd': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                             c_void_p, c_ll, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'vkocr_head_tail_bwd_points': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_ll,
-                                   c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                                   c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'vkocr_head_tail_fwd_points': [c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_ll,
+                                   c_void_p, c_ll, c_void_p],
     'vkocr_points_claim': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'vkocr_gather_up_taps': [c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     'vkocr_scatter_up_taps': [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p],

@@ -103,7 +103,8 @@ template <typename T, int NVL, int O>
 __global__ void __launch_bounds__(HT_THREADS)
 head_tail_fwd_kernel(const T* __restrict__ x, long long ld_x, int inner, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ w2, const float* __restrict__ b2, int softplus,
-                     float* __restrict__ out, unsigned ppi, float inv_ppi, unsigned rows) {
+                     float* __restrict__ out, unsigned ppi, float inv_ppi, unsigned rows, const int* __restrict__ row_index) {
+    // row_index (nullable): x row e is the conv output of pixel row_index[e] (< 0: skip) -- the label-point forward
     constexpr int V = VkVec<T>::N;
     const int lane = threadIdx.x & 31;
     const unsigned warp0 = blockIdx.x * HT_WARPS + (threadIdx.x >> 5);
@@ -165,9 +166,12 @@ head_tail_fwd_kernel(const T* __restrict__ x, long long ld_x, int inner, const f
             for (int o = 0; o < O; ++o) v = (lane == o) ? dot[o] : v;
             v += bias2;
             if (softplus) v = vk_softplus(v);
-            unsigned b, pix;
-            split_row(r, ppi, inv_ppi, &b, &pix);
-            out[((long long)b * O + lane) * ppi + pix] = v;
+            const long long pr = row_index ? (long long)__ldg(row_index + r) : (long long)r;
+            if (pr >= 0) {
+                unsigned b, pix;
+                split_row((unsigned)pr, ppi, inv_ppi, &b, &pix);
+                out[((long long)b * O + lane) * ppi + pix] = v;
+            }
         }
     }
 }
@@ -217,7 +221,7 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
                      const float* __restrict__ beta, const float* __restrict__ w2, int softplus, const float* __restrict__ out,
                      const float* __restrict__ dout, unsigned ppi, float inv_ppi, unsigned rows, T* __restrict__ dx,
                      long long ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw2,
-                     float* __restrict__ db2, float* __restrict__ dbias, const int* __restrict__ row_index) {
+                     float* __restrict__ db2, float* __restrict__ dbias, const int* __restrict__ row_index, int x_compact) {
     // row_index (nullable): entry e reads pixel row row_index[e] (< 0: no pixel, the entry's gradient row is zero) and writes
     // dx row e -- the label-point form used when the upstream gradient is zero outside a short list of pixels
     constexpr int V = VkVec<T>::N;
@@ -268,7 +272,7 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
         long long pr = (long long)rr;
         if (rr < rows && row_index) pr = __ldg(row_index + rr);
         if (rr < rows && pr >= 0) {
-            ring_issue<T, NVL>(ring, sl, x + pr * ld_x, lane, inner);
+            ring_issue<T, NVL>(ring, sl, x + (x_compact ? (long long)rr : pr) * ld_x, lane, inner);   // x_compact: x holds one row per ENTRY
             if (lane < 2 * O && (softplus || lane < O)) {
                 unsigned b, pix;
                 split_row((unsigned)pr, ppi, inv_ppi, &b, &pix);
@@ -415,7 +419,7 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
 
 template <typename T, int NVL>
 int launch_fwd(int O, const void* x, long long ld_x, int inner, const float* gamma, const float* beta, const float* w2,
-               const float* b2, int softplus, float* out, long long ppi, long long rows, cudaStream_t s) {
+               const float* b2, int softplus, float* out, long long ppi, long long rows, const int* row_index, cudaStream_t s) {
     long long blocks = (rows + HT_WARPS - 1) / HT_WARPS;
     const long long cap = (long long)vkocr_sm_count() * 8;
     if (blocks > cap) blocks = cap;
@@ -424,7 +428,7 @@ int launch_fwd(int O, const void* x, long long ld_x, int inner, const float* gam
 #define VK_HT_FWD(OO)                                                                                            \
     head_tail_fwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS, RING * NVL * HT_THREADS * 16, s>>>(reinterpret_cast<const T*>(x), ld_x, inner, \
                                                                              gamma, beta, w2, b2, softplus, out,  \
-                                                                             (unsigned)ppi, inv_ppi, (unsigned)rows)
+                                                                             (unsigned)ppi, inv_ppi, (unsigned)rows, row_index)
     switch (O) {
         case 1: VK_HT_FWD(1); break;
         case 2: VK_HT_FWD(2); break;
@@ -439,7 +443,7 @@ int launch_fwd(int O, const void* x, long long ld_x, int inner, const float* gam
 template <typename T, int NVL>
 int launch_bwd(int O, const void* x, long long ld_x, int inner, int slice_w, const float* gamma, const float* beta,
                const float* w2, int softplus, const float* out, const float* dout, long long ppi, long long rows, void* dx,
-               long long ld_dx, float* dgamma, float* dbeta, float* dw2, float* db2, float* dbias, const int* row_index, cudaStream_t s) {
+               long long ld_dx, float* dgamma, float* dbeta, float* dw2, float* db2, float* dbias, const int* row_index, int x_compact, cudaStream_t s) {
     constexpr int V = VkVec<T>::N;
     long long blocks = (rows + HT_WARPS - 1) / HT_WARPS;
     const long long cap = (long long)vkocr_sm_count() * ((NVL * O <= 4) ? 2 : 1);
@@ -451,7 +455,7 @@ int launch_bwd(int O, const void* x, long long ld_x, int inner, int slice_w, con
     head_tail_bwd_kernel<T, NVL, OO><<<(unsigned)blocks, HT_THREADS,                                                        \
         RING * NVL * HT_THREADS * 16 + (RING * HT_WARPS * 2 * OO + (3 + OO + (OO >= 3 ? OO : 0)) * 32 * NVL * V + OO + 1) * sizeof(float), s>>>(      \
         reinterpret_cast<const T*>(x), ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, (unsigned)ppi, inv_ppi,  \
-        (unsigned)rows, reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias, row_index)
+        (unsigned)rows, reinterpret_cast<T*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias, row_index, x_compact)
     switch (O) {
         case 1: VK_HT_BWD(1); break;
         case 2: VK_HT_BWD(2); break;
@@ -489,13 +493,40 @@ int vkocr_head_tail_fwd(int dtype, const void* x, long long ld_x, int inner, int
     if (rows == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int rc = 0;
-#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_fwd<T, NVL>(O, x, ld_x, inner, gamma, beta, w2, b2, softplus, out, pixels_per_image, rows, s)))
+#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_fwd<T, NVL>(O, x, ld_x, inner, gamma, beta, w2, b2, softplus, out, pixels_per_image, rows, nullptr, s)))
     if (nvl == 1) VK_CALL(1);
     else if (nvl == 2) VK_CALL(2);
     else VK_CALL(4);
 #undef VK_CALL
     VK_REQUIRE(rc == 0, VKOCR_BAD_SHAPE, "head_tail_fwd: dispatch failed");
     VK_CHECK_LAUNCH("head_tail_fwd_kernel");
+    return VKOCR_OK;
+}
+
+// The same tail over a COMPACT list of conv-output rows: x = [entries, ld_x], entry e belongs to pixel row_index[e] (global
+// pixel index b * pixels_per_image + y * W + x; < 0 = skip) of the NCHW fp32 map `out`, which is written at those pixels
+// only.  The label-point forward of the precise heads (training: the loss reads these maps at the label points alone).
+int vkocr_head_tail_fwd_points(int dtype, const void* x, long long ld_x, int inner, int slice_w, const float* gamma, const float* beta,
+                               const float* w2, const float* b2, int O, int softplus, float* out, long long pixels_per_image,
+                               const int* row_index, long long entries, void* stream) {
+    VK_REQUIRE(x && gamma && beta && w2 && b2 && out && row_index, VKOCR_BAD_ARGUMENT, "head_tail_fwd_points: null argument");
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    VK_REQUIRE(slice_w % V == 0 && ld_x % V == 0 && slice_w >= inner, VKOCR_BAD_ALIGN, "head_tail_fwd_points: slice %d ld %lld", slice_w, ld_x);
+    VK_REQUIRE(O >= 1 && O <= 4, VKOCR_BAD_SHAPE, "head_tail_fwd_points: out channels %d (1..4 supported)", O);
+    VK_REQUIRE(entries < (1LL << 31) && pixels_per_image >= 1 && pixels_per_image < (1LL << 31), VKOCR_BAD_SHAPE,
+               "head_tail_fwd_points: %lld entries / %lld pixels per image out of range", entries, pixels_per_image);
+    const int nvl = pick_nvl(dtype, slice_w);
+    VK_REQUIRE(nvl > 0, VKOCR_BAD_SHAPE, "head_tail_fwd_points: inner width %d too large", slice_w);
+    if (entries == 0) return VKOCR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = 0;
+#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_fwd<T, NVL>(O, x, ld_x, inner, gamma, beta, w2, b2, softplus, out, pixels_per_image, entries, row_index, s)))
+    if (nvl == 1) VK_CALL(1);
+    else if (nvl == 2) VK_CALL(2);
+    else VK_CALL(4);
+#undef VK_CALL
+    VK_REQUIRE(rc == 0, VKOCR_BAD_SHAPE, "head_tail_fwd_points: dispatch failed");
+    VK_CHECK_LAUNCH("head_tail_fwd_kernel(points)");
     return VKOCR_OK;
 }
 
@@ -517,7 +548,7 @@ int vkocr_head_tail_bwd(int dtype, const void* x, long long ld_x, int inner, int
     if (rows == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int rc = 0;
-#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_bwd<T, NVL>(O, x, ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, pixels_per_image, rows, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, nullptr, s)))
+#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_bwd<T, NVL>(O, x, ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, pixels_per_image, rows, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, nullptr, 0, s)))
     if (nvl == 1) VK_CALL(1);
     else if (nvl == 2) VK_CALL(2);
     else VK_CALL(4);
@@ -529,11 +560,12 @@ int vkocr_head_tail_bwd(int dtype, const void* x, long long ld_x, int inner, int
 
 // The same backward restricted to a list of pixels: entry e < entries reads the conv / out / dout values of pixel row
 // row_index[e] (global pixel index b * pixels_per_image + y * W + x; < 0 = no pixel) and writes the gradient row e of dx
-// ([entries, ld_dx], zeros for empty entries).  Used when d(loss)/d(out) is zero outside the label points.
+// ([entries, ld_dx], zeros for empty entries).  Used when d(loss)/d(out) is zero outside the label points.  x_compact != 0: x itself
+// holds one conv-output row per ENTRY (the label-point forward kept nothing else).
 int vkocr_head_tail_bwd_points(int dtype, const void* x, long long ld_x, int inner, int slice_w, const float* gamma, const float* beta,
                                const float* w2, int O, int softplus, const float* out, const float* dout, long long pixels_per_image,
-                               const int* row_index, long long entries, void* dx, long long ld_dx, float* dgamma, float* dbeta,
-                               float* dw2, float* db2, float* dbias, void* stream) {
+                               const int* row_index, long long entries, int x_compact, void* dx, long long ld_dx, float* dgamma,
+                               float* dbeta, float* dw2, float* db2, float* dbias, void* stream) {
     VK_REQUIRE(x && gamma && beta && w2 && out && dout && dx && dgamma && dbeta && dw2 && db2 && dbias && row_index, VKOCR_BAD_ARGUMENT,
                "head_tail_bwd_points: null argument");
     const int V = dtype == VKOCR_F32 ? 4 : 8;
@@ -546,7 +578,7 @@ int vkocr_head_tail_bwd_points(int dtype, const void* x, long long ld_x, int inn
     if (entries == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int rc = 0;
-#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_bwd<T, NVL>(O, x, ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, pixels_per_image, entries, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, row_index, s)))
+#define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_bwd<T, NVL>(O, x, ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, pixels_per_image, entries, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, row_index, x_compact, s)))
     if (nvl == 1) VK_CALL(1);
     else if (nvl == 2) VK_CALL(2);
     else VK_CALL(4);

@@ -62,7 +62,7 @@ class SoftplusHead(nn.Sequential):
         return ops.HeadGroupFn.apply(x, head.upsampling_factor, head.resample_mode, (True,), *head.head_params())[0]
 
 
-def _run_head_group(neck_feature: torch.Tensor, heads: Sequence[nn.Module]) -> Tuple[torch.Tensor, ...]:
+def _run_head_group(neck_feature: torch.Tensor, heads: Sequence[nn.Module], label_points=None) -> Tuple[torch.Tensor, ...]:
     softplus = tuple(isinstance(h, SoftplusHead) for h in heads)
     cores = [h[0] if isinstance(h, SoftplusHead) else h for h in heads]
     factor, mode = cores[0].upsampling_factor, cores[0].resample_mode
@@ -70,6 +70,10 @@ def _run_head_group(neck_feature: torch.Tensor, heads: Sequence[nn.Module]) -> T
     for core in cores:
         assert core.upsampling_factor == factor
         params.extend(core.head_params())
+    if label_points is not None:
+        per_head = [params[6 * i:6 * i + 6] for i in range(len(cores))]
+        if ops.HeadGroupPointsFn.supported(neck_feature, factor, per_head):
+            return ops.HeadGroupPointsFn.apply(neck_feature, factor, mode, softplus, label_points[0], label_points[1], *params)
     return ops.HeadGroupFn.apply(neck_feature, factor, mode, softplus, *params)
 
 
@@ -127,11 +131,23 @@ class AdaptiveScaling(nn.Module):
         mask, height = _run_head_group(rough_neck_feature, (self.rough_char_mask_head, self.rough_char_height_head))
         return mask, height
 
-    def forward_precise(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    def forward_precise(self, x: torch.Tensor, label_points=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
         """-> (prob logits (B,1,.), up-left offset (B,2,.), corner-angle logits (B,4,.), softplus corner distance (B,4,.))
-        at (H/2, W/2), fp32 (reference adaptive_scaling.py:156-177)."""
+        at (H/2, W/2), fp32 (reference adaptive_scaling.py:156-177).
+
+        ``label_points`` (an extension, off by default): ``(downsampled_label_point_y, downsampled_label_point_x)``, (B, P)
+        int64.  The precise loss reads the offset / angle / distance maps at these points only
+        (loss_function/adaptive_scaling.py:235-260); given them, those three heads are evaluated at the label pixels alone
+        (``ops.HeadGroupPointsFn``) and their maps are ZERO elsewhere -- loss and gradients are those of the dense call."""
         feature = self.backbone(x)
         precise_neck_feature = self.precise_neck(feature)
+        if label_points is not None:
+            precise_neck_feature = ops.to_nhwc(precise_neck_feature, runtime.compute_dtype())
+            (prob,) = _run_head_group(precise_neck_feature, (self.precise_char_prob_head,))
+            offset, angle, distance = _run_head_group(precise_neck_feature, (
+                self.precise_char_up_left_corner_offset_head, self.precise_char_corner_angle_head,
+                self.precise_char_corner_distance_head), label_points=label_points)
+            return prob, offset, angle, distance
         prob, offset, angle, distance = _run_head_group(precise_neck_feature, (
             self.precise_char_prob_head,
             self.precise_char_up_left_corner_offset_head,

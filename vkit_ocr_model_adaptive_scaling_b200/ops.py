@@ -1019,7 +1019,7 @@ class HeadGroupFn(torch.autograd.Function):
                         L.PROFILE.note(f'head_tail_bwd_points entries{E} inner{inner} O{O}', 0.0, E * (2 * inner * conv.element_size() + 8 * O))
                     L.check(L.LIB.vkocr_head_tail_bwd_points(
                         _tag(dt), L.ptr(conv[:, i * slot:(i + 1) * slot]), conv.stride(3), inner, slot, L.ptr(hd[2].detach()),
-                        L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), O, int(softplus[i]), L.ptr(outs[i]), L.ptr(dout), H * W, L.ptr(pix_index), E,
+                        L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), O, int(softplus[i]), L.ptr(outs[i]), L.ptr(dout), H * W, L.ptr(pix_index), E, 0,
                         ctypes.c_void_p(g.data_ptr() + k * slot * g.element_size()), n_s, L.ptr(grad_buffer(hd[2])), L.ptr(grad_buffer(hd[3])),
                         L.ptr(grad_buffer(hd[4])), L.ptr(grad_buffer(hd[5])), L.ptr(grad_buffer(hd[1])), _s()), 'head_tail_bwd_points')
                 # weight gradient: dW_tap = G^T . A_tap with A_tap the up-sampled, tap-shifted input rows of the label pixels
@@ -1063,6 +1063,111 @@ class HeadGroupFn(torch.autograd.Function):
                     dx = dup
         _ready(*params)
         return (dx, None, None, None) + (None,) * len(params)
+
+
+class HeadGroupPointsFn(torch.autograd.Function):
+    """Opt-in label-point evaluation of heads whose outputs the loss reads at the (B, P) label points only (the precise
+    corner-offset / angle / distance heads, loss_function/adaptive_scaling.py:235-260): the conv outputs of those pixels are
+    ONE small GEMM, conv[e, :] = bias + A[e, :] . W^T with A[e, tap, :] = up(x)[r_e + dy - k/2, s_e + dx - k/2, :]
+    (csrc/head_sparse.cu), the LayerNorm -> GELU -> projection (-> Softplus) tail runs on those rows, and the returned NCHW
+    maps hold the heads' values at the label pixels and ZERO elsewhere.  Loss and gradients equal the dense evaluation's
+    (UperNextHead.forward upernext.py:233-248 / FpnHead.forward fpn.py:193-208); the maps do not, so this is never the default."""
+
+    @staticmethod
+    def supported(x: Tensor, factor: int, heads) -> bool:
+        C = int(x.shape[1])
+        inners = [int(hd[0].shape[0]) for hd in heads]
+        return factor > 1 and C % 64 == 0 and len(heads) <= L.MAX_HEADS and max(inners) <= 256 \
+            and max(int(hd[4].shape[0]) for hd in heads) <= 4
+
+    @staticmethod
+    def forward(ctx, x: Tensor, factor: int, mode: int, softplus: Tuple[bool, ...], py: Tensor, px: Tensor, *params: Tensor):
+        nh = len(softplus)
+        heads = [params[6 * i:6 * i + 6] for i in range(nh)]
+        B, h, w, C, ld = geom(x)
+        dt, dev = x.dtype, x.device
+        H, W = h * factor, w * factor
+        py, px = _i64c(py), _i64c(px)
+        if tuple(py.shape) != tuple(px.shape) or py.dim() != 2 or py.shape[0] != B:
+            raise L.VkocrError(f'label points {tuple(py.shape)} / {tuple(px.shape)} do not match the batch {B}')
+        P = int(py.shape[1])
+        E = B * P
+        inners = [int(hd[0].shape[0]) for hd in heads]
+        ks = int(heads[0][0].shape[2])
+        T = ks * ks
+        slot = _ceil_to(max(inners), 8)
+        n_s = slot * nh
+        owner = _zeros(B * H * W, torch.int32, dev)
+        pix_index = torch.empty(E, dtype=torch.int32, device=dev)
+        L.check(L.LIB.vkocr_points_claim(L.ptr(py), L.ptr(px), B, P, H, W, L.ptr(owner), L.ptr(pix_index), _s()), 'points_claim')
+        a_pts = torch.empty((E, T * C), dtype=dt, device=dev)
+        L.check(L.LIB.vkocr_gather_up_taps(_tag(dt), L.ptr(x), ld, B, h, w, C, factor, mode, ks, L.ptr(pix_index), E, L.ptr(a_pts), _s()),
+                'gather_up_taps')
+        wp, c_pad, _ = packed_conv_fwd([hd[0] for hd in heads], dt, slot)     # [n_s, T * c_pad], k = tap * c_pad + c (c_pad == C)
+
+        def fill_bias(buf: Tensor) -> None:
+            for i, hd in enumerate(heads):
+                _pack(hd[1].detach(), 0, 0, 1, 1, 1, inners[i], 0, None, buf, i * slot, 0, 0)
+        bias = PACK.get(('head_bias', tuple(id(hd[1]) for hd in heads), slot), [hd[1] for hd in heads], (n_s,), torch.float32, fill_bias)
+        conv_pts = torch.empty((E, n_s), dtype=dt, device=dev)
+        gemm_nt(a_pts, 1, 1, E, T * C, T * C, 1, wp, T * c_pad, n_s, _epilogue(conv_pts, n_s, bias=bias), alg_kn=T * C * sum(inners))
+        outs = []
+        for i, hd in enumerate(heads):
+            O = int(hd[4].shape[0])
+            out = zero_(torch.empty((B, O, H, W), dtype=torch.float32, device=dev))
+            L.check(L.LIB.vkocr_head_tail_fwd_points(
+                _tag(dt), ctypes.c_void_p(conv_pts.data_ptr() + i * slot * conv_pts.element_size()), n_s, inners[i], slot,
+                L.ptr(hd[2].detach()), L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), L.ptr(hd[5].detach()), O, int(softplus[i]), L.ptr(out),
+                H * W, L.ptr(pix_index), E, _s()), 'head_tail_fwd_points')
+            outs.append(out)
+        if _needs_grad(ctx):
+            ctx.save_for_backward(x, a_pts, conv_pts, pix_index, *outs, *params)
+            ctx.meta = (nh, factor, mode, tuple(softplus), slot, ks)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts: Tensor):
+        nh, factor, mode, softplus, slot, ks = ctx.meta
+        saved = ctx.saved_tensors
+        x, a_pts, conv_pts, pix_index = saved[:4]
+        outs = saved[4:4 + nh]
+        params = saved[4 + nh:]
+        heads = [params[6 * i:6 * i + 6] for i in range(nh)]
+        B, h, w, C, ld = geom(x)
+        H, W = h * factor, w * factor
+        dt, dev = x.dtype, x.device
+        T = ks * ks
+        E = int(pix_index.shape[0])
+        n_s = slot * nh
+        g = torch.empty((E, n_s), dtype=dt, device=dev)
+        for i, hd in enumerate(heads):
+            SPARSE_GRADS.pop(douts[i].data_ptr() if douts[i] is not None else 0, None)
+            dout = douts[i] if douts[i] is not None else zero_(torch.empty_like(outs[i]))
+            dout = dout.contiguous().float()
+            inner, O = int(hd[0].shape[0]), int(hd[4].shape[0])
+            L.check(L.LIB.vkocr_head_tail_bwd_points(
+                _tag(dt), ctypes.c_void_p(conv_pts.data_ptr() + i * slot * conv_pts.element_size()), n_s, inner, slot, L.ptr(hd[2].detach()),
+                L.ptr(hd[3].detach()), L.ptr(hd[4].detach()), O, int(softplus[i]), L.ptr(outs[i]), L.ptr(dout), H * W, L.ptr(pix_index), E, 1,
+                ctypes.c_void_p(g.data_ptr() + i * slot * g.element_size()), n_s, L.ptr(grad_buffer(hd[2])), L.ptr(grad_buffer(hd[3])),
+                L.ptr(grad_buffer(hd[4])), L.ptr(grad_buffer(hd[5])), L.ptr(grad_buffer(hd[1])), _s()), 'head_tail_bwd_points')
+        inner_sum = sum(int(hd[0].shape[0]) for hd in heads)
+        gw = _zeros_f32(n_s * T * C, dev)
+        gemm_tn(g, 1, 1, E, n_s, n_s, 1, a_pts, T * C, T * C, _epilogue(gw, T * C, out_f32=True, accumulate=True, tn=(0, T * C, 1)),
+                alg_ij=T * C * inner_sum)
+        for i, hd in enumerate(heads):
+            L.check(L.LIB.vkocr_scatter_add_f32(ctypes.c_void_p(gw.data_ptr() + 4 * i * slot * T * C), T * C, C, 1, int(hd[0].shape[0]), T, C,
+                                                L.ptr(grad_buffer(hd[0])), C * T, 1, T, _s()), 'scatter_add_f32')
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wp, k_pad = packed_tapsplit_points_dgrad([hd[0] for hd in heads], dt, slot)
+            u = torch.empty((E, T * C), dtype=dt, device=dev)
+            gemm_nt(g, 1, 1, E, n_s, n_s, 1, wp, k_pad, T * C, _epilogue(u, T * C), alg_kn=T * C * inner_sum)
+            dx = alloc_nhwc(B, h, w, C, dt, dev)
+            zero_(dx.permute(0, 2, 3, 1))
+            L.check(L.LIB.vkocr_scatter_up_taps(_tag(dt), L.ptr(u), B, h, w, C, factor, mode, ks, L.ptr(pix_index), E, L.ptr(dx), dx.stride(3),
+                                                _s()), 'scatter_up_taps')
+        _ready(*params)
+        return (dx, None, None, None, None, None) + (None,) * len(params)
 
 
 # ----------------------------------------------------------------------------------------------------- fused losses

@@ -29,8 +29,11 @@ def batch_to_device(batch: Dict[str, object], device, non_blocking: bool = True)
 
 def train_step(model, rough_loss_function: AdaptiveScalingRoughLossFunction,
                precise_loss_function: AdaptiveScalingPreciseLossFunction, rough_batch: Dict[str, object],
-               precise_batch: Dict[str, object], dp: Optional[DataParallel] = None) -> Tuple[Tensor, Tensor]:
-    """One two-pass step; returns the (un-halved) rough and precise losses as device tensors."""
+               precise_batch: Dict[str, object], dp: Optional[DataParallel] = None,
+               label_point_forward: bool = False) -> Tuple[Tensor, Tensor]:
+    """One two-pass step; returns the (un-halved) rough and precise losses as device tensors.  ``label_point_forward``
+    (an extension, off by default): evaluate the precise offset / angle / distance heads at the label points only
+    (``AdaptiveScaling.forward_precise(x, label_points=...)``) -- same losses and gradients, less work."""
     scale = 0.5 * (dp.loss_scale if dp is not None else 1.0)
     if dp is not None:
         dp.begin_step()
@@ -42,7 +45,9 @@ def train_step(model, rough_loss_function: AdaptiveScalingRoughLossFunction,
     del mask, height
     if dp is not None:
         dp.begin_pass(final=None)
-    prob, offset, angle, distance = model.forward_precise(precise_batch['image'])
+    lp = (precise_batch['downsampled_label_point_y'], precise_batch['downsampled_label_point_x']) if label_point_forward else None
+    prob, offset, angle, distance = model.forward_precise(precise_batch['image'], label_points=lp) if lp is not None \
+        else model.forward_precise(precise_batch['image'])
     precise_loss = precise_loss_function(
         precise_char_mask_feature=None, precise_char_prob_feature=prob,
         precise_char_up_left_corner_offset_feature=offset, precise_char_corner_angle_feature=angle,
