@@ -269,6 +269,59 @@ def test_head_convolve_first_kernels_agree(vk, kind):
             assert_close(results[0][2][n], other[2][n], 5e-5, f'{what}: grad {n}', atol=1e-6)
 
 
+@pytest.mark.parametrize('rows_shape,slot,softplus', [((3, 37, 41), 192, 0), ((2, 24, 31), 200, 1), ((1, 1, 1), 192, 1), ((1, 64, 64), 200, 0)])
+def test_head_tail_backward_half_warp_kernel(vk, rows_shape, slot, softplus):
+    """The inner = 192 / one-map backward (a half-warp per pixel row: every dense call of the training step) against the
+    generic warp-per-row kernel (reached through the label-point entry with an identity pixel list) and against a torch fp32
+    restatement of LN -> GELU -> 1x1 (-> Softplus) on the same bf16 conv rows.  Odd row counts, a padded slot, a slice inside
+    a wider buffer."""
+    from vkit_ocr_model_adaptive_scaling_b200 import _lib as L
+    dev = torch.device('cuda')
+    B, H, W = rows_shape
+    M, inner, ld = B * H * W, 192, 2 * slot + 8
+    g = torch.Generator().manual_seed(M + slot)
+    buf = (torch.randn(M, ld, generator=g) * 1.5).to(dev).to(torch.bfloat16)
+    conv = buf[:, slot:2 * slot]
+    gamma = (torch.rand(inner, generator=g) + 0.5).to(dev)
+    beta = (torch.randn(inner, generator=g) * 0.2).to(dev)
+    w2 = (torch.randn(1, inner, generator=g) * 0.2).to(dev)
+    b2 = torch.randn(1, generator=g).to(dev)
+    dout = torch.randn(B, 1, H, W, generator=g).to(dev)
+    # torch reference (fp32 math on the bf16-rounded rows)
+    xr = conv[:, :inner].float().requires_grad_(True)
+    gr, br, wr, b2r = (t.clone().requires_grad_(True) for t in (gamma, beta, w2, b2))
+    pre = F.linear(F.gelu(F.layer_norm(xr, (inner,), gr, br, 1e-6)), wr, b2r)
+    outr = F.softplus(pre) if softplus else pre
+    (outr.view(B, H, W, 1).permute(0, 3, 1, 2) * dout).sum().backward()
+    out = outr.detach().view(B, H, W, 1).permute(0, 3, 1, 2).contiguous()
+
+    def run(points):
+        dx = torch.full((M, ld), 7.0, device=dev, dtype=torch.bfloat16)
+        gs = [torch.zeros(inner, device=dev) for _ in range(3)] + [torch.zeros(1, inner, device=dev), torch.zeros(1, device=dev)]
+        dsl = dx[:, slot:2 * slot]
+        if points:
+            idx = torch.arange(M, device=dev, dtype=torch.int32)
+            L.check(L.LIB.vkocr_head_tail_bwd_points(1, L.ptr(conv), ld, inner, slot, L.ptr(gamma), L.ptr(beta), L.ptr(w2), 1, softplus,
+                                                     L.ptr(out), L.ptr(dout), H * W, L.ptr(idx), M, 0, L.ptr(dsl), ld, L.ptr(gs[0]),
+                                                     L.ptr(gs[1]), L.ptr(gs[3]), L.ptr(gs[4]), L.ptr(gs[2]), L.stream_ptr()), 'bwd_points')
+        else:
+            L.check(L.LIB.vkocr_head_tail_bwd(1, L.ptr(conv), ld, inner, slot, L.ptr(gamma), L.ptr(beta), L.ptr(w2), 1, softplus, L.ptr(out),
+                                              L.ptr(dout), H * W, M, L.ptr(dsl), ld, L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(gs[3]), L.ptr(gs[4]),
+                                              L.ptr(gs[2]), L.stream_ptr()), 'bwd')
+        torch.cuda.synchronize()
+        return dx, gs
+    dx_h, gs_h = run(False)
+    dx_g, gs_g = run(True)
+    # the two kernels do the same fp32 arithmetic per row: identical bf16 rows up to the order of the warp reductions
+    assert_close(dx_h[:, slot:slot + inner].float(), dx_g[:, slot:slot + inner].float(), 1e-2, 'dx: half-warp vs generic kernel')
+    assert_close(dx_h[:, slot:slot + inner].float(), xr.grad, 1e-2, 'dx vs torch')
+    assert torch.all(dx_h[:, slot + inner:2 * slot] == 0), 'pad columns of the slice must be written as zeros'
+    assert torch.all(dx_h[:, :slot] == 7.0) and torch.all(dx_h[:, 2 * slot:] == 7.0), 'columns outside the slice must not be touched'
+    for a, b, r, name in zip(gs_h, gs_g, (gr.grad, br.grad, xr.grad.sum(0), wr.grad, b2r.grad), ('dgamma', 'dbeta', 'dbias', 'dw2', 'db2')):
+        assert_close(a, b, 1e-4, f'{name}: half-warp vs generic kernel', atol=1e-5)
+        assert_close(a, r, 2e-3 if name != 'dbias' else 1e-2, f'{name} vs torch', atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------------- losses
 def _loss_inputs(B, H, W, inset, P, seed, dev):
     from oracle import synth

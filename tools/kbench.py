@@ -116,7 +116,7 @@ if 'up' in groups:
 if 'head' in groups:
     B, H, W = 32, 320, 320
     M = B * H * W
-    for (nh, slot, inner, O, sp) in ((2, 192, 192, 1, 0), (4, 208, 194, 4, 1), (4, 208, 193, 2, 0)):
+    for (nh, slot, inner, O, sp) in ((2, 192, 192, 1, 0), (2, 192, 192, 1, 1), (4, 200, 192, 1, 0), (4, 200, 194, 4, 1), (4, 200, 193, 2, 0)):
         ntot = nh * slot
         conv = ops.alloc_nhwc(B, H, W, ntot, BF, dev); conv.normal_()
         dconv = ops.alloc_nhwc(B, H, W, ntot, BF, dev)

@@ -227,9 +227,13 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
         : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
     d = *reinterpret_cast<float2*>(&dd);
 }
-// two bf16 channels in one 32-bit word -> an fp32 pair (one shift, one mask)
+// two bf16 channels in one 32-bit word -> an fp32 pair.  Both halves are produced on the ALU pipe (PRMT, LOP3): ptxas turns a
+// plain `raw << 16` into IMAD.U32 on every other conversion "to balance the pipes", and the FMA pipe is the one these kernels
+// are short of (28 IMADs beside 112 FFMA2s per halo row).
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t raw) {
-    return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+    uint32_t lo;
+    asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(raw));
+    return make_float2(__uint_as_float(lo), __uint_as_float(raw & 0xffff0000u));
 }
 
 // Column-wise halo loader: thread -> one 16-byte quarter of one halo column, walking down the HALO_H rows with a

@@ -696,19 +696,24 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
                     }
                     const bool full = nb + 32 <= p.N;
+                    // per-element arithmetic on fp32 PAIRS (FADD2 / FMUL2 / FFMA2): one issue slot for two columns
+                    auto add4 = [&](int j, const float4 b) {
+                        const float2 a = vk_add2(make_float2(v[j], v[j + 1]), make_float2(b.x, b.y));
+                        const float2 c = vk_add2(make_float2(v[j + 2], v[j + 3]), make_float2(b.z, b.w));
+                        v[j] = a.x; v[j + 1] = a.y; v[j + 2] = c.x; v[j + 3] = c.y;
+                    };
+                    auto mul4 = [&](int j, const float4 b) {
+                        const float2 a = vk_mul2(make_float2(v[j], v[j + 1]), make_float2(b.x, b.y));
+                        const float2 c = vk_mul2(make_float2(v[j + 2], v[j + 3]), make_float2(b.z, b.w));
+                        v[j] = a.x; v[j + 1] = a.y; v[j + 2] = c.x; v[j + 3] = c.y;
+                    };
                     if (has_bias && vec_in_smem && full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(s_vec + nb + j);
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
+                        for (int j = 0; j < 32; j += 4) add4(j, *reinterpret_cast<const float4*>(s_vec + nb + j));
                     } else if (has_bias) {
                         if (full) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
-                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                            }
+                            for (int j = 0; j < 32; j += 4) add4(j, __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j)));
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(ep.bias + nb + j) : 0.f;
@@ -722,7 +727,12 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         for (int j = 0; j < 4; ++j) {
                             float dg[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) vk_gelu_both(v[8 * j + e], &v[8 * j + e], &dg[e]);
+                            for (int e = 0; e < 8; e += 2) {      // packed pairs: the epilogue is bound by instruction issue
+                                float2 g2, d2;
+                                vk_gelu_both2(make_float2(v[8 * j + e], v[8 * j + e + 1]), &g2, &d2);
+                                v[8 * j + e] = g2.x; v[8 * j + e + 1] = g2.y;
+                                dg[e] = d2.x; dg[e + 1] = d2.y;
+                            }
                             if (ep.row_scale) {       // stochastic-depth mask: side channel = m_b * gelu', dropped samples' activation = 0
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
@@ -751,24 +761,18 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                             for (int j = 0; j < 4; ++j) {
                                 float f[8];
                                 unpack8_f16(extra[j], f);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) v[8 * j + e] *= f[e];
+                                mul4(8 * j, make_float4(f[0], f[1], f[2], f[3]));
+                                mul4(8 * j + 4, make_float4(f[4], f[5], f[6], f[7]));
                             }
                         }
                     }
                     if (has_cs && vec_in_smem && full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(s_vec + 896 + nb + j);
-                            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-                        }
+                        for (int j = 0; j < 32; j += 4) mul4(j, *reinterpret_cast<const float4*>(s_vec + 896 + nb + j));
                     } else if (has_cs) {
                         if (full) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + nb + j));
-                                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-                            }
+                            for (int j = 0; j < 32; j += 4) mul4(j, __ldg(reinterpret_cast<const float4*>(ep.col_scale + nb + j)));
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] *= (nb + j < p.N) ? __ldg(ep.col_scale + nb + j) : 0.f;
@@ -776,15 +780,15 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     }
                     if (ep.row_scale && act != 3) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= rs;
+                        for (int j = 0; j < 32; j += 4) mul4(j, make_float4(rs, rs, rs, rs));
                     }
                     if (has_res) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             float f[8];
                             unpack8(extra[j], f);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
+                            add4(8 * j, make_float4(f[0], f[1], f[2], f[3]));
+                            add4(8 * j + 4, make_float4(f[4], f[5], f[6], f[7]));
                         }
                     }
                     store_tile(v, ep.out, ep.ldo);

@@ -417,6 +417,182 @@ head_tail_bwd_kernel(const T* __restrict__ x, long long ld_x, int inner, int sli
     if (threadIdx.x < O) atomicAdd(db2 + threadIdx.x, sacc[(3 + O) * CW + threadIdx.x]);
 }
 
+// Backward for the shape every DENSE call of the training step has (bf16 storage, inner = 192, one output map: both rough
+// heads and the precise mask head): a HALF-warp per pixel row.  With a warp per row 8 of the 32 lanes idle (192 channels =
+// 24 16-byte vectors) and the per-row work that is not per-element -- two shuffle reductions, the ring bookkeeping, the
+// upstream scalars -- is paid once per 6 elements of a lane.  Here every lane owns 12 channels (three 8-byte vectors, 16
+// lanes apart: a half-warp covers a 128-byte line per vector) and one round of shuffles serves the two rows of the warp.
+constexpr int HH_RING = 4;             // rows in flight per half-warp (12 KB per warp, as in the generic kernel)
+constexpr int HH_INNER = 192;
+constexpr int HH_NV = 3;               // 8-byte vectors per lane
+__device__ __forceinline__ void vk_cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ float2 half_sum2(float a, float b) {      // sums over the 16 lanes of a half-warp
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    return make_float2(a, b);
+}
+__global__ void __launch_bounds__(HT_THREADS, 2)
+head_tail_bwd_h192_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, int slice_w, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ w2, int softplus, const float* __restrict__ out,
+                          const float* __restrict__ dout, unsigned rows, __nv_bfloat16* __restrict__ dx, long long ld_dx,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw2, float* __restrict__ db2,
+                          float* __restrict__ dbias) {
+    // one output map: the NCHW fp32 maps out / dout are indexed by the pixel row itself
+    extern __shared__ uint4 ring[];
+    uint2* ring2 = reinterpret_cast<uint2*>(ring);                               // [HH_RING][HH_NV][HT_THREADS]
+    float* dring = reinterpret_cast<float*>(ring2 + HH_RING * HH_NV * HT_THREADS);   // [HH_RING][2 * HT_WARPS][2]: dout, out
+    float* sacc = dring + HH_RING * 2 * HT_WARPS * 2;                            // [4][HH_INNER] + [1]
+    for (int i = threadIdx.x; i < 4 * HH_INNER + 1; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4, wib = threadIdx.x >> 5;
+    const unsigned row0 = (blockIdx.x * HT_WARPS + wib) * 2;
+    const unsigned stride = gridDim.x * HT_WARPS * 2;
+    float2 gm[HH_NV][2], bt[HH_NV][2], w[HH_NV][2], ag[HH_NV][2], ab[HH_NV][2], ax[HH_NV][2], aw[HH_NV][2];
+    float adb = 0.f;
+#pragma unroll
+    for (int j = 0; j < HH_NV; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c = (l16 + 16 * j) * 4 + 2 * i;
+            gm[j][i] = make_float2(__ldg(gamma + c), __ldg(gamma + c + 1));
+            bt[j][i] = make_float2(__ldg(beta + c), __ldg(beta + c + 1));
+            w[j][i] = make_float2(__ldg(w2 + c), __ldg(w2 + c + 1));
+            ag[j][i] = ab[j][i] = ax[j][i] = aw[j][i] = make_float2(0.f, 0.f);
+        }
+    const float inv = 1.f / HH_INNER;
+    const int pad_vecs = (slice_w - HH_INNER) / 4;       // zero-filled pad columns of the dx slice, 4 per lane
+    float* my_d = dring + (2 * wib + half) * 2;
+    auto issue = [&](unsigned long long rb, int sl) {
+        const unsigned long long r = rb + (unsigned)half;
+        if (r < rows) {
+            const __nv_bfloat16* xr = x + (long long)r * ld_x + l16 * 4;
+#pragma unroll
+            for (int j = 0; j < HH_NV; ++j) vk_cp_async8(ring2 + (sl * HH_NV + j) * HT_THREADS + threadIdx.x, xr + 64 * j);
+            if (l16 == 0 || (l16 == 1 && softplus)) vk_cp_async4(my_d + sl * 2 * HT_WARPS * 2 + l16, (l16 == 0 ? dout : out) + r);
+        }
+        vk_cp_async_commit();
+    };
+#pragma unroll 1
+    for (int d = 0; d < HH_RING; ++d) issue((unsigned long long)row0 + (unsigned long long)d * stride, d);
+    int slot = 0;
+    for (unsigned rb = row0; rb < rows; rb += stride) {
+        const bool live = rb + (unsigned)half < rows;
+        vk_cp_async_wait<HH_RING - 1>();
+        __syncwarp();                                   // the upstream values were copied by other lanes
+        float2 f[HH_NV][2];
+#pragma unroll
+        for (int j = 0; j < HH_NV; ++j) {
+            uint2 raw = make_uint2(0u, 0u);
+            if (live) raw = ring2[(slot * HH_NV + j) * HT_THREADS + threadIdx.x];
+            f[j][0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u));
+            f[j][1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+        }
+        float d = live ? my_d[slot * 2 * HT_WARPS * 2] : 0.f;
+        if (softplus) {
+            const float y = live ? my_d[slot * 2 * HT_WARPS * 2 + 1] : 0.f;
+            d *= (y > 20.f) ? 1.f : (1.f - __expf(-y));   // sigmoid(pre) = 1 - exp(-softplus(pre))
+        }
+        adb += d;
+        const float2 dpre = vk_splat2(d);
+        __syncwarp();                                   // every lane has read the slot before it is refilled
+        issue((unsigned long long)rb + (unsigned long long)HH_RING * stride, slot);
+        slot = (slot + 1) & (HH_RING - 1);
+        float mean, rstd;
+        {
+            const float x0 = __shfl_sync(0xffffffffu, f[0][0].x, lane & 16);
+            const float2 nx0 = vk_splat2(-x0);
+            float2 sm = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < HH_NV; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float2 dd = vk_add2(f[j][i], nx0);
+                    sm = vk_add2(sm, dd);
+                    q = vk_fma2(dd, dd, q);
+                }
+            const float2 rsum = half_sum2(sm.x + sm.y, q.x + q.y);
+            const float m = rsum.x * inv;                     // mean - x0
+            mean = x0 + m;
+            rstd = rsqrtf(fmaxf(fmaf(-m, m, rsum.y * inv), 0.f) + LN_EPS);
+        }
+        const float2 rstd2 = vk_splat2(rstd), shift2 = vk_splat2(-mean * rstd);
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+        float2 dz[HH_NV][2];
+#pragma unroll
+        for (int j = 0; j < HH_NV; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float2 h = vk_fma2(f[j][i], rstd2, shift2);
+                float2 g, gp;
+                vk_gelu_both2(vk_fma2(h, gm[j][i], bt[j][i]), &g, &gp);
+                aw[j][i] = vk_fma2(dpre, g, aw[j][i]);
+                const float2 dd = vk_mul2(vk_mul2(dpre, w[j][i]), gp);
+                const float2 dxh = vk_mul2(dd, gm[j][i]);
+                f[j][i] = h;
+                dz[j][i] = dxh;
+                s1 = vk_add2(s1, dxh);
+                s2 = vk_fma2(dxh, h, s2);
+                ag[j][i] = vk_fma2(dd, h, ag[j][i]);
+                ab[j][i] = vk_add2(ab[j][i], dd);
+            }
+        const float2 ss = half_sum2(s1.x + s1.y, s2.x + s2.y);
+        // dx = rstd * (dz - m1 - xhat * m2) = dz * rstd + (xhat * (-m2 rstd) + (-m1 rstd))
+        const float2 cb = vk_splat2(-ss.x * inv * rstd), cc = vk_splat2(-ss.y * inv * rstd);
+        if (live) {
+            __nv_bfloat16* dxr = dx + (long long)(rb + (unsigned)half) * ld_dx;
+#pragma unroll
+            for (int j = 0; j < HH_NV; ++j) {
+                const float2 d0 = vk_fma2(dz[j][0], rstd2, vk_fma2(f[j][0], cc, cb));
+                const float2 d1 = vk_fma2(dz[j][1], rstd2, vk_fma2(f[j][1], cc, cb));
+                ax[j][0] = vk_add2(ax[j][0], d0);
+                ax[j][1] = vk_add2(ax[j][1], d1);
+                uint2 pk;
+                *reinterpret_cast<__nv_bfloat162*>(&pk.x) = __floats2bfloat162_rn(d0.x, d0.y);
+                *reinterpret_cast<__nv_bfloat162*>(&pk.y) = __floats2bfloat162_rn(d1.x, d1.y);
+                *reinterpret_cast<uint2*>(dxr + (l16 + 16 * j) * 4) = pk;
+            }
+            if (l16 < pad_vecs) *reinterpret_cast<uint2*>(dxr + HH_INNER + l16 * 4) = make_uint2(0u, 0u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < HH_NV; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c = (l16 + 16 * j) * 4 + 2 * i;
+            atomicAdd(&sacc[c], ag[j][i].x);                   atomicAdd(&sacc[c + 1], ag[j][i].y);
+            atomicAdd(&sacc[HH_INNER + c], ab[j][i].x);        atomicAdd(&sacc[HH_INNER + c + 1], ab[j][i].y);
+            atomicAdd(&sacc[2 * HH_INNER + c], ax[j][i].x);    atomicAdd(&sacc[2 * HH_INNER + c + 1], ax[j][i].y);
+            atomicAdd(&sacc[3 * HH_INNER + c], aw[j][i].x);    atomicAdd(&sacc[3 * HH_INNER + c + 1], aw[j][i].y);
+        }
+    if (l16 == 0) atomicAdd(&sacc[4 * HH_INNER], adb);
+    __syncthreads();
+    for (int c = threadIdx.x; c < HH_INNER; c += blockDim.x) {
+        atomicAdd(dgamma + c, sacc[c]);
+        atomicAdd(dbeta + c, sacc[HH_INNER + c]);
+        atomicAdd(dbias + c, sacc[2 * HH_INNER + c]);
+        atomicAdd(dw2 + c, sacc[3 * HH_INNER + c]);
+    }
+    if (threadIdx.x == 0) atomicAdd(db2, sacc[4 * HH_INNER]);
+}
+
+int launch_bwd_h192(const void* x, long long ld_x, int slice_w, const float* gamma, const float* beta, const float* w2, int softplus,
+                    const float* out, const float* dout, long long rows, void* dx, long long ld_dx, float* dgamma, float* dbeta,
+                    float* dw2, float* db2, float* dbias, cudaStream_t s) {
+    long long blocks = (rows + 2 * HT_WARPS - 1) / (2 * HT_WARPS);
+    const long long cap = (long long)vkocr_sm_count() * 2;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)HH_RING * HH_NV * HT_THREADS * 8 + (HH_RING * 2 * HT_WARPS * 2 + 4 * HH_INNER + 1) * sizeof(float);
+    head_tail_bwd_h192_kernel<<<(unsigned)blocks, HT_THREADS, smem, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ld_x, slice_w, gamma, beta, w2, softplus, out, dout, (unsigned)rows,
+        reinterpret_cast<__nv_bfloat16*>(dx), ld_dx, dgamma, dbeta, dw2, db2, dbias);
+    return 0;
+}
+
 template <typename T, int NVL>
 int launch_fwd(int O, const void* x, long long ld_x, int inner, const float* gamma, const float* beta, const float* w2,
                const float* b2, int softplus, float* out, long long ppi, long long rows, const int* row_index, cudaStream_t s) {
@@ -548,6 +724,12 @@ int vkocr_head_tail_bwd(int dtype, const void* x, long long ld_x, int inner, int
     if (rows == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int rc = 0;
+    static const bool generic_only = getenv("VKOCR_HEAD_TAIL_GENERIC") != nullptr;     // A/B switch for tools/kbench.py
+    if (dtype == VKOCR_BF16 && inner == HH_INNER && O == 1 && slice_w - HH_INNER <= 64 && ld_x % 4 == 0 && ld_dx % 4 == 0 && !generic_only) {
+        launch_bwd_h192(x, ld_x, slice_w, gamma, beta, w2, softplus, out, dout, rows, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, s);
+        VK_CHECK_LAUNCH("head_tail_bwd_h192_kernel");
+        return VKOCR_OK;
+    }
 #define VK_CALL(NVL) VK_DISPATCH_DTYPE(dtype, T, (rc = launch_bwd<T, NVL>(O, x, ld_x, inner, slice_w, gamma, beta, w2, softplus, out, dout, pixels_per_image, rows, dx, ld_dx, dgamma, dbeta, dw2, db2, dbias, nullptr, 0, s)))
     if (nvl == 1) VK_CALL(1);
     else if (nvl == 2) VK_CALL(2);

@@ -582,22 +582,26 @@ class ConvNextLayerFn(torch.autograd.Function):
         dh = torch.empty((M, hid), dtype=dt, device=dev)
         gemm_nt(dy, 1, 1, M, C, dy.stride(3), 1, w2d, n2, hid, _epilogue(dh, hid, act=4, aux=hpre, ld_aux=hid))
         # sU[c] = sum_p m_b dY[p,c];  S[c,k] = sum_p dY[p,c] G[p,k] over the kept samples (x 1/p_keep in the finaliser)
-        su = _zeros_f32(C, dev)
+        # one zero-fill for the three fp32 accumulators of this layer (sU, S and [dW1 | db1]): they are a few MB, the launches
+        # are what costs
+        ones_tail = lnout.stride(3) == C + 8
+        acc = _zeros_f32(C + C * hid + (hid * (C + 8) if ones_tail else 0), dev)
+        su = acc[:C]
         if ctx.has_mask:
             L.check(L.LIB.vkocr_scale_rows_colsum(_tag(dt), L.ptr(dy), dy.stride(3), None, 0, M, C, L.ptr(mask), H * W, L.ptr(su), _s()),
                     'scale_rows_colsum')
         else:
             colsum(dy, dy.stride(3), M, C, su)
-        s = _zeros_f32(C * hid, dev)
+        s = acc[C:C + C * hid]
         gemm_tn(dy, 1, 1, M, C, dy.stride(3), 1, g, hid, hid, _epilogue(s, hid, out_f32=True, accumulate=True, tn=(0, hid, 1)))
         L.check(L.LIB.vkocr_mlp2_grad_finalize(L.ptr(s), hid, ctx.inv_keep, L.ptr(su), 1, L.ptr(w2.detach()), L.ptr(b2.detach()),
                                                L.ptr(gamma), C, hid, L.ptr(grad_buffer(w2)), L.ptr(grad_buffer(scale)),
                                                L.ptr(grad_buffer(b2)), _s()),
                 'mlp2_grad_finalize')
-        del s, g
+        del g
         ldl = lnout.stride(3)
-        if ldl == C + 8:          # LN_out carries the ones channel (see forward): dW1 and db1 from one GEMM
-            gwb = _zeros_f32(hid * (C + 8), dev)
+        if ones_tail:             # LN_out carries the ones channel (see forward): dW1 and db1 from one GEMM
+            gwb = acc[C + C * hid:]
             gemm_tn(dh, 1, 1, M, hid, hid, 1, lnout, C + 8, ldl, _epilogue(gwb, C + 8, out_f32=True, accumulate=True, tn=(0, C + 8, 1)))
             L.check(L.LIB.vkocr_scatter_add_f32(L.ptr(gwb), C + 8, 0, 1, hid, 1, C, L.ptr(grad_buffer(w1)), C, 0, 1, _s()), 'scatter_add_f32')
             L.check(L.LIB.vkocr_scatter_add_f32(ctypes.c_void_p(gwb.data_ptr() + 4 * C), C + 8, 0, 0, hid, 1, 1, L.ptr(grad_buffer(b1)), 1, 0, 0,
