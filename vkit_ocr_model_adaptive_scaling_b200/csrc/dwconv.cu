@@ -227,13 +227,10 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
         : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
     d = *reinterpret_cast<float2*>(&dd);
 }
-// two bf16 channels in one 32-bit word -> an fp32 pair.  Both halves are produced on the ALU pipe (PRMT, LOP3): ptxas turns a
-// plain `raw << 16` into IMAD.U32 on every other conversion "to balance the pipes", and the FMA pipe is the one these kernels
-// are short of (28 IMADs beside 112 FFMA2s per halo row).
+// two bf16 channels in one 32-bit word -> an fp32 pair (one shift, one mask; a PRMT for the low half instead of the shift,
+// which ptxas turns into IMAD.U32 on the FMA pipe, measured no faster: the kernels are not bound by that pipe's throughput)
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t raw) {
-    uint32_t lo;
-    asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(raw));
-    return make_float2(__uint_as_float(lo), __uint_as_float(raw & 0xffff0000u));
+    return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
 }
 
 // Column-wise halo loader: thread -> one 16-byte quarter of one halo column, walking down the HALO_H rows with a
@@ -378,6 +375,102 @@ dwconv7_tile_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bf
     }
 }
 
+// Forward / data gradient, second arrangement (TW % 8 == 0): thread -> 4 channels x an 8 x 1 pixel strip.  The 4 x 2 patch
+// above reads every tap vector twice (once per output row) and delivers 0.70 shared-memory wavefronts per FFMA2 -- the LSU
+// data pipe (one 128-byte wavefront per clock and SM; a 16-byte-per-lane tap load costs 4 of them however much of it is a
+// broadcast) runs at 1.2x the FMA pipe's time and bounds the kernel.  Here the 7 tap vectors of a kernel row stay in
+// registers for the whole strip and each of the 14 input pixels of the row is loaded and converted once, then applied to
+// every output it reaches:  acc[o] += w[j - o] * in[j]  -- 0.50 wavefronts per FFMA2, below the FMA pipe's time.
+__host__ __device__ constexpr int rs_strip(int tw) { return ((tw + 6) * PIX_B) % 128 == 0 ? (tw + 6) * PIX_B + 64 : (tw + 6) * PIX_B; }
+template <int TW>
+__global__ void __launch_bounds__(8 * TW, 2)
+dwconv7_strip_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bfloat16* __restrict__ y, long long ld_y, int B,
+                     int H, int W, int C, const float* __restrict__ wt, const float* __restrict__ bias,
+                     const __nv_bfloat16* __restrict__ add, long long ld_add, int tiles_x, int tiles_y, int ntiles) {
+    static_assert(TW % 8 == 0, "8-pixel strips");
+    constexpr int RS = rs_strip(TW);             // consecutive rows land 64 B apart (mod 128): the 4 strips of a warp are stacked in y
+    constexpr int BUF = HALO_H * RS;
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    uint8_t* s_in = dw_smem;                                             // [2][HALO_H][RS]
+    float* s_w = reinterpret_cast<float*>(dw_smem + 2 * BUF);            // [49][CB]
+    float* s_b = s_w + 49 * CB;                                          // [CB]
+    const int c0 = blockIdx.y * CB;
+    const uint32_t s_in_a = (uint32_t)__cvta_generic_to_shared(s_in);
+    int t = blockIdx.x;
+    if (t < ntiles) load_halo_cols<TW, RS>(s_in_a, x, ld_x, tile_coord<TW>(t, tiles_x, tiles_y), H, W, c0);
+    vk_cp_async_commit();
+    for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) s_w[i] = __ldg(wt + (long long)(i / CB) * C + c0 + (i % CB));
+    if (threadIdx.x < CB) s_b[threadIdx.x] = bias ? __ldg(bias + c0 + threadIdx.x) : 0.f;
+    const int cq = threadIdx.x & 7;
+    const int sidx = threadIdx.x >> 3;          // 0 .. TW - 1
+    const int py = sidx & 7, px = (sidx >> 3) * 8;
+    int buf = 0;
+    for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+        const TileCoord tc = tile_coord<TW>(t, tiles_x, tiles_y);
+        vk_cp_async_wait<0>();
+        __syncthreads();                        // tile t has landed; everybody is done with the other buffer
+        if (t + (int)gridDim.x < ntiles)
+            load_halo_cols<TW, RS>(s_in_a + (uint32_t)((buf ^ 1) * BUF), x, ld_x, tile_coord<TW>(t + gridDim.x, tiles_x, tiles_y), H, W, c0);
+        vk_cp_async_commit();
+        float2 acc[8][2];
+        {
+            const float4 bv = *reinterpret_cast<const float4*>(s_b + cq * 4);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) { acc[o][0] = make_float2(bv.x, bv.y); acc[o][1] = make_float2(bv.z, bv.w); }
+        }
+        const uint8_t* rowp = s_in + buf * BUF + py * RS + px * PIX_B + cq * 8;
+        const float* wk = s_w + cq * 4;
+#pragma unroll 1
+        for (int ky = 0; ky < 7; ++ky, rowp += RS, wk += 7 * CB) {
+            float2 w[7][2];
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wk + kx * CB);
+                w[kx][0] = make_float2(w4.x, w4.y);
+                w[kx][1] = make_float2(w4.z, w4.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 14; ++j) {
+                const uint2 raw = *reinterpret_cast<const uint2*>(rowp + j * PIX_B);
+                const float2 i0 = bf2_to_f2(raw.x), i1 = bf2_to_f2(raw.y);
+#pragma unroll
+                for (int o = (j > 6 ? j - 6 : 0); o <= (j < 7 ? j : 7); ++o) {
+                    ffma2(acc[o][0], w[j - o][0], i0);
+                    ffma2(acc[o][1], w[j - o][1], i1);
+                }
+            }
+        }
+        const int yy = tc.y0 + py;
+        if (yy < H) {
+            const long long pix0 = ((long long)tc.b * H + yy) * W + tc.x0 + px;
+            __nv_bfloat16* yp = y + pix0 * ld_y + c0 + cq * 4;
+            const __nv_bfloat16* ap = add ? add + pix0 * ld_add + c0 + cq * 4 : nullptr;
+            uint2 av[8];
+            if (add) {
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    av[o] = make_uint2(0u, 0u);
+                    if (tc.x0 + px + o < W) av[o] = __ldg(reinterpret_cast<const uint2*>(ap + (long long)o * ld_add));
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                if (tc.x0 + px + o < W) {
+                    float2 a0 = acc[o][0], a1 = acc[o][1];
+                    if (add) {
+                        const float2 f0 = bf2_to_f2(av[o].x), f1 = bf2_to_f2(av[o].y);
+                        a0.x += f0.x; a0.y += f0.y; a1.x += f1.x; a1.y += f1.y;
+                    }
+                    uint2 raw;
+                    *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(a0.x, a0.y);
+                    *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(a1.x, a1.y);
+                    *reinterpret_cast<uint2*>(yp + (long long)o * ld_y) = raw;
+                }
+            }
+        }
+    }
+}
+
 // Weight gradient.  Thread -> 4 channels (cq) x one kernel row ky x one tile row; it slides along x keeping the 7 input
 // vectors of its window in registers: acc[kx][4] += dy[y][x][4] * in[y + ky][x + kx][4].  Persistent over the tiles of one
 // 32-channel block with double-buffered (halo tile of x, tile of dy) stages: the copies of tile t+1 fly while tile t is
@@ -471,7 +564,39 @@ dwconv7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy,
     for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) atomicAdd(dw + (long long)(c0 + i % CB) * 49 + i / CB, s_acc[i]);
 }
 
-inline int pick_tw(int W) { return (W % 40 == 0) ? 40 : ((W % 20 == 0 && W < 40) ? 20 : 32); }
+inline int pick_tw(int W) {
+    static const int forced = getenv("VKOCR_DW_TW") ? atoi(getenv("VKOCR_DW_TW")) : 0;      // experiments
+    if (forced && W % forced == 0) return forced;
+    return (W % 40 == 0) ? 40 : ((W % 20 == 0 && W < 40) ? 20 : 32);
+}
+// forward / data gradient: 16-pixel-wide strip tiles where they tile the map exactly (4 blocks of 4 warps per SM: the per-tile
+// block barrier costs less with small blocks -- 160 x 160 x 96: 0.250 ms with 40-wide tiles, 0.234 with 16-wide ones)
+inline int pick_tw_fwd(int W) {
+    const int tw = pick_tw(W);
+    static const bool forced = getenv("VKOCR_DW_TW") != nullptr;
+    return (!forced && W % 16 == 0) ? 16 : tw;
+}
+
+template <int TW>
+int launch_dw_strip(const void* x, long long ld_x, void* y, long long ld_y, int B, int H, int W, int C, const float* wt,
+                    const float* bias, const void* add, long long ld_add, cudaStream_t s) {
+    const int tiles_x = vk_cdiv(W, TW), tiles_y = vk_cdiv(H, TH);
+    const long long ntiles = (long long)B * tiles_x * tiles_y;
+    const int cblocks = C / CB;
+    const int smem = 2 * HALO_H * rs_strip(TW) + (49 * CB + CB) * (int)sizeof(float);
+    cudaFuncSetAttribute(dwconv7_strip_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_strip_kernel<TW>, 8 * TW, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    long long gx = ((long long)vkocr_sm_count() * per_sm) / cblocks;     // persistent: the resident block count, rounded DOWN
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    dwconv7_strip_kernel<TW><<<dim3((unsigned)gx, (unsigned)cblocks), 8 * TW, smem, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ld_x, reinterpret_cast<__nv_bfloat16*>(y), ld_y, B, H, W, C, wt, bias,
+        reinterpret_cast<const __nv_bfloat16*>(add), ld_add, tiles_x, tiles_y, (int)ntiles);
+    return 0;
+}
 
 template <int TW>
 int launch_dw_tile(const void* x, long long ld_x, void* y, long long ld_y, int B, int H, int W, int C, const float* wt,
@@ -481,10 +606,14 @@ int launch_dw_tile(const void* x, long long ld_x, void* y, long long ld_y, int B
     const int cblocks = C / CB;
     const int smem = 2 * HALO_H * rs_fwd(TW) + (49 * CB + CB) * (int)sizeof(float);
     // persistent: as many blocks as are resident at once (2 per SM by registers; shared memory allows it for every TW)
-    long long gx = ((long long)vkocr_sm_count() * 2) / cblocks;     // rounded DOWN: one block too many is a whole second wave
+    cudaFuncSetAttribute(dwconv7_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static int per_sm = 0;      // resident blocks per SM (2 by registers for TW = 40 / 32, 4 for TW = 20)
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_tile_kernel<TW>, 8 * TW, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    long long gx = ((long long)vkocr_sm_count() * per_sm) / cblocks;     // rounded DOWN: one block too many is a whole second wave
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
-    cudaFuncSetAttribute(dwconv7_tile_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dwconv7_tile_kernel<TW><<<dim3((unsigned)gx, (unsigned)cblocks), 8 * TW, smem, s>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), ld_x, reinterpret_cast<__nv_bfloat16*>(y), ld_y, B, H, W, C, wt, bias,
         reinterpret_cast<const __nv_bfloat16*>(add), ld_add, tiles_x, tiles_y, (int)ntiles);
@@ -530,8 +659,14 @@ int vkocr_dwconv7_fwd(int dtype, const void* x, long long ld_x, void* y, long lo
     if (total == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == VKOCR_BF16 && C % CB == 0 && (long long)B * H * W < (1LL << 30)) {
-        const int tw = pick_tw(W);
-        if (tw == 40) launch_dw_tile<40>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        const int tw = pick_tw_fwd(W);
+        static const bool patch_kernel = getenv("VKOCR_DW_PATCH") != nullptr;      // A/B switch for tools/kbench.py
+        if (tw == 40 && !patch_kernel) launch_dw_strip<40>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        else if (tw == 32 && !patch_kernel) launch_dw_strip<32>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        else if (tw == 16) launch_dw_strip<16>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        else if (tw == 8) launch_dw_strip<8>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        else if (tw == 24) launch_dw_strip<24>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        else if (tw == 40) launch_dw_tile<40>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
         else if (tw == 20) launch_dw_tile<20>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
         else launch_dw_tile<32>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
         VK_CHECK_LAUNCH("dwconv7_tile_kernel");
