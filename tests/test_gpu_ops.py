@@ -269,6 +269,48 @@ def test_head_convolve_first_kernels_agree(vk, kind):
             assert_close(results[0][2][n], other[2][n], 5e-5, f'{what}: grad {n}', atol=1e-6)
 
 
+@pytest.mark.parametrize('shape,train', [((2, 9, 13), True), ((1, 16, 8), False), ((3, 5, 7), True), ((1, 1, 1), True)])
+def test_head_combine_half_warp_tails(vk, shape, train, monkeypatch):
+    """Heads with inner = 192 and one map take the half-warp tail of the combine kernel (bf16): same conv rows bit for bit and
+    the same prediction maps up to the order of the warp reductions as the lane-per-vector tail."""
+    import ctypes
+    from vkit_ocr_model_adaptive_scaling_b200 import _lib as L, ops
+    dev = torch.device('cuda')
+    B, h, w = shape
+    H, W, slot, nh = 2 * h, 2 * w, 200, 2
+    ntot, nz = nh * slot, 9 * nh * slot
+    g = torch.Generator().manual_seed(h * 100 + w)
+    z = torch.randn(B * h * w, nz, generator=g).to(dev).to(torch.bfloat16)
+    bias = torch.randn(ntot, generator=g).to(dev)
+    par = [((torch.rand(192, generator=g) + 0.5).to(dev), (torch.randn(192, generator=g) * 0.1).to(dev),
+            (torch.randn(1, 192, generator=g) * 0.1).to(dev), torch.randn(1, generator=g).to(dev)) for _ in range(nh)]
+    # the pad channels of a slot: zero taps / zero bias, as the packer writes them
+    zv = z.view(B * h * w, 9, nh, slot)
+    zv[..., 192:] = 0
+    bias.view(nh, slot)[:, 192:] = 0
+
+    def run():
+        outs = [torch.full((B, 1, H, W), -3.0, device=dev) for _ in range(nh)]
+        conv = torch.full((B * H * W, ntot), 5.0, device=dev, dtype=torch.bfloat16)
+        ht = L.HeadTail()
+        ht.num_heads, ht.slot, ht.pixels_per_image = nh, slot, H * W
+        for i in range(nh):
+            ht.gamma[i], ht.beta[i], ht.w2[i], ht.b2[i] = (t.data_ptr() for t in par[i])
+            ht.out[i] = outs[i].data_ptr()
+            ht.inner[i], ht.out_channels[i], ht.softplus[i] = 192, 1, i
+        L.check(L.LIB.vkocr_head_combine_fwd(1, L.ptr(z), nz, B, h, w, 2, 0, 3, ntot, L.ptr(bias), ctypes.byref(ht),
+                                             L.ptr(conv) if train else None, ntot if train else 0, 0, L.stream_ptr()), 'head_combine_fwd')
+        torch.cuda.synchronize()
+        return outs, conv
+    outs_h, conv_h = run()
+    monkeypatch.setenv('VKOCR_HC_NOHALF', '1')
+    outs_v, conv_v = run()
+    if train:
+        assert torch.equal(conv_h, conv_v), 'conv rows differ between the two tails'
+    for a, b in zip(outs_h, outs_v):
+        assert_close(a, b, 1e-5, 'prediction map: half-warp vs lane-per-vector tail', atol=1e-5)
+
+
 @pytest.mark.parametrize('rows_shape,slot,softplus', [((3, 37, 41), 192, 0), ((2, 24, 31), 200, 1), ((1, 1, 1), 192, 1), ((1, 64, 64), 200, 0)])
 def test_head_tail_backward_half_warp_kernel(vk, rows_shape, slot, softplus):
     """The inner = 192 / one-map backward (a half-warp per pixel row: every dense call of the training step) against the

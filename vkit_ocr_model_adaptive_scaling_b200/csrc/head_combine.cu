@@ -484,7 +484,90 @@ __device__ __forceinline__ void hc_tail2(const float2 (&c0)[NVL][NP], const floa
     }
 }
 
-template <typename T, int NVL, int O, int HC_R, int THREADS, int MINB>
+// Channel order of a V entry: interleaved planes (hc_plane) for one-lane-per-16-byte-vector readers, plain channel order for
+// the half-warp readers below (a lane reads the float4s l16, l16 + 16, l16 + 32 of a 192-channel entry).
+template <bool LIN>
+__device__ __forceinline__ int hc_voff(int cv, int e, int nvec) { return LIN ? cv * 8 + (e >> 2) * 4 : hc_plane(cv, e, nvec); }
+
+// The tail for heads with inner = 192 and one output map (both rough heads, the precise mask head) with a HALF-warp per
+// (row, low-res column): 192 channels are 24 16-byte vectors, so with a lane per vector a quarter of the warp idles and the
+// per-pixel reductions serve two pixels; here a lane owns 12 channels (float4s l16 + 16 k of the entry) of the unit's two
+// pixels, every lane works, and one round of shuffles serves the four pixels of the warp's two units.
+constexpr int HH_K = 3;      // float4s per lane
+struct TailParH {
+    float2 gm[HH_K][2], bt[HH_K][2], w[HH_K][2];
+    float bias2;
+    __device__ __forceinline__ void load(const HeadArgs& hd, int l16) {
+#pragma unroll
+        for (int k = 0; k < HH_K; ++k)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int c = 4 * (l16 + 16 * k) + 2 * i;
+                gm[k][i] = make_float2(__ldg(hd.gamma + c), __ldg(hd.gamma + c + 1));
+                bt[k][i] = make_float2(__ldg(hd.beta + c), __ldg(hd.beta + c + 1));
+                w[k][i] = make_float2(__ldg(hd.w2 + c), __ldg(hd.w2 + c + 1));
+            }
+        bias2 = __ldg(hd.b2);
+    }
+};
+__device__ __forceinline__ void hc_tail2_half(const float2 (&c0)[HH_K][2], const float2 (&c1)[HH_K][2], const TailParH& tp, int lane,
+                                              int softplus, bool valid, float* out0, float* out1) {
+    const int base = lane & 16;
+    const float x0 = __shfl_sync(0xffffffffu, c0[0][0].x, base);
+    const float x1 = __shfl_sync(0xffffffffu, c1[0][0].x, base);
+    const float2 n0 = vk_splat2(-x0), n1 = vk_splat2(-x1);
+    float2 s0 = make_float2(0.f, 0.f), q0 = s0, s1 = s0, q1 = s0;
+#pragma unroll
+    for (int k = 0; k < HH_K; ++k)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float2 d0 = vk_add2(c0[k][i], n0), d1 = vk_add2(c1[k][i], n1);
+            s0 = vk_add2(s0, d0);
+            q0 = vk_fma2(d0, d0, q0);
+            s1 = vk_add2(s1, d1);
+            q1 = vk_fma2(d1, d1, q1);
+        }
+    // four values over 16 lanes, half of them kept per round: lane bit 3 selects the pixel, bit 2 sum / sum of squares
+    float t;
+    {
+        const float a0 = s0.x + s0.y, a1 = q0.x + q0.y, a2 = s1.x + s1.y, a3 = q1.x + q1.y;
+        const bool up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
+        const float v0 = (up8 ? a2 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a2, 8);
+        const float v1 = (up8 ? a3 : a1) + __shfl_xor_sync(0xffffffffu, up8 ? a1 : a3, 8);
+        t = (up4 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, up4 ? v0 : v1, 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+    }
+    const float sA = __shfl_sync(0xffffffffu, t, base), qA = __shfl_sync(0xffffffffu, t, base + 4);
+    const float sB = __shfl_sync(0xffffffffu, t, base + 8), qB = __shfl_sync(0xffffffffu, t, base + 12);
+    constexpr float inv = 1.f / 192.f;
+    const float mA = sA * inv, mB = sB * inv;                                                     // mean - x0
+    const float rA = rsqrtf(fmaxf(fmaf(-mA, mA, qA * inv), 0.f) + LN_EPS), rB = rsqrtf(fmaxf(fmaf(-mB, mB, qB * inv), 0.f) + LN_EPS);
+    const float2 rs0 = vk_splat2(rA), sh0 = vk_splat2(-(x0 + mA) * rA), rs1 = vk_splat2(rB), sh1 = vk_splat2(-(x1 + mB) * rB);
+    float2 d0 = make_float2(0.f, 0.f), d1 = d0;
+#pragma unroll
+    for (int k = 0; k < HH_K; ++k)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float2 g0 = hc_gelu2(vk_fma2(vk_fma2(c0[k][i], rs0, sh0), tp.gm[k][i], tp.bt[k][i]));
+            const float2 g1 = hc_gelu2(vk_fma2(vk_fma2(c1[k][i], rs1, sh1), tp.gm[k][i], tp.bt[k][i]));
+            d0 = vk_fma2(g0, tp.w[k][i], d0);
+            d1 = vk_fma2(g1, tp.w[k][i], d1);
+        }
+    const bool up8 = (lane & 8) != 0;
+    const float p0 = d0.x + d0.y, p1 = d1.x + d1.y;
+    float v = (up8 ? p1 : p0) + __shfl_xor_sync(0xffffffffu, up8 ? p0 : p1, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (valid && (lane & 7) == 0) {
+        v += tp.bias2;
+        if (softplus) v = vk_softplus(v);
+        *(up8 ? out1 : out0) = v;
+    }
+}
+
+template <typename T, int NVL, int O, int HC_R, int THREADS, int MINB, bool HALF = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ conv, long long ld_conv, int cw, int tiles_j,
                   int tiles_i, long long ntiles) {
@@ -497,10 +580,12 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
     float2* sWc = sWr + HC_R * 2 * 3 * 2;                                     // [TJ][2][3] column-pair weights (wA, wB)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cvn = cw / V;                            // channel vectors that hold real channels
-    TailPar2<NVL, NP, O> tp;
-    tp.load(hd, lane);
+    TailPar2<HALF ? 1 : NVL, HALF ? 1 : NP, HALF ? 1 : O> tp;      // (unused with HALF)
+    TailParH tph;
+    if constexpr (HALF) tph.load(hd, lane & 15);
+    else tp.load(hd, lane);
     for (int c = threadIdx.x; c < cw; c += blockDim.x)
-        sBias[hc_plane(c / V, c % V, cvn) + (c & 3)] = c < hd.inner ? __ldg(hd.bias + c) : 0.f;
+        sBias[hc_voff<HALF>(c / V, c % V, cvn) + (c & 3)] = c < hd.inner ? __ldg(hd.bias + c) : 0.f;
     const long long ppi = (long long)g.H * g.W;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int jt = (int)(tile % tiles_j);
@@ -595,12 +680,78 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
                         float* dst = sV + ((((li * 2 + a) * 3 + dx) * HC_QL + ql)) * cw;
 #pragma unroll
                         for (int e = 0; e < NP; e += 2)
-                            *reinterpret_cast<float4*>(dst + hc_plane(cv, 2 * e, cvn)) =
+                            *reinterpret_cast<float4*>(dst + hc_voff<HALF>(cv, 2 * e, cvn)) =
                                 make_float4(acc[li][a][e].x, acc[li][a][e].y, acc[li][a][e + 1].x, acc[li][a][e + 1].y);
                     }
             }
         }
         __syncthreads();
+        if constexpr (HALF) {
+            // ---------------- phase 2, half-warp flavour: a warp takes two neighbouring low-res columns of one output row
+            const int l16 = lane & 15;
+            for (int u2 = warp; u2 < HC_R * HC_TJ; u2 += (blockDim.x >> 5)) {
+                const int unit = 2 * u2 + (lane >> 4);
+                const int jl = unit % HC_TJ;
+                const int la = unit / HC_TJ;               // li * 2 + a
+                const int i = i0 + (la >> 1), j = j0 + jl;
+                if (i >= g.h || j0 + (jl & ~1) >= g.w) continue;       // warp-uniform: the row or both columns are outside
+                const bool valid = j < g.w;
+                int qm = j - 1, qp = j + 1;
+                qm = qm < 0 ? 0 : qm;
+                qp = qp > g.w - 1 ? g.w - 1 : qp;
+                int col[3] = {qm - (j0 - 1), jl + 1, qp - (j0 - 1)};
+                if (!valid) col[0] = col[1] = col[2] = 0;
+                float2 c0[HH_K][2], c1[HH_K][2];
+#pragma unroll
+                for (int k = 0; k < HH_K; ++k) {
+                    const float4 bv = *reinterpret_cast<const float4*>(sBias + 4 * (l16 + 16 * k));
+                    c0[k][0] = c1[k][0] = make_float2(bv.x, bv.y);
+                    c0[k][1] = c1[k][1] = make_float2(bv.z, bv.w);
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float2 w0 = sWc[(jl * 2 + 0) * 3 + d], w1 = sWc[(jl * 2 + 1) * 3 + d];
+                    const float* base = sV + ((la * 3 + d) * HC_QL) * cw;
+#pragma unroll
+                    for (int pp = 0; pp < 3; ++pp) {
+                        float u0 = 0.f, u1 = 0.f;
+                        bool r0 = false, r1 = false;
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            if (hc_pos(0, d, kk) == pp - 1) { r0 = true; u0 = kk ? w0.y : w0.x; }
+                            if (hc_pos(1, d, kk) == pp - 1) { r1 = true; u1 = kk ? w1.y : w1.x; }
+                        }
+                        if (!r0 && !r1) continue;
+                        const float2 u02 = vk_splat2(u0), u12 = vk_splat2(u1);
+                        const float* src = base + col[pp] * cw + 4 * l16;
+#pragma unroll
+                        for (int k = 0; k < HH_K; ++k) {
+                            const float4 v = *reinterpret_cast<const float4*>(src + 64 * k);
+                            const float2 va = make_float2(v.x, v.y), vb = make_float2(v.z, v.w);
+                            if (r0) { c0[k][0] = vk_fma2(u02, va, c0[k][0]); c0[k][1] = vk_fma2(u02, vb, c0[k][1]); }
+                            if (r1) { c1[k][0] = vk_fma2(u12, va, c1[k][0]); c1[k][1] = vk_fma2(u12, vb, c1[k][1]); }
+                        }
+                    }
+                }
+                const int y = 2 * i + (la & 1), x = 2 * j;
+                const long long rem = (long long)y * g.W + x;
+                if (conv && valid) {
+                    T* cr = conv + ((long long)b * ppi + rem) * ld_conv + hd.col0 + 4 * l16;
+#pragma unroll
+                    for (int k = 0; k < HH_K; ++k) {
+                        uint2 p0, p1;
+                        *reinterpret_cast<__nv_bfloat162*>(&p0.x) = __floats2bfloat162_rn(c0[k][0].x, c0[k][0].y);
+                        *reinterpret_cast<__nv_bfloat162*>(&p0.y) = __floats2bfloat162_rn(c0[k][1].x, c0[k][1].y);
+                        *reinterpret_cast<__nv_bfloat162*>(&p1.x) = __floats2bfloat162_rn(c1[k][0].x, c1[k][0].y);
+                        *reinterpret_cast<__nv_bfloat162*>(&p1.y) = __floats2bfloat162_rn(c1[k][1].x, c1[k][1].y);
+                        __stcs(reinterpret_cast<uint2*>(cr + 64 * k), p0);
+                        __stcs(reinterpret_cast<uint2*>(cr + ld_conv + 64 * k), p1);
+                    }
+                }
+                float* o0 = hd.out + (long long)b * ppi + (valid ? rem : 0);
+                hc_tail2_half(c0, c1, tph, lane, hd.softplus, valid, o0, o0 + 1);
+            }
+        } else
         // ---------------- phase 2: one warp per (row, low-res column): its two output pixels (column parity 0 / 1) together
         for (int unit = warp; unit < HC_R * 2 * HC_TJ; unit += (blockDim.x >> 5)) {
             const int jl = unit % HC_TJ;
@@ -849,6 +1000,10 @@ int hc_launch_fwd(const void* z, const Geom& g, const HeadArgs& hd, void* conv, 
             const int tiles_j = vk_cdiv(g.w, HC_TJ), tiles_i = vk_cdiv(g.h, R);
             const long long ntiles = (long long)g.B * tiles_i * tiles_j;
             auto kern = hc_fwd_2x3_kernel<T, NVL, O, R, THREADS, MINB>;
+            if constexpr (std::is_same<T, __nv_bfloat16>::value && NVL == 1 && O == 1) {
+                const bool no_half = getenv("VKOCR_HC_NOHALF") != nullptr;      // A/B switch (tests, tools/profile_combine.py)
+                if (hd.inner == 192 && !no_half) kern = hc_fwd_2x3_kernel<T, NVL, O, R, THREADS, MINB, true>;   // half-warp tails
+            }
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return 2;
             int per_sm = (int)((220 * 1024) / (smem + 1024));

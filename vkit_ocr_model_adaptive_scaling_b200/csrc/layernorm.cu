@@ -272,7 +272,13 @@ __device__ __forceinline__ float2 group_sum2(float a, float b) {
 }
 
 // ring depth: about 8 KB .. 24 KB of vectors per block
-template <int NV, int STREAMS> struct LnRing { static constexpr int value = (NV * STREAMS >= 6) ? 2 : ((NV * STREAMS >= 3) ? 3 : 4); };
+#ifndef VK_LN_DEEP
+#define VK_LN_DEEP 1
+#endif
+template <int NV, int STREAMS> struct LnRing {
+    static constexpr int value = VK_LN_DEEP ? ((NV * STREAMS >= 6) ? 2 : ((NV * STREAMS >= 4) ? 4 : ((NV * STREAMS >= 3) ? 4 : 8)))
+                                            : ((NV * STREAMS >= 6) ? 2 : ((NV * STREAMS >= 3) ? 3 : 4));
+};
 
 // y = LN(x) (* optional GELU).  G lanes per row, NV vectors per lane; R = 32 / G rows per warp iteration.
 template <typename T, int G, int NV>
@@ -384,7 +390,7 @@ ln_fwd_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long l
 
 // Backward.  Each lane owns the same channel vectors for all rows it visits, so its column partials stay in registers.
 template <typename T, int G, int NV>
-__global__ void __launch_bounds__(FT)
+__global__ void __launch_bounds__(FT, NV == 1 ? 3 : (NV == 2 ? 2 : 1))
 ln_bwd_fast_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restrict__ x, long long ld_x,
                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                    const float* __restrict__ beta, int act, T* __restrict__ dx, long long ld_dx, long long rows, int C,
@@ -634,17 +640,20 @@ bool launch_ln_bwd_fast(const void* dy, long long ld_dy, const void* x, long lon
     const int R = 32 / G;
     const long long iters = (rows + R - 1) / R;
     long long blocks = (iters + FT / 32 - 1) / (FT / 32);
-    long long cap = (long long)vkocr_sm_count() * 4;
+    long long cap = (long long)vkocr_sm_count() * 4;       // replaced below by the resident block count of the instantiation
     // small maps: every block ends with 3 C shared -> global atomics and starts with a parameter / accumulator prologue, so a
     // warp should see at least ~8 row-iterations (12 800 x 768: 592 -> 200 blocks, 0.059 -> 0.033 ms)
     const long long by_work = iters / ((FT / 32) * 8);
-    if (by_work < cap) cap = by_work > vkocr_sm_count() ? by_work : vkocr_sm_count();
-    if (blocks > cap) blocks = cap;
 #define VK_LN_BWD_FAST(GG, NN)                                                                                              \
     do {                                                                                                                     \
         constexpr int D = LnRing<NN, 2>::value;                                                                              \
         const size_t smem = (size_t)D * 2 * NN * FT * 16 + ((size_t)D * (FT / 32) * (32 / GG) * 2 + (size_t)5 * GG * NN * V) * sizeof(float); \
         cudaFuncSetAttribute(ln_bwd_fast_kernel<T, GG, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);         \
+        static int per_sm = 0;          /* one wave: a grid-stride block beyond the resident ones is a whole second wave */  \
+        if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ln_bwd_fast_kernel<T, GG, NN>, FT, smem) != cudaSuccess || per_sm < 1)) per_sm = 1; \
+        cap = (long long)vkocr_sm_count() * per_sm;                                                                          \
+        if (by_work < cap) cap = by_work > vkocr_sm_count() ? by_work : vkocr_sm_count();                                   \
+        if (blocks > cap) blocks = cap;                                                                                      \
         ln_bwd_fast_kernel<T, GG, NN><<<(unsigned)blocks, FT, smem, s>>>(                                                    \
             reinterpret_cast<const T*>(dy), ld_dy, reinterpret_cast<const T*>(x), ld_x, mean, rstd, gamma, beta, act,       \
             reinterpret_cast<T*>(dx), ld_dx, rows, C, dgamma, dbeta, dxsum);                                                 \
