@@ -263,6 +263,21 @@ __device__ __forceinline__ void vk_gelu_both2(float2 x, float2* g, float2* dg) {
     *g = vk_mul2(x, cdf);
     *dg = vk_fma2(x, pdf, cdf);
 }
+// Forward-only exact GELU of a pair: vk_gelu with the polynomial packed (one MUFU.EX2 per element).  A scalar 3-register FFMA
+// issues every other cycle per scheduler (tools/micro/ffma2_operands.cu: 68 FMA/clk/SM), the packed form does two lanes in
+// the same slot, so GELU-heavy epilogues and tails are written on pairs.
+__device__ __forceinline__ float2 vk_gelu2(float2 x) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 a = make_float2(fminf(ax.x, 9.f), fminf(ax.y, 9.f));
+    float2 q = vk_fma2(a, vk_splat2(-3.159132926264e-05f), vk_splat2(7.531542511152e-04f));
+    q = vk_fma2(q, a, vk_splat2(-8.015595779370e-03f));
+    q = vk_fma2(q, a, vk_splat2(5.328616913828e-02f));
+    q = vk_fma2(q, a, vk_splat2(4.588905654064e-01f));
+    q = vk_fma2(q, a, vk_splat2(1.151150930355e+00f));
+    q = vk_fma2(q, a, vk_splat2(1.f));
+    const float2 e = make_float2(vk_ex2(-q.x), vk_ex2(-q.y));
+    return vk_fma2(make_float2(-ax.x, -ax.y), e, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
 __device__ __forceinline__ float vk_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }   // per-pixel maps only (IEEE division)
 __device__ __forceinline__ float vk_softplus(float x) {  // beta 1, threshold 20 (torch.nn.Softplus)
     return x > 20.f ? x : log1pf(expf(x));

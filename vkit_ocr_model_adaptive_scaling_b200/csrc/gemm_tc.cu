@@ -89,6 +89,7 @@ struct TcParams {
     int num_stages;
     int stage_bytes;
     int skip_tma;            // debug: producers arrive without loading (timing experiments)
+    int no_acc_prefetch;     // A/B switch: the epilogue loads each chunk's accumulators only when it gets to them
     int staged_store;        // NT: aligned bf16 outputs leave through the shared-memory staging tiles
     int cta2;                // NT: CTA pairs (cluster of 2, tcgen05 cta_group::2): M = 256 per pair, each CTA stages its 128 pixel rows and HALF of the weight tile
     int prefetch_extra;      // NT staged path: residual / aux tiles are prefetched one chunk ahead (cp.async) into a second set of staging tiles
@@ -250,6 +251,28 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
+}
+// The same load split in two so that the epilogue can have the NEXT chunk's accumulators in flight while it stages and stores
+// the current one.  The wait names all 32 result registers as read-write operands: every consumer depends on the wait, not
+// on the load (see the note in tc_ld32 below), and nothing else touches the registers in between.
+#define VK_F32RW(r) "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]), "+f"(r[8]), "+f"(r[9]), \
+    "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]), "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]),  \
+    "+f"(r[20]), "+f"(r[21]), "+f"(r[22]), "+f"(r[23]), "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]),  \
+    "+f"(r[30]), "+f"(r[31])
+// (the results land in the float variables the arithmetic works on: no register copies between the load and its consumers)
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, float* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]),
+          "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]),
+          "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32_wait(float* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VK_F32RW(r) : : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -631,10 +654,17 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 const bool prefetch = p.prefetch_extra && esrc != nullptr;
                 if (prefetch && !pf_issued) issue_prefetch(t, cpart);
                 pf_issued = false;
+                // the accumulators of the warp's NEXT chunk of this tile are requested from tensor memory as soon as the
+                // current chunk's values are packed, and arrive while the current chunk is staged and stored
+                float v[32];
+                bool acc_issued = false;
                 for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
                     const int cb = c * 32;
                     const int nb = t.n0 + cb;
                     if (nb >= col_end || (p.skip_tma & 16)) break;   // debug bit 4: epilogue = barrier traffic only
+                    if (!acc_issued) tc_ld32_issue(taddr + (uint32_t)cb, v);
+                    const int c_next = c + EPI_WARPS / 4;
+                    const bool more = !p.no_acc_prefetch && c_next < chunks && t.n0 + c_next * 32 < col_end;
                     const int col = nb + seg * 8;
                     uint4 extra[4];
                     if (uses_extra && prefetch) {
@@ -688,13 +718,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         for (int j = 0; j < 4; ++j) pk[j] = pack8(vals + 8 * j);
                         store_packed(pk, base, ld);
                     };
-                    float v[32];
-                    {
-                        uint32_t acc[32];
-                        tc_ld32(taddr + (uint32_t)cb, acc);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                    }
+                    tc_ld32_wait(v);
                     const bool full = nb + 32 <= p.N;
                     // per-element arithmetic on fp32 PAIRS (FADD2 / FMUL2 / FFMA2): one issue slot for two columns
                     auto add4 = [&](int j, const float4 b) {
@@ -747,7 +771,10 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         if (has_pre) store_tile(v, ep.out_pre, ep.ld_pre);      // pre-activation copy (acc + bias)
                         if (act == 1) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = vk_gelu(v[j]);
+                            for (int j = 0; j < 32; j += 2) {
+                                const float2 g2 = vk_gelu2(make_float2(v[j], v[j + 1]));
+                                v[j] = g2.x; v[j + 1] = g2.y;
+                            }
                         } else if (act == 2) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -791,7 +818,14 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                             add4(8 * j + 4, make_float4(f[4], f[5], f[6], f[7]));
                         }
                     }
-                    store_tile(v, ep.out, ep.ldo);
+                    {
+                        uint4 pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pk[j] = pack8(v + 8 * j);
+                        acc_issued = more;
+                        if (more) tc_ld32_issue(taddr + (uint32_t)(c_next * 32), v);       // the packed copy is all that is still needed
+                        store_packed(pk, ep.out, ep.ldo);
+                    }
                 }
             };
             if constexpr (EPI != 0) {
@@ -1162,6 +1196,7 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaSt
     if (p.mode == 1)
         if (const char* e = getenv("VKOCR_TN_STAGES")) p.num_stages = atoi(e) < p.num_stages ? atoi(e) : p.num_stages;
     if (const char* e = getenv("VKOCR_DEBUG_SKIP_TMA")) p.skip_tma = atoi(e);
+    p.no_acc_prefetch = getenv("VKOCR_NO_ACC_PREFETCH") != nullptr;
     const long long sms = vkocr_sm_count();
     if (p.cta2) {
         // one cluster of two CTAs per SM pair; in head mode the cluster count is a multiple of the head count so that a

@@ -377,7 +377,10 @@ ln_fwd_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long l
                     }
                     if (act) {
 #pragma unroll
-                        for (int i = 0; i < V; ++i) o[i] = vk_gelu(o[i]);
+                        for (int i = 0; i < V; i += 2) {
+                            const float2 g2 = vk_gelu2(make_float2(o[i], o[i + 1]));
+                            o[i] = g2.x; o[i + 1] = g2.y;
+                        }
                     }
                     VkVec<T> t;
                     t.pack(o);
