@@ -7,15 +7,16 @@ import torch
 # losses, and of the gradient (all parameter gradients taken together, the vector the optimizer / global-norm clip sees).
 TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
 GRAD_TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
-# Small-shape exceptions, stated.  The north-star bound holds at the benchmark shapes for BOTH necks
-# (tests/test_gpu_fullsize.py, B=32 / 640x640: UPERNEXT 1.1e-2, FPN 8.5e-3 against the fp32 oracle).  On a 2-image 160x224
-# batch the parameter gradients are sums over 45x fewer pixels: their coherent part shrinks with the pixel count while
-# the bf16 rounding noise of ~60 chained tensors only shrinks with its square root, and the FPN configuration (kaiming-
-# initialised 384-channel laterals, forward mask-logit error 1.8e-2) measures 2.9e-2 - 3.1e-2 there; the reference's own
-# ops under torch.autocast(bfloat16) measure 3.3e-2 on the same inputs (the test prints both; UPERNEXT: 1.5e-2 vs 1.5e-2).
-# The deeper SMALL (27-layer stage) / wider BASE / LARGE backbones on a single 64x96 image measure 3.1e-2 / 2.2e-2 / 2.04e-2.
+# One small-shape exception, stated.  The north-star bound holds at the benchmark shapes for BOTH necks
+# (tests/test_gpu_fullsize.py, B=32 / 640x640: UPERNEXT 1.1e-2, FPN 8.5e-3 against the fp32 oracle) and for the SMALL / BASE /
+# LARGE configurations on two 128x192 images (test_larger_configs_against_oracle: 1.3e-2 / 1.3e-2 / 1.0e-2).  On the 2-image
+# 160x224 batch of test_training_step_against_oracle (synthetic weights seed 7) the parameter gradients are sums over 45x
+# fewer pixels than at the benchmark shape: their coherent part shrinks with the pixel count while the bf16 rounding noise
+# of ~60 chained tensors only shrinks with its square root, and the FPN configuration (kaiming-initialised 384-channel
+# laterals, forward mask-logit error 1.8e-2) measures 2.9e-2 - 3.1e-2 there; the reference's own ops under
+# torch.autocast(bfloat16) measure 3.3e-2 on the same inputs (the test prints both; UPERNEXT: 1.5e-2 vs 1.5e-2).
 # Anything not listed here is held to GRAD_TOL.
-SMALL_SHAPE_BF16_GRAD_TOL = {'tiny/fpn': 3.5e-2, 'small/upernext': 3.5e-2, 'base/fpn': 3.5e-2, 'large/upernext': 3.5e-2}
+SMALL_SHAPE_BF16_GRAD_TOL = {'tiny/fpn': 3.5e-2}
 # Individual parameter-gradient tensors are sums over up to millions of pixels: rounding noise scales with
 # sqrt(sum t_i^2), not with |sum t_i|, so a tensor whose terms cancel (biases of zero-mean maps, the stem at the end of
 # the longest backward chain) carries a larger *relative* error than the gradient as a whole.  Per-tensor bound:

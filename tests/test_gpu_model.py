@@ -218,13 +218,16 @@ def test_state_dict_round_trip_and_shapes(vk):
 def test_larger_configs_against_oracle(vk, size, neck, dtype):
     """The other `create_*` sizes of the reference (convnext.py:188-225): BASE has 128..1024 channels, so the heads'
     inner width (256 + out)/2 no longer fits one 256-column tile and the head group takes the unfused tail; SMALL has a
-    27-layer stage.  Forward outputs, both losses and every gradient against the oracle at a small image."""
+    27-layer stage.  Forward outputs, both losses and every gradient against the oracle on two 128x192 images, held to the
+    north-star tolerances (measured bf16 gradient error: SMALL 1.3e-2, BASE 1.3e-2, LARGE 1.0e-2; on a single 64x96 image the
+    same configurations measure 3.2e-2 - 3.5e-2 / 1.9e-2 / 1.9e-2: the coherent part of a gradient grows with the pixel count,
+    the rounding noise of the chained bf16 tensors with its square root)."""
     from oracle import loss as ol
     from oracle import model as om
     from oracle import synth
     from vkit_ocr_model_adaptive_scaling_b200.training import train_step
     dev = torch.device('cuda')
-    B, H, W, P = 1, 64, 96, 8
+    B, H, W, P = 2, 128, 192, 16
     model = _build(vk, neck, size)
     model.load_state_dict(synth.synth_state_dict(size, neck, seed=11), strict=True)
     model.to(dev).eval()
@@ -245,9 +248,7 @@ def test_larger_configs_against_oracle(vk, size, neck, dtype):
     tol = TOL[dtype]
     assert abs(float(rl) - float(rl_ref)) <= tol * abs(float(rl_ref)), (float(rl), float(rl_ref))
     assert abs(float(pl) - float(pl_ref)) <= tol * abs(float(pl_ref)), (float(pl), float(pl_ref))
-    # bf16: the 40-layer SMALL / 1024-channel BASE chains on ONE 64x96 image: the stated small-shape bound of _util.py
-    explicit = SMALL_SHAPE_BF16_GRAD_TOL.get(f'{size}/{neck}') if dtype == torch.bfloat16 else None
-    compare_grads(model, params, dtype, f'{size}/{neck} step', grad_tol=explicit)
+    compare_grads(model, params, dtype, f'{size}/{neck} step')
 
 
 def test_frozen_parameters_get_no_gradient(vk):

@@ -440,14 +440,30 @@ def _zeros(n: int, dtype: torch.dtype, device) -> Tensor:
     return zero_(torch.empty(n, dtype=dtype, device=device))
 
 
+_GRAD_MODE = [True]      # grad mode of the caller of the innermost Function.apply in flight (forward itself always runs with it off)
+
+
+class _Function(torch.autograd.Function):
+    """``torch.autograd.Function`` that remembers the caller's grad mode: ``ctx.needs_input_grad`` only says which inputs
+    require grad -- it is the same under ``torch.no_grad()`` -- and a forward that takes it for "a backward will follow"
+    writes every training side channel (gelu' maps, LayerNorm statistics, conv outputs) during inference."""
+
+    @classmethod
+    def apply(cls, *args, **kwargs):
+        _GRAD_MODE.append(torch.is_grad_enabled())
+        try:
+            return super().apply(*args, **kwargs)
+        finally:
+            _GRAD_MODE.pop()
+
+
 def _needs_grad(ctx) -> bool:
-    """True when autograd will call this node's backward (grad mode is off inside Function.forward, so the node's own
-    needs_input_grad is the only reliable signal)."""
-    return any(ctx.needs_input_grad)
+    """True when autograd will call this node's backward: grad mode was on at ``apply`` and some input requires grad."""
+    return _GRAD_MODE[-1] and any(ctx.needs_input_grad)
 
 
 # ----------------------------------------------------------------------------------------------------- autograd nodes
-class StemFn(torch.autograd.Function):
+class StemFn(_Function):
     """pconv(p x p, stride p) + bias -> LayerNorm, image NCHW fp32 -> NHWC (convnext.py:106-123, helper.py:43-58)."""
 
     @staticmethod
@@ -490,7 +506,7 @@ class StemFn(torch.autograd.Function):
         return None, None, None, None, None, None
 
 
-class LayerNormFn(torch.autograd.Function):
+class LayerNormFn(_Function):
     """Channels-last LayerNorm, optionally followed by exact GELU (helper.py:96-101)."""
 
     @staticmethod
@@ -519,7 +535,7 @@ class LayerNormFn(torch.autograd.Function):
         return dx, None, None, None
 
 
-class ConvNextLayerFn(torch.autograd.Function):
+class ConvNextLayerFn(_Function):
     """x + mask * scale * Linear2(GELU(Linear1(LN(dwconv7x7(x)))))  (ConvNextBlockLayer, convnext.py:20-59)."""
 
     @staticmethod
@@ -625,7 +641,7 @@ class ConvNextLayerFn(torch.autograd.Function):
         return (dx,) + (None,) * 11
 
 
-class PatchConvFn(torch.autograd.Function):
+class PatchConvFn(_Function):
     """pconv2x2 (kernel 2, stride 2) on NHWC = space-to-depth gather + GEMM (helper.py:43-49, convnext.py:89-99)."""
 
     @staticmethod
@@ -672,7 +688,7 @@ class PatchConvFn(torch.autograd.Function):
         return dx, None, None
 
 
-class ConvLnGeluFn(torch.autograd.Function):
+class ConvLnGeluFn(_Function):
     """k x k 'same' conv (k = 1 is the Linear of build_conv1x1_block) + bias -> LayerNorm -> GELU
     (upernext.py:21-45, fpn.py:21-48), as an implicit GEMM on the tensor cores."""
 
@@ -734,7 +750,7 @@ class ConvLnGeluFn(torch.autograd.Function):
         return dx, None, None, None, None
 
 
-class AvgPoolFn(torch.autograd.Function):
+class AvgPoolFn(_Function):
     """nn.AdaptiveAvgPool2d(S) on NHWC (upernext.py:59-65)."""
 
     @staticmethod
@@ -760,7 +776,7 @@ class AvgPoolFn(torch.autograd.Function):
         return dx, None
 
 
-class UpsampleAddFn(torch.autograd.Function):
+class UpsampleAddFn(_Function):
     """base + F.interpolate(src, size=base.shape[-2:], mode) — the top-down step (upernext.py:174-182, fpn.py:121-129)."""
 
     @staticmethod
@@ -784,7 +800,7 @@ class UpsampleAddFn(torch.autograd.Function):
         return (dout if ctx.needs_input_grad[0] else None), dsrc, None
 
 
-class UpsampleConcatFn(torch.autograd.Function):
+class UpsampleConcatFn(_Function):
     """torch.cat([F.interpolate(t, size) or t ...], dim=1): every level is resampled straight into its channel slice of
     the NHWC concat buffer (upernext.py:76-82,189-197; fpn.py:136-144)."""
 
@@ -827,7 +843,7 @@ class UpsampleConcatFn(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
-class HeadGroupFn(torch.autograd.Function):
+class HeadGroupFn(_Function):
     """All heads that read one neck tensor, fused: x`factor` up-sample (once) -> one implicit-GEMM conv with the heads'
     k x k weights concatenated along N -> per-head LayerNorm+GELU+1x1(+Softplus) tail writing NCHW fp32 maps.
     (UperNextHead.forward upernext.py:233-248, FpnHead.forward fpn.py:193-208, Softplus adaptive_scaling.py:101,140.)
@@ -1069,7 +1085,7 @@ class HeadGroupFn(torch.autograd.Function):
         return (dx, None, None, None) + (None,) * len(params)
 
 
-class HeadGroupPointsFn(torch.autograd.Function):
+class HeadGroupPointsFn(_Function):
     """Opt-in label-point evaluation of heads whose outputs the loss reads at the (B, P) label points only (the precise
     corner-offset / angle / distance heads, loss_function/adaptive_scaling.py:235-260): the conv outputs of those pixels are
     ONE small GEMM, conv[e, :] = bias + A[e, :] . W^T with A[e, tap, :] = up(x)[r_e + dy - k/2, s_e + dx - k/2, :]
@@ -1190,7 +1206,7 @@ def _i64c(t: Tensor) -> Tensor:
     return t.contiguous()
 
 
-class RoughLossFn(torch.autograd.Function):
+class RoughLossFn(_Function):
     """focal + dice + masked log-space smooth-L1 of the rough maps inside the core box, one reduction pass
     (AdaptiveScalingRoughLossFunction.__call__, loss_function/adaptive_scaling.py:53-131)."""
 
@@ -1237,7 +1253,7 @@ def _device_factors(values: Tuple[float, ...], device) -> Tensor:
     return t
 
 
-class PreciseLossFn(torch.autograd.Function):
+class PreciseLossFn(_Function):
     """Dense pos/neg L2 of sigmoid(prob) inside the core box + label-point gather terms (offset smooth-L1, distance
     regulation, soft-label CE of the corner angles, corner-distance smooth-L1), x loss_factor
     (AdaptiveScalingPreciseLossFunction.__call__, loss_function/adaptive_scaling.py:181-346)."""
@@ -1296,7 +1312,7 @@ class PreciseLossFn(torch.autograd.Function):
 FOCAL, DICE, L1, SMOOTH_L1, L2, WAHR = range(6)
 
 
-class PointwiseLossFn(torch.autograd.Function):
+class PointwiseLossFn(_Function):
     """One of the element-wise primitive losses with optional mask, reduced on the device
     (focal_with_logits.py, dice.py, l1.py, l2.py, weight_adaptive_heatmap_regression.py)."""
 
@@ -1333,7 +1349,7 @@ class PointwiseLossFn(torch.autograd.Function):
         return dpred.reshape(shape), None, None, None, None, None, None
 
 
-class SoftCrossEntropyFn(torch.autograd.Function):
+class SoftCrossEntropyFn(_Function):
     """F.cross_entropy(pred, gt) with probability targets, class axis 1 (cross_entropy_with_logits.py:16-19)."""
 
     @staticmethod
@@ -1363,7 +1379,7 @@ class SoftCrossEntropyFn(torch.autograd.Function):
         return dpred, None
 
 
-class HardNegativeBceFn(torch.autograd.Function):
+class HardNegativeBceFn(_Function):
     """BCE-with-logits over all positives plus the k hardest negatives, k = min(round(ratio * #pos), #neg), selected by
     a device-side radix select (weighted_bce_with_logits.py:18-54; no host synchronisation)."""
 
