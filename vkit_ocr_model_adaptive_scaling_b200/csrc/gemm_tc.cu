@@ -90,6 +90,7 @@ struct TcParams {
     int stage_bytes;
     int skip_tma;            // debug: producers arrive without loading (timing experiments)
     int no_acc_prefetch;     // A/B switch: the epilogue loads each chunk's accumulators only when it gets to them
+    int tn_vec;              // TN: J is contiguous and 16-byte aligned in the output -> staged 16-byte reductions
     int staged_store;        // NT: aligned bf16 outputs leave through the shared-memory staging tiles
     int cta2;                // NT: CTA pairs (cluster of 2, tcgen05 cta_group::2): M = 256 per pair, each CTA stages its 128 pixel rows and HALF of the weight tile
     int prefetch_extra;      // NT staged path: residual / aux tiles are prefetched one chunk ahead (cp.async) into a second set of staging tiles
@@ -203,6 +204,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
+}
+// four consecutive fp32 accumulations as ONE 16-byte reduction (REDG.E.ADD.F32x4)
+__device__ __forceinline__ void red_add_v4(float* addr, uint4 v) {
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                 "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
 }
 __device__ __forceinline__ void unpack8(uint4 raw, float* f) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
@@ -983,6 +989,36 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
                 uint32_t acc[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), acc);
+                if (p.mode == 1 && p.tn_vec) {
+                    // weight gradient with contiguous J (the MLP / 1x1 layers): a lane holds 32 columns of ONE row, so scalar
+                    // atomics would touch 32 rows per instruction; the chunk goes through the warp's staging tile 16 columns
+                    // at a time and leaves as 16-byte reductions, four lanes per 64-byte row segment
+                    const uint32_t wb = epi_base + (uint32_t)(warp - 4) * (uint32_t)EPI_TILE_BYTES;
+                    const uint32_t my_row = wb + (uint32_t)lane * 64u;
+                    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+                    float* obase = reinterpret_cast<float*>(ep.out) + (long long)t.tap * ep.tn_s_tap;
+                    const int seg = lane & 3;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            sts128(my_row + (((uint32_t)j ^ sw) << 4),
+                                   make_uint4(acc[16 * h + 4 * j], acc[16 * h + 4 * j + 1], acc[16 * h + 4 * j + 2], acc[16 * h + 4 * j + 3]));
+                        __syncwarp();
+                        const int cl = c * 32 + 16 * h + seg * 4;          // column inside the N tile
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = 8 * i + (lane >> 2);
+                            const int irow = t.i0 + q * 32 + rr;
+                            if (irow < p.I && t.n0 + cl < p.N && cl < BN && !(p.skip_tma & 256)) {   // debug bit 8: no atomics
+                                const uint4 val = lds128(wb + (uint32_t)rr * 64u + (((uint32_t)seg ^ (uint32_t)((rr >> 1) & 3)) << 4));
+                                red_add_v4(obase + (long long)irow * ep.tn_s_i + t.n0 + cl, val);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 if (!row_ok) continue;
                 const int nbase = t.n0 + c * 32;
                 if (vec_ok && (nbase + 32 <= p.N) && (c * 32 + 32 <= BN) && ((nbase & 7) == 0)) {
@@ -1055,7 +1091,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = nbase + j;
-                        if (n < p.N && (c * 32 + j) < BN) vk_epilogue_store_tn(ep, t.tap, t.i0 + r, n, __uint_as_float(acc[j]));
+                        if (n < p.N && (c * 32 + j) < BN && !(p.skip_tma & 256)) vk_epilogue_store_tn(ep, t.tap, t.i0 + r, n, __uint_as_float(acc[j]));   // debug bit 8: no atomics
                     }
                 } else {
 #pragma unroll
@@ -1384,6 +1420,8 @@ int vkocr_gemm_tc_tn(const void* pmat, const VkocrConvGeom* g, const void* qmat,
     p.splits = (int)splits;
     p.units = out_tiles * splits;
     p.ep = ep;
+    p.tn_vec = ep.tn_s_j == 1 && ep.tn_s_i % 4 == 0 && ep.tn_s_tap % 4 == 0 && J % 4 == 0 &&
+               (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && getenv("VKOCR_TN_SCALAR_RED") == nullptr;
     CUtensorMap mapA, mapB;
     int rc = encode_nhwc(&mapA, pmat, I, g->W, g->H, g->batch, ld_p, p.BW, p.BH);
     if (rc) return rc;
