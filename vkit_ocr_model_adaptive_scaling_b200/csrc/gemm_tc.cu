@@ -91,6 +91,7 @@ struct TcParams {
     int skip_tma;            // debug: producers arrive without loading (timing experiments)
     int no_acc_prefetch;     // A/B switch: the epilogue loads each chunk's accumulators only when it gets to them
     int tn_vec;              // TN: J is contiguous and 16-byte aligned in the output -> staged 16-byte reductions
+    int tma_store;           // NT staged epilogue: the staging tiles leave as bulk tensor stores (mapO: out, mapP: out_pre)
     int staged_store;        // NT: aligned bf16 outputs leave through the shared-memory staging tiles
     int cta2;                // NT: CTA pairs (cluster of 2, tcgen05 cta_group::2): M = 256 per pair, each CTA stages its 128 pixel rows and HALF of the weight tile
     int prefetch_extra;      // NT staged path: residual / aux tiles are prefetched one chunk ahead (cp.async) into a second set of staging tiles
@@ -146,6 +147,16 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// Bulk tensor STORE of a staged tile (shared -> global, bulk async-group completion).  Rows / columns outside the tensor are
+// clipped by the copy engine.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -313,6 +324,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo1
 template <bool CTA2, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapP,
                      const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -584,6 +596,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         }
         bool pf_issued = false;                 // the first chunk of the coming tile is already being prefetched
+        bool tma_pending = false;               // a bulk store of this warp's staging tile may still be reading it
         const uint32_t pre_base = bar_base + 256u;
         for (long long w = w0; w < wcount; w += wstride) {
             const long long u = unit_of(w);
@@ -664,11 +677,18 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 // current chunk's values are packed, and arrive while the current chunk is staged and stored
                 float v[32];
                 bool acc_issued = false;
+                // pixel coordinates of the warp's first row inside the image (bulk tensor stores)
+                const int st_x = t.x0 + (r0 & (p.BW - 1)), st_y = t.y0 + (r0 >> p.bw_shift);
                 for (int c = cpart; c < chunks; c += EPI_WARPS / 4) {
                     const int cb = c * 32;
                     const int nb = t.n0 + cb;
                     if (nb >= col_end || (p.skip_tma & 16)) break;   // debug bit 4: epilogue = barrier traffic only
                     if (!acc_issued) tc_ld32_issue(taddr + (uint32_t)cb, v);
+                    if (tma_pending && uses_extra && !prefetch) {      // the extra operand is transposed through the same tile
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+                        tma_pending = false;
+                    }
                     const int c_next = c + EPI_WARPS / 4;
                     const bool more = !p.no_acc_prefetch && c_next < chunks && t.n0 + c_next * 32 < col_end;
                     const int col = nb + seg * 8;
@@ -702,6 +722,24 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     }
                     // stage the lane's 32 finished values and write the warp's tile out as coalesced row segments
                     auto store_packed = [&](const uint4 (&pk)[4], void* base, long long ld) {
+                        if (p.tma_store) {
+                            // the tile's layout IS the copy engine's SWIZZLE_64B box (32 columns x the warp's 32 pixels): one
+                            // lane hands it over and the warp moves on; the tile is reused once the engine has read it
+                            if (tma_pending) {
+                                if (lane == 0) bulk_wait_read0();
+                                __syncwarp();
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pk[j]);
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0 && !(p.skip_tma & 8)) {
+                                tma_store_4d(base == ep.out ? &mapO : &mapP, wb, nb, st_x, st_y, t.b);
+                                bulk_commit();
+                            }
+                            tma_pending = true;
+                            return;
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) sts128(my_row + (((uint32_t)j ^ sw) << 4), pk[j]);
                         __syncwarp();
@@ -1112,6 +1150,7 @@ vkocr_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             }
             if (++as == 2) { as = 0; aph ^= 1u; }
         }
+        if (tma_pending && lane == 0) bulk_wait_all();      // the staging tiles outlive their bulk stores
     }
 
     tc_fence_before();
@@ -1145,7 +1184,7 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 tensor map, SWIZZLE_128B, inner box = 64 elements (128 B), zero OOB fill.
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+               const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode_fn();
     VK_REQUIRE(fn != nullptr, VKOCR_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t gdim[5];
@@ -1159,7 +1198,7 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VK_REQUIRE(r == CUDA_SUCCESS, VKOCR_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu box %u %u",
                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
@@ -1174,6 +1213,16 @@ int encode_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int B, 
     const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * W, (uint64_t)ld * 2 * W * H};
     const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
     return encode_map(map, base, 4, dims, str, box);
+}
+
+// Output map of the staged epilogue: the same pixel grid, `N` columns, boxes of 32 columns x the 32 pixels of one epilogue warp
+// (bw x bh of them: a 32-pixel piece of a tile row, or 32 / BW whole tile rows) in the 64-byte-row swizzle of the staging tiles.
+int encode_nhwc_store(CUtensorMap* map, const void* base, int N, int W, int H, int B, long long ld, int BW) {
+    const int bw = BW < 32 ? BW : 32;
+    const uint64_t dims[4] = {(uint64_t)N, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * W, (uint64_t)ld * 2 * W * H};
+    const uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)(32 / bw), 1};
+    return encode_map(map, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 void pick_box(int W, int H, int pixels, int* bw_out, int* bh_out) {
@@ -1191,7 +1240,7 @@ void pick_box(int W, int H, int pixels, int* bw_out, int* bh_out) {
     }
 }
 
-typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams);
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 template <int... I>
 struct KernelTable {
     static TcKernel get(bool cta2, int epi) {
@@ -1203,7 +1252,11 @@ struct KernelTable {
 using Kernels = KernelTable<0, 1, 2, 3, 4, 5, 6>;
 static_assert(NUM_EPI == 7, "KernelTable lists every epilogue kind");
 
-int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaStream_t stream, const CUtensorMap* mapO_in = nullptr,
+           const CUtensorMap* mapP_in = nullptr) {
+    // output maps of the bulk-store epilogue; the input map stands in where there is none (never dereferenced then)
+    const CUtensorMap& mapO = mapO_in ? *mapO_in : mapA;
+    const CUtensorMap& mapP = mapP_in ? *mapP_in : mapO;
     static bool attr_set = false;
     const int smem = MAX_SMEM + 1024 + EPI_WARPS * EPI_TILE_BYTES + HEAD_PAR_BYTES + HEAD_XCH_BYTES + 256;
     if (!attr_set) {
@@ -1253,14 +1306,14 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams& p, cudaSt
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, mapA, mapB, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, mapA, mapB, mapO, mapP, p);
         VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "cudaLaunchKernelEx(cluster 2): %s", cudaGetErrorString(e));
         VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
         return VKOCR_OK;
     }
     const int grid = (int)(p.units < sms ? p.units : sms);
     if (grid <= 0) return VKOCR_OK;
-    kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, p);
+    kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA, mapB, mapO, mapP, p);
     VK_CHECK_LAUNCH("vkocr_gemm_tc_kernel");
     return VKOCR_OK;
 }
@@ -1338,7 +1391,22 @@ int vkocr_gemm_tc_nt(const void* x, const VkocrConvGeom* g, const void* w_packed
         else if (ep->act == 0 && b && cs && res && !pre) p.epi_kind = 5;
         else if (ep->act == 4 && !b && !cs && !res && !pre && !rsc) p.epi_kind = 6;
     }
-    return launch(mapA, mapB, p, stream);
+    // the staged tiles leave through the copy engine (bulk tensor stores): no per-lane store instructions, clipping for free
+    CUtensorMap mapO, mapP;
+    // (a box is 32 whole columns: N tiles that are not a multiple of 32 wide would spill into their neighbour's columns; with a
+    // residual / aux operand prefetched by cp.async the proxy fence in front of the bulk store would wait for those copies --
+    // measured 10 % slower -- so these keep the per-lane stores)
+    p.tma_store = p.staged_store && !p.head_mode && !p.prefetch_extra && (p.BN % 32 == 0 || p.n_tiles == 1) &&
+                  getenv("VKOCR_NO_TMA_STORE") == nullptr;
+    if (p.tma_store) {
+        rc = encode_nhwc_store(&mapO, ep->out, N, g->W, g->H, g->batch, ep->ldo, p.BW);
+        if (rc) return rc;
+        if (ep->out_pre) {
+            rc = encode_nhwc_store(&mapP, ep->out_pre, N, g->W, g->H, g->batch, ep->ld_pre, p.BW);
+            if (rc) return rc;
+        }
+    }
+    return launch(mapA, mapB, p, stream, p.tma_store ? &mapO : nullptr, (p.tma_store && ep->out_pre) ? &mapP : nullptr);
 }
 
 // TN: G[tap,i,j] += sum_pix P[pix,i] * Q[pix+off(tap), j]   (bf16 in, fp32 out accumulated with red.add)
