@@ -27,7 +27,7 @@ fi
 
 if [ "$WHAT" = ncu ]; then
     # launch list of the bench command (the same command exited 0 without ncu in the `bench` pass)
-    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3900 -c 1400 --csv --log-file $O/launches_${TAG}.csv \
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3690 -c 1200 --csv --log-file $O/launches_${TAG}.csv \
         python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras --no-eager-baseline > $O/${TAG}_ncu_bench.log 2>&1
     capture() {   # name, kernel regex, launches to skip, launches to capture, command...
         local name=$1 regex=$2 skip=$3 count=$4; shift 4
@@ -38,12 +38,13 @@ if [ "$WHAT" = ncu ]; then
         ncu -i $O/prof_${name}_${TAG}.ncu-rep --page source --csv --launch-count 1 > $O/prof_${name}_${TAG}_source.csv 2>/dev/null
         if [ $(stat -c %s $O/prof_${name}_${TAG}.ncu-rep) -gt 12000000 ]; then rm -f $O/prof_${name}_${TAG}.ncu-rep; fi
     }
-    capture hcfwd 'hc_fwd' 4 4 python tools/profile_combine.py 2 fwd
+    capture hcfwd 'hc_fwd' 0 4 python tools/profile_combine.py 1 fwd
+    capture hcfwd_rough 'hc_fwd' 0 2 env ROUGH=1 python tools/profile_combine.py 1 fwd
     capture hcbwd 'hc_bwd' 1 1 python tools/profile_combine.py 2 bwd
     capture zgemm 'vkocr_gemm_tc' 1 1 python tools/profile_combine.py 2 z
     capture dgrad 'vkocr_gemm_tc' 1 1 python tools/profile_combine.py 2 dgrad
     capture wgrad 'vkocr_gemm_tc' 1 1 python tools/profile_combine.py 2 wgrad
-    capture htb 'head_tail_bwd_kernel' 3 1 python tools/kbench.py head
+    capture htb 'head_tail_bwd_h192' 3 1 python tools/kbench.py head
     capture dw 'dwconv7' 2 2 python tools/profile_dw.py 2
 fi
 du -sh $O; ls -la $O | grep ${TAG} | head -60
