@@ -2,8 +2,8 @@
 # Round measurement sweep on one B200 (run through gpurun from the repo root).
 #   tools/round_sweep.sh <tag> bench     parity tests, smoke, every bench line                      (~2.5 min)
 #   tools/round_sweep.sh <tag> ncu       launch list of the bench command + ncu --set full captures  (~6 min)
-# Outputs: gpurun_out/<tag>_*.  gpurun copies back at most 64 MiB, so the ncu reports are exported to CSV on the box (raw
-# metrics of every captured launch, source page of the first one) and only reports under 12 MiB travel.
+# Outputs: gpurun_out/<tag>_*.  gpurun copies back at most 64 MiB IN TOTAL, so the ncu reports are exported to CSV on the box
+# (raw metrics of every captured launch) and stay there.
 TAG=${1:-r02}
 WHAT=${2:-bench}
 O=gpurun_out
@@ -33,17 +33,13 @@ if [ "$WHAT" = ncu ]; then
         local name=$1 regex=$2 skip=$3 count=$4; shift 4
         "$@" > $O/${TAG}_plain_${name}.log 2>&1 || return
         timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$regex" -s $skip -c $count -f \
-            -o $O/prof_${name}_${TAG} "$@" > $O/${TAG}_ncu_${name}.log 2>&1
-        ncu -i $O/prof_${name}_${TAG}.ncu-rep --page raw --csv > $O/prof_${name}_${TAG}_raw.csv 2>/dev/null
-        ncu -i $O/prof_${name}_${TAG}.ncu-rep --page source --csv --launch-count 1 > $O/prof_${name}_${TAG}_source.csv 2>/dev/null
-        if [ $(stat -c %s $O/prof_${name}_${TAG}.ncu-rep) -gt 12000000 ]; then rm -f $O/prof_${name}_${TAG}.ncu-rep; fi
+            -o /tmp/prof_${name}_${TAG} "$@" > $O/${TAG}_ncu_${name}.log 2>&1
+        ncu -i /tmp/prof_${name}_${TAG}.ncu-rep --page raw --csv > $O/prof_${name}_${TAG}_raw.csv 2>/dev/null
+        # the reports themselves (5-12 MB each) stay on the box: gpurun copies back at most 64 MiB in total
     }
     capture hcfwd 'hc_fwd' 0 4 python tools/profile_combine.py 1 fwd
     capture hcfwd_rough 'hc_fwd' 0 2 env ROUGH=1 python tools/profile_combine.py 1 fwd
-    capture hcbwd 'hc_bwd' 1 1 python tools/profile_combine.py 2 bwd
     capture zgemm 'vkocr_gemm_tc' 1 1 python tools/profile_combine.py 2 z
-    capture dgrad 'vkocr_gemm_tc' 1 1 python tools/profile_combine.py 2 dgrad
-    capture wgrad 'vkocr_gemm_tc' 1 1 python tools/profile_combine.py 2 wgrad
     capture htb 'head_tail_bwd_h192' 3 1 python tools/kbench.py head
     capture dw 'dwconv7' 2 2 python tools/profile_dw.py 2
 fi
