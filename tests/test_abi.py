@@ -118,3 +118,33 @@ def test_config_defaults_and_enums():
         M.FpnHead(16, 1, upsampling_factor=5)
     with pytest.raises(AssertionError):
         M.UperNextNeck((8, 16, 24), 16)
+
+
+def test_autograd_nodes_see_the_callers_grad_mode():
+    """``ctx.needs_input_grad`` is the same under ``torch.no_grad()``; the nodes of ops.py must not take it for "a backward will
+    follow" (they would write every training side channel during inference): ``ops._Function.apply`` records the grad mode."""
+    import torch
+    from vkit_ocr_model_adaptive_scaling_b200 import ops
+    seen = []
+
+    class Probe(ops._Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            seen.append((ops._needs_grad(ctx), tuple(ctx.needs_input_grad)))
+            return x * w
+
+        @staticmethod
+        def backward(ctx, g):
+            return g, g
+
+    x, w = torch.randn(3), torch.nn.Parameter(torch.randn(3))
+    Probe.apply(x, w)
+    with torch.no_grad():
+        Probe.apply(x, w)
+    with torch.inference_mode():
+        Probe.apply(x, w)
+    Probe.apply(x, w.detach())
+    assert [s[0] for s in seen] == [True, False, False, False], seen
+    assert seen[1][1] == (False, True)          # what torch reports under no_grad: the reason for the wrapper
+    assert ops._GRAD_MODE == [True]             # the stack unwinds (also through exceptions: try / finally)
+    assert all(issubclass(getattr(ops, n), ops._Function) for n in dir(ops) if n.endswith('Fn') and isinstance(getattr(ops, n), type))
