@@ -250,10 +250,10 @@ class Workload:
 
 
 def build_workload(vk, workload: str, neck: str, batch: int, size: int, dev, rank: int, world: int, with_optimizer: bool = False,
-                   label_point_forward: bool = False):
+                   label_point_forward: bool = False, cuda_graph: bool = False):
     import torch
     from vkit_ocr_model_adaptive_scaling_b200.parallel import DataParallel
-    from vkit_ocr_model_adaptive_scaling_b200.training import FusedAdamW, batch_to_device, train_step
+    from vkit_ocr_model_adaptive_scaling_b200.training import FusedAdamW, GraphedTrainStep, batch_to_device, train_step
     from oracle import synth  # synthetic weights / batches only (test infrastructure generating inputs, never on the timed path)
     M, LF = vk.model, vk.loss_function
     w = Workload()
@@ -285,10 +285,14 @@ def build_workload(vk, workload: str, neck: str, batch: int, size: int, dev, ran
             if opt is not None:     # clip_grad_norm_(2.5) + AdamW (train.py:468-478): outside BASELINE's metric, reported in `extra`
                 opt.step()
             return losses
+        if cuda_graph:              # the same step captured once and replayed (training.GraphedTrainStep): reported in `extra`
+            assert opt is None and world == 1
+            step = GraphedTrainStep(model, rough_fn, precise_fn, w.rb, w.pb, dp, label_point_forward=label_point_forward)
         w.images_per_step = batch
         w.text = (f'adaptive-scaling TINY/{neck.upper()} two-pass training step (fwd+bwd+loss'
                   f'{"+bucketed NCCL grad all-reduce" if world > 1 else ""}{"+clip+AdamW" if with_optimizer else ""}'
-                  f'{"; offset/angle/distance heads evaluated at the label points only" if label_point_forward else ""}), '
+                  f'{"; offset/angle/distance heads evaluated at the label points only" if label_point_forward else ""}'
+                  f'{"; replayed from one CUDA graph" if cuda_graph else ""}), '
                   f'batch {batch}/GPU, {size}x{size}, {POINTS} label points')
         w.metric, w.unit = METRIC, UNIT
     elif workload == 'backbone':
@@ -546,14 +550,15 @@ def run_ours(args) -> None:
     extra = None
     if world == 1 and args.workload == 'train' and not args.no_extras:
         extra = {}
-        for key, (wl, neck, b, sz, opt, lpf) in {
-                'fpn_train': ('train', 'fpn' if args.neck == 'upernext' else 'upernext', batch, size, False, False),
-                'with_optimizer': ('train', args.neck, batch, size, True, False),
-                'label_point_forward': ('train', args.neck, batch, size, False, True),
-                'backbone_config2': ('backbone', args.neck, 32, 640, False, False),
-                'infer_config5': ('infer', 'upernext', 8, 2048, False, False)}.items():
+        for key, (wl, neck, b, sz, opt, lpf, graph) in {
+                'fpn_train': ('train', 'fpn' if args.neck == 'upernext' else 'upernext', batch, size, False, False, False),
+                'with_optimizer': ('train', args.neck, batch, size, True, False, False),
+                'label_point_forward': ('train', args.neck, batch, size, False, True, False),
+                'cuda_graph': ('train', args.neck, batch, size, False, False, True),
+                'backbone_config2': ('backbone', args.neck, 32, 640, False, False, False),
+                'infer_config5': ('infer', 'upernext', 8, 2048, False, False, False)}.items():
             try:
-                wx = build_workload(vk, wl, neck, b, sz, dev, 0, 1, with_optimizer=opt, label_point_forward=lpf)
+                wx = build_workload(vk, wl, neck, b, sz, dev, 0, 1, with_optimizer=opt, label_point_forward=lpf, cuda_graph=graph)
                 msx, _, lx, _, _ = time_device_resident(wx, 5, 3, dev, 0, 1, local_rank, sample_clocks=False)
                 extra[key] = {'workload': wx.text, 'value': wx.images_per_step / (msx / 1e3), 'unit': wx.unit, 'ms_per_step': msx,
                               'gpu_launches': lx}

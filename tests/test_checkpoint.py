@@ -111,3 +111,35 @@ def test_fused_adamw_rejects_frozen_parameters(vk):
     model.backbone.stem[0].weight.requires_grad_(False)
     with pytest.raises(ValueError):
         FusedAdamW(GradientBuckets(model, flatten_params=True))
+
+
+def test_cosine_warm_restarts_schedule_equals_torch(vk):
+    """training.CosineWarmRestartsSchedule against torch's CosineAnnealingWarmRestarts stepped the way the reference loop
+    steps it (fractional epochs, experiment/adaptive_scaling/train.py:293-298,474-477), across two restarts, and the
+    state_dict interchange in both directions."""
+    import torch
+    from vkit_ocr_model_adaptive_scaling_b200.training import CosineWarmRestartsSchedule
+    for t0, t_mult, batches in ((10, 10, 7), (3, 2, 5), (4, 1, 3)):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([p], lr=8e-4)
+        ref = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=t0, T_mult=t_mult, eta_min=8e-6)
+        ours = CosineWarmRestartsSchedule(8e-4, t0, t_mult, 8e-6)
+        assert abs(ours.last_lr - ref.get_last_lr()[0]) <= 1e-12
+        for epoch_idx in range(0, t0 * (1 + t_mult) + 3):
+            for batch_idx in range(1, batches + 1):
+                epoch = epoch_idx + (batch_idx - 1) / batches
+                ref.step(epoch)
+                assert abs(ours.step(epoch) - ref.get_last_lr()[0]) <= 1e-12 * 8e-4 + 1e-15, (t0, t_mult, epoch)
+        theirs = ref.state_dict()
+        mine = ours.state_dict()
+        for k in ('T_0', 'T_i', 'T_mult', 'eta_min', 'base_lrs', 'last_epoch'):
+            assert mine[k] == theirs[k], k
+        assert abs(mine['T_cur'] - theirs['T_cur']) <= 1e-9 and abs(mine['_last_lr'][0] - theirs['_last_lr'][0]) <= 1e-15
+        resumed = CosineWarmRestartsSchedule()
+        resumed.load_state_dict(theirs)                       # a reference RestoreState's optimizer_scheduler_state_dict
+        assert resumed.state_dict() == {**mine, 'T_cur': theirs['T_cur'], '_last_lr': theirs['_last_lr']}
+        ref2 = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(torch.optim.AdamW([p], lr=8e-4), T_0=1)
+        ref2.load_state_dict(mine)                            # ... and ours resumes the torch scheduler
+        nxt = theirs['last_epoch'] + 1.25
+        ref2.step(nxt)
+        assert abs(resumed.step(nxt) - ref2.get_last_lr()[0]) <= 1e-15

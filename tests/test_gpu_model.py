@@ -394,3 +394,49 @@ def test_label_point_forward_gives_the_dense_loss_and_gradients(vk, neck):
     assert set(gs) == set(gd)
     for n in gd:
         assert_close(gs[n], gd[n], 5e-5, f'grad {n}', atol=1e-7)
+
+
+def test_graphed_train_step_replays_the_eager_step(vk):
+    """training.GraphedTrainStep: the two-pass step captured into one CUDA graph.  In eval mode (no stochastic depth) a
+    replay gives the eager step's losses and gradients (up to the order of the fp32 atomics); new batches copied into the
+    graph's input buffers give the eager result for THOSE batches; in train mode successive replays draw fresh
+    stochastic-depth masks (torch's graph-safe Philox offsets)."""
+    from oracle import synth
+    from vkit_ocr_model_adaptive_scaling_b200.parallel import DataParallel
+    from vkit_ocr_model_adaptive_scaling_b200.training import GraphedTrainStep, train_step
+    dev = torch.device('cuda')
+    B, H, W, P = 2, 96, 128, 10
+    model = _build(vk, 'upernext')
+    model.load_state_dict(synth.synth_state_dict('tiny', 'upernext', seed=23), strict=True)
+    model.to(dev).eval()
+    LF = vk.loss_function
+    rough_fn = LF.AdaptiveScalingRoughLossFunction(LF.AdaptiveScalingRoughLossFunctionConifg())
+    precise_fn = LF.AdaptiveScalingPreciseLossFunction(LF.AdaptiveScalingPreciseLossFunctionConifg())
+    batches = [(_to(synth.synth_rough_batch(B, H, W, seed=s, inset=4), dev), _to(synth.synth_precise_batch(B, H, W, points=P, seed=s, inset=4), dev))
+               for s in (1, 2)]
+    dp = DataParallel(model)
+    try:
+        with vk.precision(torch.float32):      # exact fp32 kernels: run-to-run noise is the atomics' order only
+            eager = []
+            for rb, pb in batches:
+                losses = train_step(model, rough_fn, precise_fn, rb, pb, dp)
+                eager.append(([float(x) for x in losses], [f.clone() for f in dp.buckets.flat]))
+            step = GraphedTrainStep(model, rough_fn, precise_fn, *batches[0], dp, warmup=1)
+            for (rb, pb), (want_losses, want_grads) in list(zip(batches, eager)) + [(batches[0], eager[0])]:
+                for f in dp.buckets.flat:
+                    f.fill_(float('nan'))            # the replay zeroes and refills the buckets itself
+                losses = [float(x) for x in step(rb, pb)]
+                assert losses == pytest.approx(want_losses, rel=1e-5), (losses, want_losses)
+                for name, got, want in zip(dp.buckets.names, dp.buckets.flat, want_grads):
+                    assert_close(got, want, 1e-4, f'bucket {name}')
+            with pytest.raises(ValueError):
+                step({**batches[0][0], 'downsampled_shape': (1, 1)}, batches[0][1])
+            del step
+            model.train()
+            torch.manual_seed(5)
+            step = GraphedTrainStep(model, rough_fn, precise_fn, *batches[0], dp, warmup=1)
+            a = [float(x) for x in step(*batches[0])]
+            b = [float(x) for x in step(*batches[0])]
+            assert all(np.isfinite(a + b)) and a != b, (a, b)     # other drop-path masks -> other losses
+    finally:
+        dp.close()

@@ -589,12 +589,15 @@ def test_errors_are_loud(vk):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('shape', [(2, 32, 16, 40), (1, 64, 19, 80), (2, 32, 20, 20), (1, 96, 13, 35), (3, 32, 8, 120)])
-def test_dwconv7_tiled_kernels_against_conv2d(vk, shape):
-    """The bf16 tiled depthwise kernels (helper.dconv7x7, model/helper.py:61-73) at every tile width (40 / 20 / 32), with
-    partial tiles and the fused residual operand: forward and weight gradient against torch's own convolution of the
-    same bf16-rounded operands in fp64 (only the final bf16 rounding / fp32 summation order may differ)."""
+@pytest.mark.parametrize('strip2', ['0', '1', '2'])
+@pytest.mark.parametrize('shape', [(2, 32, 16, 40), (1, 64, 19, 80), (2, 32, 20, 20), (1, 96, 13, 35), (3, 32, 8, 120),
+                                   (2, 64, 32, 48), (1, 32, 16, 16), (2, 32, 48, 32), (1, 32, 24, 80)])
+def test_dwconv7_tiled_kernels_against_conv2d(vk, shape, strip2, monkeypatch):
+    """The bf16 tiled depthwise kernels (helper.dconv7x7, model/helper.py:61-73) at every tile width (40 / 20 / 32 / 16), with
+    partial tiles and the fused residual operand, 8 x 1 and 8 x 2 strips: forward and weight gradient against torch's own
+    convolution of the same bf16-rounded operands in fp64 (only the final bf16 rounding / fp32 summation order may differ)."""
     from vkit_ocr_model_adaptive_scaling_b200 import ops
+    monkeypatch.setenv('VKOCR_DW_STRIP2', strip2)
     B, C, H, W = shape
     dev = torch.device('cuda')
     g = torch.Generator().manual_seed(H * 1000 + W)

@@ -89,7 +89,7 @@ if 'colsum' in groups:
         report(f'colsum rows{M} C{C}', ms, 1.0 * M * C * 2)
 
 if 'dw' in groups:
-    for (B, H, W, C) in ((32, 160, 160, 96), (32, 80, 80, 192), (32, 40, 40, 384), (32, 20, 20, 768)):
+    for (B, H, W, C) in ((32, 160, 160, 96), (32, 80, 80, 192), (32, 40, 40, 384), (32, 20, 20, 768), (8, 512, 512, 96)):
         x = ops.alloc_nhwc(B, H, W, C, BF, dev); x.normal_()
         y = ops.alloc_nhwc(B, H, W, C, BF, dev)
         add = ops.alloc_nhwc(B, H, W, C, BF, dev); add.normal_()

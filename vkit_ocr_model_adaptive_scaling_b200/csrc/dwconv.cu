@@ -471,6 +471,166 @@ dwconv7_strip_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_b
     }
 }
 
+// Third arrangement: 8 x 2 strips.  The 8 x 1 strip kernel above runs the LSU data pipe (0.50 shared-memory wavefronts per
+// FFMA2) and the conversions (two ALU / FMA-pipe integer operations per loaded word -- the `<< 16` is an IMAD.U32 on the
+// very pipe the FFMA2s need: ncu has 8 % of all warp instructions there, the heavy FMA pipe 65 % busy with FFMA2 alone
+// accounting for 44 points of it) at the FMA pipe's own time.  A thread that owns TWO output rows of its strip applies every
+// loaded and converted input pixel to both (kernel row r for the upper output row, r - 1 for the lower one): 8 input rows
+// instead of 14 per pair of output rows -- 0.29 wavefronts and 0.25 conversions per FFMA2.  The taps of two kernel rows live
+// in registers (wa / wb alternate roles over an unrolled-by-two row loop, so nothing is moved); tiles are TW x TH2 with
+// TH2 = 16 (8 for maps whose height is no multiple of 16).
+template <int TH2> struct Strip2 { static constexpr int HH = TH2 + 6; };
+template <int TW, int TH2>
+__device__ __forceinline__ TileCoord tile_coord2(int t, int tiles_x, int tiles_y) {
+    TileCoord tc;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    tc.x0 = tx * TW;
+    tc.y0 = (t % tiles_y) * TH2;
+    tc.b = t / tiles_y;
+    return tc;
+}
+template <int TW, int RS, int HH>
+__device__ __forceinline__ void load_halo_cols2(uint32_t smem, const __nv_bfloat16* __restrict__ x, long long ld_x, TileCoord tc,
+                                                int H, int W, int c0) {
+    constexpr int HW = TW + 6;
+    for (int q = threadIdx.x; q < HW * 4; q += blockDim.x) {
+        const int part = q & 3, hx = q >> 2;
+        const int xx = tc.x0 + hx - 3;
+        const bool col_ok = xx >= 0 && xx < W;
+        const long long row_step = (long long)W * ld_x;
+        const __nv_bfloat16* src = x + (((long long)tc.b * H + (tc.y0 - 3)) * W + (col_ok ? xx : 0)) * ld_x + c0 + part * 8;
+        uint32_t dst = smem + (uint32_t)(hx * PIX_B + part * 16);
+#pragma unroll
+        for (int hy = 0; hy < HH; ++hy) {
+            const int yy = tc.y0 + hy - 3;
+            const bool ok = col_ok && yy >= 0 && yy < H;
+            cp_async16_zfill(dst, ok ? src : x, ok);
+            src += row_step;
+            dst += RS;
+        }
+    }
+}
+template <int TW, int TH2>
+__global__ void __launch_bounds__(TW * TH2 / 2, (TW * TH2 / 2 <= 128) ? 3 : 2)
+dwconv7_strip2_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, __nv_bfloat16* __restrict__ y, long long ld_y, int B,
+                      int H, int W, int C, const float* __restrict__ wt, const float* __restrict__ bias,
+                      const __nv_bfloat16* __restrict__ add, long long ld_add, int tiles_x, int tiles_y, int ntiles) {
+    static_assert(TW % 8 == 0 && TH2 % 2 == 0, "8 x 2 strips");
+    constexpr int HH = TH2 + 6;
+    constexpr int RS = rs_fwd(TW);               // rows 2 apart land 64 B apart (mod 128): the 4 strips of a warp are stacked in y
+    constexpr int BUF = HH * RS;
+    constexpr int NR = TH2 / 2;                  // row pairs per tile
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    uint8_t* s_in = dw_smem;                                             // [2][HH][RS]
+    float* s_w = reinterpret_cast<float*>(dw_smem + 2 * BUF);            // [49][CB]
+    float* s_b = s_w + 49 * CB;                                          // [CB]
+    const int c0 = blockIdx.y * CB;
+    const uint32_t s_in_a = (uint32_t)__cvta_generic_to_shared(s_in);
+    int t = blockIdx.x;
+    if (t < ntiles) load_halo_cols2<TW, RS, HH>(s_in_a, x, ld_x, tile_coord2<TW, TH2>(t, tiles_x, tiles_y), H, W, c0);
+    vk_cp_async_commit();
+    for (int i = threadIdx.x; i < 49 * CB; i += blockDim.x) s_w[i] = __ldg(wt + (long long)(i / CB) * C + c0 + (i % CB));
+    if (threadIdx.x < CB) s_b[threadIdx.x] = bias ? __ldg(bias + c0 + threadIdx.x) : 0.f;
+    const int cq = threadIdx.x & 7;
+    const int sidx = threadIdx.x >> 3;
+    const int pr = sidx % NR, px = (sidx / NR) * 8;
+    int buf = 0;
+    for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+        const TileCoord tc = tile_coord2<TW, TH2>(t, tiles_x, tiles_y);
+        vk_cp_async_wait<0>();
+        __syncthreads();                        // tile t has landed; everybody is done with the other buffer
+        if (t + (int)gridDim.x < ntiles)
+            load_halo_cols2<TW, RS, HH>(s_in_a + (uint32_t)((buf ^ 1) * BUF), x, ld_x, tile_coord2<TW, TH2>(t + gridDim.x, tiles_x, tiles_y), H, W, c0);
+        vk_cp_async_commit();
+        float2 acc[2][8][2];
+        {
+            const float4 bv = *reinterpret_cast<const float4*>(s_b + cq * 4);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int o = 0; o < 8; ++o) { acc[r][o][0] = make_float2(bv.x, bv.y); acc[r][o][1] = make_float2(bv.z, bv.w); }
+        }
+        const uint8_t* rowp = s_in + buf * BUF + (2 * pr) * RS + px * PIX_B + cq * 8;
+        const float* wk = s_w + cq * 4;
+        float2 wa[7][2], wb[7][2];
+        auto taps = [&](float2 (&w)[7][2]) {           // the 7 taps of the kernel row wk points at, then on to the next row
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wk + kx * CB);
+                w[kx][0] = make_float2(w4.x, w4.y);
+                w[kx][1] = make_float2(w4.z, w4.w);
+            }
+            wk += 7 * CB;
+        };
+        // one input row: `up` (nullable at compile time) weighs it into the upper output row, `lo` into the lower one
+        auto row = [&](auto has_up, auto has_lo, const float2 (&up)[7][2], const float2 (&lo)[7][2]) {
+#pragma unroll
+            for (int j = 0; j < 14; ++j) {
+                const uint2 raw = *reinterpret_cast<const uint2*>(rowp + j * PIX_B);
+                const float2 i0 = bf2_to_f2(raw.x), i1 = bf2_to_f2(raw.y);
+#pragma unroll
+                for (int o = (j > 6 ? j - 6 : 0); o <= (j < 7 ? j : 7); ++o) {
+                    if constexpr (decltype(has_up)::value) {
+                        ffma2(acc[0][o][0], up[j - o][0], i0);
+                        ffma2(acc[0][o][1], up[j - o][1], i1);
+                    }
+                    if constexpr (decltype(has_lo)::value) {
+                        ffma2(acc[1][o][0], lo[j - o][0], i0);
+                        ffma2(acc[1][o][1], lo[j - o][1], i1);
+                    }
+                }
+            }
+            rowp += RS;
+        };
+        using Y = std::true_type;
+        using N = std::false_type;
+        taps(wa);                               // kernel row 0
+        row(Y{}, N{}, wa, wa);                  // input row 0: upper output row only
+#pragma unroll 1
+        for (int r = 1; r < 7; r += 2) {
+            taps(wb);                           // kernel row r
+            row(Y{}, Y{}, wb, wa);              // input row r:     upper <- kernel row r,     lower <- kernel row r - 1
+            taps(wa);                           // kernel row r + 1
+            row(Y{}, Y{}, wa, wb);              // input row r + 1: upper <- kernel row r + 1, lower <- kernel row r
+        }
+        // The residual operand of the data gradient is read with plain global loads: the upper row's go out before the last
+        // input row is applied (its accumulators are final, and wb's registers are free), the lower row's before the upper
+        // row is converted and stored -- one exposed DRAM round trip per tile instead of two.
+        const long long pix0 = ((long long)tc.b * H + tc.y0 + 2 * pr) * W + tc.x0 + px;
+        const __nv_bfloat16* ap = add ? add + pix0 * ld_add + c0 + cq * 4 : nullptr;
+        auto fetch = [&](int r, uint2 (&av)[8]) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                av[o] = make_uint2(0u, 0u);
+                if (add && tc.y0 + 2 * pr + r < H && tc.x0 + px + o < W)
+                    av[o] = __ldg(reinterpret_cast<const uint2*>(ap + ((long long)r * W + o) * ld_add));
+            }
+        };
+        auto store = [&](int r, const uint2 (&av)[8]) {
+            if (tc.y0 + 2 * pr + r >= H) return;
+            __nv_bfloat16* yp = y + (pix0 + (long long)r * W) * ld_y + c0 + cq * 4;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                if (tc.x0 + px + o < W) {
+                    const float2 f0 = bf2_to_f2(av[o].x), f1 = bf2_to_f2(av[o].y);       // zeros without the operand
+                    const float2 a0 = acc[r][o][0], a1 = acc[r][o][1];
+                    uint2 raw;
+                    *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(a0.x + f0.x, a0.y + f0.y);
+                    *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(a1.x + f1.x, a1.y + f1.y);
+                    *reinterpret_cast<uint2*>(yp + (long long)o * ld_y) = raw;
+                }
+            }
+        };
+        uint2 av0[8], av1[8];
+        fetch(0, av0);
+        row(N{}, Y{}, wa, wa);                  // input row 7: lower output row only, kernel row 6
+        fetch(1, av1);
+        store(0, av0);
+        store(1, av1);
+    }
+}
+
 // Weight gradient.  Thread -> 4 channels (cq) x one kernel row ky x one tile row; it slides along x keeping the 7 input
 // vectors of its window in registers: acc[kx][4] += dy[y][x][4] * in[y + ky][x + kx][4].  Persistent over the tiles of one
 // 32-channel block with double-buffered (halo tile of x, tile of dy) stages: the copies of tile t+1 fly while tile t is
@@ -598,6 +758,28 @@ int launch_dw_strip(const void* x, long long ld_x, void* y, long long ld_y, int 
     return 0;
 }
 
+template <int TW, int TH2>
+int launch_dw_strip2(const void* x, long long ld_x, void* y, long long ld_y, int B, int H, int W, int C, const float* wt,
+                     const float* bias, const void* add, long long ld_add, cudaStream_t s) {
+    const int tiles_x = vk_cdiv(W, TW), tiles_y = vk_cdiv(H, TH2);
+    const long long ntiles = (long long)B * tiles_x * tiles_y;
+    const int cblocks = C / CB;
+    const int threads = TW * TH2 / 2;
+    const int smem = 2 * (TH2 + 6) * rs_fwd(TW) + (49 * CB + CB) * (int)sizeof(float);
+    cudaFuncSetAttribute(dwconv7_strip2_kernel<TW, TH2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_strip2_kernel<TW, TH2>, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    long long gx = ((long long)vkocr_sm_count() * per_sm) / cblocks;     // persistent: the resident block count, rounded DOWN
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    dwconv7_strip2_kernel<TW, TH2><<<dim3((unsigned)gx, (unsigned)cblocks), threads, smem, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ld_x, reinterpret_cast<__nv_bfloat16*>(y), ld_y, B, H, W, C, wt, bias,
+        reinterpret_cast<const __nv_bfloat16*>(add), ld_add, tiles_x, tiles_y, (int)ntiles);
+    return 0;
+}
+
 template <int TW>
 int launch_dw_tile(const void* x, long long ld_x, void* y, long long ld_y, int B, int H, int W, int C, const float* wt,
                    const float* bias, const void* add, long long ld_add, cudaStream_t s) {
@@ -661,6 +843,11 @@ int vkocr_dwconv7_fwd(int dtype, const void* x, long long ld_x, void* y, long lo
     if (dtype == VKOCR_BF16 && C % CB == 0 && (long long)B * H * W < (1LL << 30)) {
         const int tw = pick_tw_fwd(W);
         static const bool patch_kernel = getenv("VKOCR_DW_PATCH") != nullptr;      // A/B switch for tools/kbench.py
+        int strip2 = 1;                                          // 8 x 2 strips; VKOCR_DW_STRIP2=0 is the A/B switch (tools/kbench.py)
+        if (const char* e = getenv("VKOCR_DW_STRIP2")) strip2 = atoi(e);
+        if (strip2 && tw == 16 && H % 16 == 0) launch_dw_strip2<16, 16>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
+        else if (strip2 == 2 && tw == 40 && H % 8 == 0) launch_dw_strip2<40, 8>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);   // measured slower: 10 warps per SM
+        else
         if (tw == 40 && !patch_kernel) launch_dw_strip<40>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
         else if (tw == 32 && !patch_kernel) launch_dw_strip<32>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);
         else if (tw == 16) launch_dw_strip<16>(x, ld_x, y, ld_y, B, H, W, C, wt, bias, add, ld_add, s);

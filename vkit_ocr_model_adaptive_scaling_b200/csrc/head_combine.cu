@@ -394,9 +394,14 @@ __device__ __forceinline__ void hc_reduce_multi(float (&v)[N], int lane) {
 template <int O> struct HcPow2 { static constexpr int value = O <= 1 ? 1 : (O <= 2 ? 2 : 4); };
 
 // Per-lane pairs of the tail's per-channel parameters (lane owns channels (lane + 32 j) V .. + V of the head).
+// Heads with three or four output maps keep the projection weights in shared memory ([o][vector][pair][lane] float2, a
+// conflict-free LDS.64 per use): in registers they are 8 O values per lane next to gamma / beta and the two pixels'
+// channels, and the O = 4 instances spilled.
+template <int O> struct HcW2Smem { static constexpr bool value = O >= 3; };
 template <int NVL, int NP, int O>
 struct TailPar2 {
-    float2 gm[NVL][NP], bt[NVL][NP], w[O][NVL][NP];
+    static constexpr int OR = HcW2Smem<O>::value ? 1 : O;
+    float2 gm[NVL][NP], bt[NVL][NP], w[OR][NVL][NP];
     float bias2;      // b2[o] of the (pixel, o) this lane writes after the projection reduce
     __device__ __forceinline__ void load(const HeadArgs& hd, int lane) {
         auto ldc = [&](const float* p, int c) { return c < hd.inner ? __ldg(p + c) : 0.f; };
@@ -407,9 +412,11 @@ struct TailPar2 {
                 const int c = (lane + 32 * j) * NP * 2 + 2 * i;
                 gm[j][i] = make_float2(ldc(hd.gamma, c), ldc(hd.gamma, c + 1));
                 bt[j][i] = make_float2(ldc(hd.beta, c), ldc(hd.beta, c + 1));
+                if constexpr (!HcW2Smem<O>::value) {
 #pragma unroll
-                for (int o = 0; o < O; ++o)
-                    w[o][j][i] = make_float2(ldc(hd.w2 + (long long)o * hd.inner, c), ldc(hd.w2 + (long long)o * hd.inner, c + 1));
+                    for (int o = 0; o < O; ++o)
+                        w[o][j][i] = make_float2(ldc(hd.w2 + (long long)o * hd.inner, c), ldc(hd.w2 + (long long)o * hd.inner, c + 1));
+                }
             }
         constexpr int OP = HcPow2<O>::value;
         constexpr int NV = 2 * OP;                    // values of the projection reduce: (pixel, o)
@@ -423,7 +430,8 @@ struct TailPar2 {
 // (pad channels hold exact zeros); results to out0[o * ostride] / out1[o * ostride].
 template <int NVL, int NP, int O>
 __device__ __forceinline__ void hc_tail2(const float2 (&c0)[NVL][NP], const float2 (&c1)[NVL][NP], const TailPar2<NVL, NP, O>& tp,
-                                         int lane, int inner, int softplus, float* out0, float* out1, long long ostride) {
+                                         int lane, int inner, int softplus, float* out0, float* out1, long long ostride,
+                                         const float2* __restrict__ sW2) {
     const float x0 = __shfl_sync(0xffffffffu, c0[0][0].x, 0);
     const float x1 = __shfl_sync(0xffffffffu, c1[0][0].x, 0);
     const float2 n0 = vk_splat2(-x0), n1 = vk_splat2(-x1);
@@ -461,8 +469,11 @@ __device__ __forceinline__ void hc_tail2(const float2 (&c0)[NVL][NP], const floa
             const float2 g1 = hc_gelu2(vk_fma2(vk_fma2(c1[j][i], rs1, sh1), tp.gm[j][i], tp.bt[j][i]));
 #pragma unroll
             for (int o = 0; o < O; ++o) {
-                d0[o] = vk_fma2(g0, tp.w[o][j][i], d0[o]);
-                d1[o] = vk_fma2(g1, tp.w[o][j][i], d1[o]);
+                float2 wv;
+                if constexpr (HcW2Smem<O>::value) wv = sW2[((o * NVL + j) * NP + i) * 32 + lane];
+                else wv = tp.w[o][j][i];
+                d0[o] = vk_fma2(g0, wv, d0[o]);
+                d1[o] = vk_fma2(g1, wv, d1[o]);
             }
         }
     float dv[2 * OP];
@@ -578,6 +589,7 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
     float* sBias = sV + HC_R * 2 * 3 * HC_QL * cw;                            // [cw] conv bias in plane order
     float2* sWr = reinterpret_cast<float2*>(sBias + cw);                      // [R][2][3][2] row weights, splatted
     float2* sWc = sWr + HC_R * 2 * 3 * 2;                                     // [TJ][2][3] column-pair weights (wA, wB)
+    float2* sW2 = sWc + HC_TJ * 2 * 3;                                        // [O][NVL][NP][32] projection weights (O >= 3 only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cvn = cw / V;                            // channel vectors that hold real channels
     TailPar2<HALF ? 1 : NVL, HALF ? 1 : NP, HALF ? 1 : O> tp;      // (unused with HALF)
@@ -586,6 +598,14 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
     else tp.load(hd, lane);
     for (int c = threadIdx.x; c < cw; c += blockDim.x)
         sBias[hc_voff<HALF>(c / V, c % V, cvn) + (c & 3)] = c < hd.inner ? __ldg(hd.bias + c) : 0.f;
+    if constexpr (!HALF && HcW2Smem<O>::value) {
+        for (int idx = threadIdx.x; idx < O * NVL * NP * 32; idx += blockDim.x) {
+            const int ln = idx & 31, i = (idx >> 5) % NP, j = (idx / (32 * NP)) % NVL, o = idx / (32 * NP * NVL);
+            const int c = (ln + 32 * j) * NP * 2 + 2 * i;
+            const float* wrow = hd.w2 + (long long)o * hd.inner;
+            sW2[idx] = make_float2(c < hd.inner ? __ldg(wrow + c) : 0.f, c + 1 < hd.inner ? __ldg(wrow + c + 1) : 0.f);
+        }
+    }
     const long long ppi = (long long)g.H * g.W;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int jt = (int)(tile % tiles_j);
@@ -820,7 +840,7 @@ hc_fwd_2x3_kernel(const T* __restrict__ z, Geom g, HeadArgs hd, T* __restrict__ 
                 }
             }
             float* o0 = hd.out + (long long)b * O * ppi + rem;
-            hc_tail2<NVL, NP, O>(c0, c1, tp, lane, hd.inner, hd.softplus, o0, o0 + 1, ppi);
+            hc_tail2<NVL, NP, O>(c0, c1, tp, lane, hd.inner, hd.softplus, o0, o0 + 1, ppi, sW2);
         }
         __syncthreads();
     }
@@ -995,7 +1015,8 @@ int hc_launch_fwd(const void* z, const Geom& g, const HeadArgs& hd, void* conv, 
         if (const char* e = getenv("VKOCR_HC_VARIANT")) variant = atoi(e);
         auto run = [&](auto rtag, auto ttag, auto btag) -> int {
             constexpr int R = decltype(rtag)::value, THREADS = decltype(ttag)::value, MINB = decltype(btag)::value;
-            const size_t smem = ((size_t)R * 2 * 3 * HC_QL * cw + cw) * sizeof(float) + (R * 2 * 3 * 2 + HC_TJ * 2 * 3) * sizeof(float2);
+            const size_t smem = ((size_t)R * 2 * 3 * HC_QL * cw + cw) * sizeof(float) + (R * 2 * 3 * 2 + HC_TJ * 2 * 3) * sizeof(float2) +
+                                (HcW2Smem<O>::value ? (size_t)O * NVL * HcPairs<T>::NP * 32 * sizeof(float2) : 0);
             if (smem > 200 * 1024) return -1;
             const int tiles_j = vk_cdiv(g.w, HC_TJ), tiles_i = vk_cdiv(g.h, R);
             const long long ntiles = (long long)g.B * tiles_i * tiles_j;

@@ -7,6 +7,7 @@
 
 Losses stay on the device (the reference's ``float(loss)`` host syncs, train.py:415,453, are left to the caller).
 """
+import math
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -56,6 +57,63 @@ def train_step(model, rough_loss_function: AdaptiveScalingRoughLossFunction,
     if dp is not None:
         dp.finish_step()
     return rough_loss.detach(), precise_loss.detach()
+
+
+class GraphedTrainStep:
+    """``train_step`` captured once into a CUDA graph and replayed: the ~1000 kernel launches of a step (every C-ABI call,
+    the autograd glue, the bucket zero-fills) become one ``cudaGraphLaunch``, which removes the launch gaps between
+    dependent kernels and the host time at the pass boundaries (opt-in; the eager step stays the default).
+
+    The captured step reads its inputs from buffers this object owns: ``__call__`` copies the new batches into them
+    (same keys, shapes and dtypes as the example batches; the non-tensor entries -- ``downsampled_shape``,
+    ``downsampled_core_box`` -- are baked into the graph and must not change) and returns the two loss tensors, which
+    are overwritten by the next replay.  Gradients land in ``dp``'s flat buckets exactly as in the eager step, stochastic
+    depth draws fresh masks on every replay (torch's graph-safe Philox offsets).  Single-process only: the bucketed
+    all-reduce of a multi-GPU step runs on side streams and stays eager.  The parameters may change between replays (the
+    fused optimizer updates them in place) only if the kernel-layout weight copies are refreshed inside the graph:
+    pass ``repack_weights=True`` when an optimizer steps between replays."""
+
+    def __init__(self, model, rough_loss_function, precise_loss_function, rough_batch: Dict[str, object],
+                 precise_batch: Dict[str, object], dp: DataParallel, warmup: int = 3, label_point_forward: bool = False,
+                 repack_weights: bool = False) -> None:
+        from . import ops
+        if dp is None or dp.world_size != 1:
+            raise ValueError('GraphedTrainStep needs a single-process DataParallel (its flat buckets hold the gradients)')
+        own = lambda d: {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+        self.rough_batch, self.precise_batch = own(rough_batch), own(precise_batch)
+
+        def run():
+            if repack_weights:
+                ops.PACK.bump()
+            return train_step(model, rough_loss_function, precise_loss_function, self.rough_batch, self.precise_batch, dp,
+                              label_point_forward=label_point_forward)
+        # warm-up on a side stream (torch's capture recipe): fills the packed-weight cache, the cached device constants and
+        # the allocator, so that the capture itself records kernels only
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = run()
+
+    @staticmethod
+    def _refill(own: Dict[str, object], new: Dict[str, object]) -> None:
+        for k, v in own.items():
+            if isinstance(v, torch.Tensor):
+                if new[k] is not v:
+                    v.copy_(new[k], non_blocking=True)
+            elif new[k] != v:
+                raise ValueError(f'GraphedTrainStep: batch entry {k!r} is part of the captured graph and cannot change')
+
+    def __call__(self, rough_batch: Dict[str, object], precise_batch: Dict[str, object]) -> Tuple[Tensor, Tensor]:
+        self._refill(self.rough_batch, rough_batch)
+        self._refill(self.precise_batch, precise_batch)
+        self.graph.replay()
+        return self.losses
 
 
 class FusedAdamW:
@@ -158,3 +216,54 @@ class FusedAdamW:
                                            bc1, bc2, L.ptr(self._sumsq) if clip else None, float(self.max_grad_norm or 0.0),
                                            grad_scale, stream), 'adamw_step')
         ops.PACK.bump()   # the parameters changed behind torch's version counters: re-pack the kernel-layout weights
+
+
+class CosineWarmRestartsSchedule:
+    """The learning-rate schedule of the reference loop as a plain function of the fractional epoch:
+    ``torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(T_0=10, T_mult=10, eta_min=8e-6)`` stepped with
+    ``epoch_idx + (batch_idx - 1) / train_num_batches`` (experiment/adaptive_scaling/train.py:73-80,293-298,474-477).
+    ``FusedAdamW.step(lr=schedule.step(epoch))`` takes the result; no optimizer object is patched.  ``state_dict`` /
+    ``load_state_dict`` speak the torch scheduler's keys, so the ``optimizer_scheduler_state_dict`` of a reference
+    ``RestoreState`` file (train.py:91-96,323-331) resumes here and ours resumes there."""
+
+    def __init__(self, base_lr: float = 8e-4, t0: int = 10, t_mult: int = 10, eta_min: float = 8e-6) -> None:
+        if t0 <= 0 or t_mult < 1:
+            raise ValueError(f'CosineWarmRestartsSchedule: T_0 {t0}, T_mult {t_mult}')
+        self.base_lr, self.t0, self.t_mult, self.eta_min = float(base_lr), int(t0), int(t_mult), float(eta_min)
+        self.t_i, self.t_cur, self.last_epoch = self.t0, 0.0, 0
+        self.last_lr = self.lr_at(0.0)
+
+    def _locate(self, epoch: float) -> Tuple[float, int]:
+        """(position inside the current cosine period, length of that period)"""
+        if epoch < 0:
+            raise ValueError(f'epoch {epoch} < 0')
+        if epoch < self.t0:
+            return epoch, self.t0
+        if self.t_mult == 1:
+            return epoch % self.t0, self.t0
+        n = int(math.log(epoch / self.t0 * (self.t_mult - 1) + 1, self.t_mult))
+        return epoch - self.t0 * (self.t_mult ** n - 1) / (self.t_mult - 1), self.t0 * self.t_mult ** n
+
+    def lr_at(self, epoch: float) -> float:
+        t_cur, t_i = self._locate(epoch)
+        return self.eta_min + (self.base_lr - self.eta_min) * (1.0 + math.cos(math.pi * t_cur / t_i)) / 2.0
+
+    def step(self, epoch: float) -> float:
+        self.t_cur, self.t_i = self._locate(epoch)
+        self.last_epoch = math.floor(epoch)
+        self.last_lr = self.lr_at(epoch)
+        return self.last_lr
+
+    def state_dict(self) -> Dict[str, object]:
+        return {'T_0': self.t0, 'T_i': self.t_i, 'T_mult': self.t_mult, 'eta_min': self.eta_min, 'T_cur': self.t_cur,
+                'base_lrs': [self.base_lr], 'last_epoch': self.last_epoch, '_last_lr': [self.last_lr]}
+
+    def load_state_dict(self, state: Dict[str, object]) -> None:
+        if len(state['base_lrs']) != 1:
+            raise ValueError('CosineWarmRestartsSchedule keeps one parameter group')
+        self.t0, self.t_i, self.t_mult = int(state['T_0']), int(state['T_i']), int(state['T_mult'])
+        self.eta_min, self.t_cur = float(state['eta_min']), float(state['T_cur'])
+        self.base_lr, self.last_epoch = float(state['base_lrs'][0]), int(state['last_epoch'])
+        self.last_lr = float(state['_last_lr'][0]) if state.get('_last_lr') else \
+            self.eta_min + (self.base_lr - self.eta_min) * (1.0 + math.cos(math.pi * self.t_cur / self.t_i)) / 2.0
+
