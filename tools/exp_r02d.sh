@@ -1,9 +1,8 @@
 #!/bin/bash
-# Round-2 late experiments on one B200 (run through gpurun from the repo root).
 O=gpurun_out
 mkdir -p $O
-python -m pytest tests/test_gpu_ops.py -q -m gpu -k "combine or convolve_first or head" > $O/r02d_tests.log 2>&1; tail -3 $O/r02d_tests.log
-for lib in _bisect/lib_base.so ""; do
-    echo "== precise group, lib '$lib'"; VKOCR_B200_LIB=$lib python tools/profile_combine.py 3 fwd 2>&1 | tail -4
-done > $O/r02d_combine_ab.log 2>&1
-cat $O/r02d_combine_ab.log
+for v in 0 1; do
+  echo "== pmajor $v"; VKOCR_HCB_PMAJOR=$v python tools/profile_combine.py 3 bwd 2>&1 | tail -2; ROUGH=1 VKOCR_HCB_PMAJOR=$v python tools/profile_combine.py 3 bwd 2>&1 | tail -2
+done > $O/r02d_hcb_ab.log 2>&1
+cat $O/r02d_hcb_ab.log
+VKOCR_HCB_PMAJOR=1 python -m pytest tests/test_gpu_ops.py -q -m gpu -k "combine or convolve_first" 2>&1 | tail -2

@@ -862,7 +862,7 @@ constexpr int HB_THREADS = HB_SL * HB_CVL;   // 320: phase 1 uses all, phase 2 t
 template <typename T>
 __global__ void __launch_bounds__(HB_THREADS, 2)
 hc_bwd_2x3_kernel(const T* __restrict__ dc, long long ld_dc, Geom g, int width, T* __restrict__ dz, int tiles_q, int tiles_p,
-                  int chunks, long long nwork) {
+                  int chunks, long long nwork, int pmajor) {
     constexpr int V = VkVec<T>::N;
     constexpr int NP = HcPairs<T>::NP;
     constexpr int CH = HB_CVL * V;
@@ -876,10 +876,18 @@ hc_bwd_2x3_kernel(const T* __restrict__ dc, long long ld_dc, Geom g, int width, 
         Work wk;
         const int ch = (int)(work % chunks);
         long long t2 = work / chunks;
-        const int qt = (int)(t2 % tiles_q);
-        t2 /= tiles_q;
-        const int pt = (int)(t2 % tiles_p);
-        wk.b = (int)(t2 / tiles_p);
+        int qt, pt;
+        if (pmajor) {           // tiles of one column back to back: the blocks of a wave share their halo rows while they are hot in L2
+            pt = (int)(t2 % tiles_p);
+            t2 /= tiles_p;
+            qt = (int)(t2 % tiles_q);
+            wk.b = (int)(t2 / tiles_q);
+        } else {
+            qt = (int)(t2 % tiles_q);
+            t2 /= tiles_q;
+            pt = (int)(t2 % tiles_p);
+            wk.b = (int)(t2 / tiles_p);
+        }
         wk.p0 = pt * HB_R; wk.q0 = qt * HB_TQ; wk.c0 = ch * CH;
         return wk;
     };
@@ -1139,12 +1147,15 @@ int vkocr_head_combine_bwd(int dtype, const void* dconv, long long ld_dc, int B,
         const size_t smem = ((size_t)HB_R * 3 * HB_SL * CH + HB_R * 3 * 4 + HB_TQ * 3 * 4) * sizeof(float);
         long long blocks = (long long)vkocr_sm_count() * 2;
         if (blocks > nwork) blocks = nwork;
+        int pmajor = 1;                                            // VKOCR_HCB_PMAJOR=0: the row-major tile order (A/B, tools/profile_combine.py)
+        if (const char* e = getenv("VKOCR_HCB_PMAJOR")) pmajor = atoi(e);
 #define VK_HC_BWD(T)                                                                                                             \
     do {                                                                                                                         \
         cudaError_t e = cudaFuncSetAttribute(hc_bwd_2x3_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         VK_REQUIRE(e == cudaSuccess, VKOCR_CUDA_ERROR, "head_combine_bwd: smem %zu: %s", smem, cudaGetErrorString(e));           \
         hc_bwd_2x3_kernel<T><<<(unsigned)blocks, HB_THREADS, smem, s>>>(reinterpret_cast<const T*>(dconv), ld_dc, g, width,             \
-                                                                 reinterpret_cast<T*>(dz), tiles_q, tiles_p, chunks, nwork);     \
+                                                                 reinterpret_cast<T*>(dz), tiles_q, tiles_p, chunks, nwork,      \
+                                                                 pmajor);                                                       \
     } while (0)
         if (dtype == VKOCR_BF16) VK_HC_BWD(__nv_bfloat16);
         else VK_HC_BWD(float);
