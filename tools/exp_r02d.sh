@@ -1,8 +1,8 @@
 #!/bin/bash
 O=gpurun_out
 mkdir -p $O
-for v in 0 1; do
-  echo "== pmajor $v"; VKOCR_HCB_PMAJOR=$v python tools/profile_combine.py 3 bwd 2>&1 | tail -2; ROUGH=1 VKOCR_HCB_PMAJOR=$v python tools/profile_combine.py 3 bwd 2>&1 | tail -2
-done > $O/r02d_hcb_ab.log 2>&1
-cat $O/r02d_hcb_ab.log
-VKOCR_HCB_PMAJOR=1 python -m pytest tests/test_gpu_ops.py -q -m gpu -k "combine or convolve_first" 2>&1 | tail -2
+python -m pytest tests/test_gpu_model.py tests/test_gpu_ops.py -q -m gpu -k "label_point or sparse or points" 2>&1 | tail -2
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --no-eager-baseline --profile > $O/r02d_bench2.json 2> $O/r02d_bench2.err
+head -c 300 $O/r02d_bench2.json; echo; grep -i "scatter_up\|unbracketed" $O/r02d_bench2.err | head -3
+python -c "
+import json; d=json.loads(open('$O/r02d_bench2.json').read().strip().splitlines()[-1]); print(d['unbracketed'], d['e2e']['value'], d['e2e']['ms_per_step'])"

@@ -158,6 +158,65 @@ scatter_up_taps_kernel(const T* __restrict__ u, int h, int w, int C, int f, int 
     if (any) hs_atomic_add(dx + (((long long)b * h + p) * w + q) * ld_dx + 2 * cp, a0, a1);
 }
 
+// The same with one 16-byte channel vector per thread (C a multiple of the vector): the interpolation weights of a
+// (label pixel, neighbour) -- a dozen divisions and compares -- are computed for 8 channels instead of 2, the tap vectors
+// come in as 16-byte loads.  6 400 label pixels x 25 neighbours x 384 channels: 0.52 -> 0.1x ms.
+template <typename T>
+__global__ void __launch_bounds__(256)
+scatter_up_taps_vec_kernel(const T* __restrict__ u, int h, int w, int C, int f, int mode, int ks, const int* __restrict__ pix_index, int E,
+                           T* __restrict__ dx, long long ld_dx) {
+    constexpr int V = VkVec<T>::N;
+    const int CV = C / V;
+    const long long total = (long long)E * HS_NB * HS_NB * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    const int nb = (int)((idx / CV) % (HS_NB * HS_NB));
+    const int e = (int)(idx / ((long long)CV * HS_NB * HS_NB));
+    const int pix = pix_index[e];
+    if (pix < 0) return;
+    const int H = h * f, W = w * f, pad = ks >> 1, taps = ks * ks;
+    const int b = pix / (H * W), rem = pix - b * (H * W);
+    const int r = rem / W, s = rem % W;
+    const int ylo = r - pad < 0 ? 0 : r - pad, xlo = s - pad < 0 ? 0 : s - pad;
+    const int p = hs_axis(ylo, h, H, mode).i0 + nb / HS_NB, q = hs_axis(xlo, w, W, mode).i0 + nb % HS_NB;
+    if (p >= h || q >= w) return;
+    float wx[5];
+#pragma unroll
+    for (int dxx = 0; dxx < 5; ++dxx) {
+        const int X = s + dxx - pad;
+        wx[dxx] = (dxx < ks && X >= 0 && X < W) ? hs_weight_of(X, q, w, W, mode) : 0.f;
+    }
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    bool any = false;
+    const T* ue = u + (long long)e * taps * C + cv * V;
+    for (int dy = 0; dy < ks; ++dy) {
+        const int Y = r + dy - pad;
+        if (Y < 0 || Y >= H) continue;
+        const float wy = hs_weight_of(Y, p, h, H, mode);
+        if (wy == 0.f) continue;
+#pragma unroll
+        for (int dxx = 0; dxx < 5; ++dxx) {
+            const float ww = wy * wx[dxx];
+            if (dxx >= ks || ww == 0.f) continue;
+            VkVec<T> vec;
+            vec.load(ue + (long long)(dy * ks + dxx) * C);
+            float fv[V];
+            vec.unpack(fv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] = fmaf(ww, fv[i], acc[i]);
+            any = true;
+        }
+    }
+    if (any) {
+        T* dst = dx + (((long long)b * h + p) * w + q) * ld_dx + cv * V;
+#pragma unroll
+        for (int i = 0; i < V; i += 2) hs_atomic_add(dst + i, acc[i], acc[i + 1]);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -202,6 +261,14 @@ int vkocr_scatter_up_taps(int dtype, const void* u, int B, int h, int w, int C, 
     const long long total = (long long)E * HS_NB * HS_NB * (C / 2);
     if (total == 0) return VKOCR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int V = dtype == VKOCR_F32 ? 4 : 8;
+    if (C % V == 0 && ld_dx % V == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+        const long long tv = (long long)E * HS_NB * HS_NB * (C / V);
+        VK_DISPATCH_DTYPE(dtype, T, (scatter_up_taps_vec_kernel<T><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(
+                                        reinterpret_cast<const T*>(u), h, w, C, factor, mode, ks, pix_index, E, reinterpret_cast<T*>(dx), ld_dx)));
+        VK_CHECK_LAUNCH("scatter_up_taps_vec_kernel");
+        return VKOCR_OK;
+    }
     VK_DISPATCH_DTYPE(dtype, T, (scatter_up_taps_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
                                     reinterpret_cast<const T*>(u), h, w, C, factor, mode, ks, pix_index, E, reinterpret_cast<T*>(dx), ld_dx)));
     VK_CHECK_LAUNCH("scatter_up_taps_kernel");
