@@ -543,7 +543,8 @@ def run_ours(args) -> None:
             json.dump({'step_ms': ms, 'step_ms_bracketed': ms_bracketed, 'step_ms_sum_of_calls': total, 'steps': args.steps,
                        'rows': [dict(label=k, calls=v['calls'] / args.steps, ms=v['ms'] / args.steps, flops=v['flops'] / args.steps,
                                      bytes=v['bytes'] / args.steps, entry=v['entry']) for k, v in rows]}, f, indent=1)
-XX
+        print(f'# per-call device time per step: {total:.2f} ms of {ms_bracketed:.2f} ms (bracketed repetition; timed region {ms:.2f} ms)',
+              file=sys.stderr)
         for k, r in rows[:70]:
             tf = r['flops'] / (r['ms'] * 1e-3) / 1e12 if r['flops'] else 0.0
             gb = r['bytes'] / (r['ms'] * 1e-3) / 1e9 if r['bytes'] else 0.0
