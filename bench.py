@@ -53,6 +53,7 @@ def parse_args():
                     'by CUDA events and write the per-kernel table to gpurun_out/kernel_table_<workload>.json')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cuda-graph', action='store_true', help='time the step replayed from one CUDA graph (training.GraphedTrainStep)')
     ap.add_argument('--no-extras', action='store_true', help='skip the FPN / optimizer / config #2 / config #5 side measurements')
     ap.add_argument('--no-eager-baseline', action='store_true', help='skip the stock-PyTorch-eager arm on the same GPU')
     return ap.parse_args()
@@ -286,7 +287,7 @@ def build_workload(vk, workload: str, neck: str, batch: int, size: int, dev, ran
                 opt.step()
             return losses
         if cuda_graph:              # the same step captured once and replayed (training.GraphedTrainStep): reported in `extra`
-            assert opt is None and world == 1
+            assert opt is None
             step = GraphedTrainStep(model, rough_fn, precise_fn, w.rb, w.pb, dp, label_point_forward=label_point_forward)
         w.images_per_step = batch
         w.text = (f'adaptive-scaling TINY/{neck.upper()} two-pass training step (fwd+bwd+loss'
@@ -527,7 +528,7 @@ def run_ours(args) -> None:
 
     size = args.size or (2048 if args.workload == 'infer' else 640)
     batch = args.batch or (8 if args.workload == 'infer' else 32)
-    w = build_workload(vk, args.workload, args.neck, batch, size, dev, rank, world)
+    w = build_workload(vk, args.workload, args.neck, batch, size, dev, rank, world, cuda_graph=args.cuda_graph and args.workload == 'train')
     ms, losses, launches, table, clocks = time_device_resident(w, args.steps, args.warmup, dev, rank, world, local_rank)
     value = w.images_per_step * world / (ms / 1e3)
     ms_bracketed = w.ms_bracketed

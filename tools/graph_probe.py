@@ -15,10 +15,14 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 neck = sys.argv[2] if len(sys.argv) > 2 else 'upernext'
 batch = int(os.environ.get('BATCH', '32'))
 size = int(os.environ.get('SIZE', '640'))
-dev = torch.device('cuda:0')
+rank, world, local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+dev = torch.device('cuda', local)
 torch.cuda.set_device(dev)
+if world > 1:        # torchrun: the bucketed NCCL all-reduces are captured into the graph too
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=dev)
 vk.set_compute_dtype(torch.bfloat16)
-w = bench.build_workload(vk, 'train', neck, batch, size, dev, 0, 1)
+w = bench.build_workload(vk, 'train', neck, batch, size, dev, rank, world)
 model, dp = w.model, w.dp
 LF = vk.loss_function
 rough_fn = LF.AdaptiveScalingRoughLossFunction(LF.AdaptiveScalingRoughLossFunctionConifg())
@@ -52,7 +56,7 @@ out['eval_grad_rel_l2_graph_vs_eager'] = (num / den) ** 0.5
 out['eval_losses_eager'] = [float(x) for x in eager_losses]
 out['eval_losses_graph'] = [float(x) for x in graph_losses]
 # other inputs through the same graph: swap the two halves of the batch, eager vs replay
-perm = torch.arange(batch, device=dev).roll(batch // 2)
+perm = torch.arange(batch, device=dev).flip(0)
 rb2 = {k: (v[perm] if isinstance(v, torch.Tensor) else v) for k, v in w.rb.items()}
 pb2 = {k: (v[perm] if isinstance(v, torch.Tensor) else v) for k, v in w.pb.items()}
 l_e = [float(x) for x in train_step(model, rough_fn, precise_fn, rb2, pb2, dp)]
@@ -70,5 +74,10 @@ for _ in range(2):
     g_train(w.rb, w.pb)
 out['graph_ms'], losses = timed(lambda: g_train(w.rb, w.pb), steps)
 out['graph_losses_train_mode'] = [float(x) for x in losses]
-out['config'] = {'neck': neck, 'batch': batch, 'size': size, 'steps': steps}
-print(json.dumps(out))
+out['config'] = {'neck': neck, 'batch': batch, 'size': size, 'steps': steps, 'world': world, 'rank': rank}
+print(json.dumps(out), flush=True)
+del g_train            # a live graph that captured NCCL kernels makes destroy_process_group() wait forever
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()

@@ -477,12 +477,22 @@ ln_bwd_fast_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restric
         const float shift = -mu * rs;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < NV; ++j)
+        for (int j = 0; j < NV; ++j) {
+            if (act) {      // LN -> GELU blocks of the necks: gelu'(z) on packed pairs (vk_gelu_both2: one MUFU.RCP + one MUFU.EX2 per element)
+#pragma unroll
+                for (int i = 0; i < V; i += 2) {
+                    const float h0 = fmaf(xh[j][i], rs, shift), h1 = fmaf(xh[j][i + 1], rs, shift);
+                    const float2 z = make_float2(fmaf(h0, gm[j][i], s_beta[(g + G * j) * V + i]), fmaf(h1, gm[j][i + 1], s_beta[(g + G * j) * V + i + 1]));
+                    float2 gv, dg;
+                    vk_gelu_both2(z, &gv, &dg);
+                    dz[j][i] *= dg.x;
+                    dz[j][i + 1] *= dg.y;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 const float h = fmaf(xh[j][i], rs, shift);
                 float d = dz[j][i];
-                if (act) d *= vk_gelu_grad(fmaf(h, gm[j][i], s_beta[(g + G * j) * V + i]));
                 xh[j][i] = h;
                 ag[j][i] = fmaf(d, h, ag[j][i]);
                 ab[j][i] += d;
@@ -491,6 +501,7 @@ ln_bwd_fast_kernel(const T* __restrict__ dy, long long ld_dy, const T* __restric
                 s1 += dxh;
                 s2 = fmaf(dxh, h, s2);
             }
+        }
         const float2 ss = group_sum2<G>(s1, s2);
         const float m1 = ss.x * invC, m2 = ss.y * invC;
         if (row_ok) {

@@ -68,8 +68,11 @@ class GraphedTrainStep:
     (same keys, shapes and dtypes as the example batches; the non-tensor entries -- ``downsampled_shape``,
     ``downsampled_core_box`` -- are baked into the graph and must not change) and returns the two loss tensors, which
     are overwritten by the next replay.  Gradients land in ``dp``'s flat buckets exactly as in the eager step, stochastic
-    depth draws fresh masks on every replay (torch's graph-safe Philox offsets).  Single-process only: the bucketed
-    all-reduce of a multi-GPU step runs on side streams and stays eager.  The parameters may change between replays (the
+    depth draws fresh masks on every replay (torch's graph-safe Philox offsets).  With several processes the bucketed NCCL
+    all-reduces are captured too: the side stream forks from the compute stream at each bucket's last gradient and joins it
+    again in ``finish_step``, which is a legal cross-stream capture (measured at 2 GPUs: 87.3 -> 85.3 ms per step, gradients
+    equal to the eager step's; delete the object BEFORE ``destroy_process_group()`` -- a live graph that holds captured NCCL
+    kernels keeps the communicator's teardown waiting).  The parameters may change between replays (the
     fused optimizer updates them in place) only if the kernel-layout weight copies are refreshed inside the graph:
     pass ``repack_weights=True`` when an optimizer steps between replays."""
 
@@ -77,8 +80,8 @@ class GraphedTrainStep:
                  precise_batch: Dict[str, object], dp: DataParallel, warmup: int = 3, label_point_forward: bool = False,
                  repack_weights: bool = False) -> None:
         from . import ops
-        if dp is None or dp.world_size != 1:
-            raise ValueError('GraphedTrainStep needs a single-process DataParallel (its flat buckets hold the gradients)')
+        if dp is None:
+            raise ValueError('GraphedTrainStep needs a DataParallel (its flat buckets hold the gradients)')
         own = lambda d: {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
         self.rough_batch, self.precise_batch = own(rough_batch), own(precise_batch)
 
