@@ -602,7 +602,9 @@ def run_ours(args) -> None:
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if dtype == torch.bfloat16 else 'f32', 'data': 'synthetic',
         'config': {'workload': workload_text, 'global_batch': batch * world, 'image_size': size, 'label_points': POINTS,
-                   'parallelism': f'dp{world}', 'l2': f'inputs per step ({h2d / 1e6:.0f} MB) and every activation exceed the 126 MB L2'},
+                   'parallelism': f'dp{world}', 'l2': f'inputs per step ({h2d / 1e6:.0f} MB) and every activation exceed the 126 MB L2',
+                   'unit_note': 'images/s counts image PAIRS (a step consumes B rough + B precise images, SURVEY 8d); '
+                                f'image-forwards/s = 2 x value = {2 * value:.1f}' if args.workload == 'train' else None},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline,
         'gpu_eager_baseline': gpu_eager, 'extra': extra, 'losses': loss_values,
     }
