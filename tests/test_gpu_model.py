@@ -440,3 +440,48 @@ def test_graphed_train_step_replays_the_eager_step(vk):
             assert all(np.isfinite(a + b)) and a != b, (a, b)     # other drop-path masks -> other losses
     finally:
         dp.close()
+
+
+def test_fpn_step_meets_the_plain_bound_at_a_third_of_a_megapixel(vk):
+    """The one stated tolerance exception (tests/_util.py: SMALL_SHAPE_BF16_GRAD_TOL, TINY/FPN on two 160x224 images:
+    2.9e-2) is a small-sample effect: the same configuration, weights and loss on four 256x320 images (4.6x the pixels) is
+    held to the plain north-star 2e-2 here, as it is at the benchmark shape (tests/test_gpu_fullsize.py: 8.5e-3)."""
+    from oracle import loss as ol
+    from oracle import model as om
+    from oracle import synth
+    from vkit_ocr_model_adaptive_scaling_b200.training import train_step
+    dev = torch.device('cuda')
+    B, H, W, P = 4, 256, 320, 16
+    model = _build(vk, 'fpn')
+    model.load_state_dict(synth.synth_state_dict('tiny', 'fpn', seed=7), strict=True)
+    model.to(dev).eval()
+    params = oracle_params(model)
+    rb = _to(synth.synth_rough_batch(B, H, W, seed=3, inset=6), dev)
+    pb = _to(synth.synth_precise_batch(B, H, W, points=P, seed=3, inset=6), dev)
+    lf = vk.loss_function
+    rough_fn = lf.AdaptiveScalingRoughLossFunction(lf.AdaptiveScalingRoughLossFunctionConifg())
+    precise_fn = lf.AdaptiveScalingPreciseLossFunction(lf.AdaptiveScalingPreciseLossFunctionConifg())
+    with vk.precision(torch.bfloat16):
+        rl, pl = train_step(model, rough_fn, precise_fn, rb, pb)
+    f64 = lambda d: {k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in d.items()}
+    rb, pb = f64(rb), f64(pb)
+    rl_ref = ol.rough_loss(*om.forward_rough(params, rb['image']), *(rb[k] for k in ROUGH_KEYS))
+    (rl_ref / 2).backward()
+    pl_ref = ol.precise_loss(None, *om.forward_precise(params, pb['image']), *(pb[k] for k in PRECISE_KEYS))
+    (pl_ref / 2).backward()
+    tol = TOL[torch.bfloat16]
+    assert abs(float(rl) - float(rl_ref)) <= tol * abs(float(rl_ref)), (float(rl), float(rl_ref))
+    assert abs(float(pl) - float(pl_ref)) <= tol * abs(float(pl_ref)), (float(pl), float(pl_ref))
+    # the optimizer's view: all parameter gradients as one vector (measured 1.75e-2; per-tensor bounds are the business of
+    # test_training_step_against_oracle and the full-size test)
+    num = den = 0.0
+    for name, p in model.named_parameters():
+        ref = params[name].grad
+        if ref is None:
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        num += float((p.grad.double() - ref).square().sum())
+        den += float(ref.square().sum())
+    err = (num / den) ** 0.5
+    print(f'[fpn step, 4 x 256x320] global gradient rel L2 error {err:.3e}')
+    assert err <= GRAD_TOL[torch.bfloat16], f'global gradient relative L2 error {err:.3e} > {GRAD_TOL[torch.bfloat16]:.1e}'
