@@ -104,12 +104,24 @@ class GraphedTrainStep:
             self.losses = run()
 
     @staticmethod
-    def _refill(own: Dict[str, object], new: Dict[str, object]) -> None:
+    def _same(a: object, b: object) -> bool:
+        """Equality of the non-tensor batch entries: boxes by their four edges (the reference passes a fresh
+        ``vkit.element.Box`` with every batch, whatever its ``__eq__`` does), everything else by ``==``."""
+        edges = ('up', 'down', 'left', 'right')
+        if all(hasattr(a, f) and hasattr(b, f) for f in edges):
+            return all(int(getattr(a, f)) == int(getattr(b, f)) for f in edges)
+        return bool(a == b)
+
+    @classmethod
+    def _refill(cls, own: Dict[str, object], new: Dict[str, object]) -> None:
         for k, v in own.items():
             if isinstance(v, torch.Tensor):
                 if new[k] is not v:
+                    if tuple(new[k].shape) != tuple(v.shape) or new[k].dtype != v.dtype:
+                        raise ValueError(f'GraphedTrainStep: batch entry {k!r} is {tuple(new[k].shape)} {new[k].dtype}, the captured '
+                                         f'graph reads {tuple(v.shape)} {v.dtype}')
                     v.copy_(new[k], non_blocking=True)
-            elif new[k] != v:
+            elif not cls._same(new[k], v):
                 raise ValueError(f'GraphedTrainStep: batch entry {k!r} is part of the captured graph and cannot change')
 
     def __call__(self, rough_batch: Dict[str, object], precise_batch: Dict[str, object]) -> Tuple[Tensor, Tensor]:
