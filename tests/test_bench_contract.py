@@ -55,3 +55,28 @@ def test_inference_oracle_small_cases():
     assert prob.shape == (4, 6) and offs.shape == (4, 6, 2) and angs.shape == (4, 6, 4) and dists.shape == (4, 6, 4)
     assert np.allclose(angs.sum(-1), 1.0, atol=1e-6)
     assert np.allclose(prob, torch.sigmoid(feats[0][0, 0]).numpy())
+
+
+def test_roofline_of_picks_the_largest_call_and_divides_algorithmic_work_by_measured_time():
+    """bench.roofline_of on a synthetic per-call table: the dominant call decides the bound (HBM bytes for a streaming
+    kernel, tensor FLOPs for a tcgen05 GEMM), `achieved` = algorithmic work per launch / average launch duration, shares are
+    taken against the (bracketed) step the per-call times were measured in."""
+    sys.path.insert(0, ROOT)
+    import bench
+    peaks = {'hbm_gbs': 6000.0, 'tflops_burst': 1600.0, 'tflops_sustained': 1400.0, 'source': 'test'}
+    steps, step_ms = 2, 50.0
+    table = {
+        'stream A': {'entry': 'vkocr_head_combine_fwd', 'calls': 2, 'ms': 20.0, 'flops': 0.0, 'bytes': 2 * 15e9},
+        'gemm B': {'entry': 'vkocr_gemm_nt', 'calls': 4, 'ms': 12.0, 'flops': 4 * 3e12, 'bytes': 0.0},
+        'tiny': {'entry': 'vkocr_zero', 'calls': 10, 'ms': 0.1, 'flops': 0.0, 'bytes': 0.0},
+    }
+    r = bench.roofline_of(table, steps, step_ms, peaks)
+    assert r['bound'] == 'hbm' and r['kernel'].startswith('vkocr_head_combine_fwd') and r['unit'] == 'GB/s'
+    assert abs(r['launch_ms'] - 10.0) < 1e-9 and abs(r['achieved'] - 1500.0) < 1e-6 and abs(r['frac'] - 0.25) < 1e-9
+    assert abs(r['share_of_step'] - 0.2) < 1e-9 and abs(r['all_gemm_share_of_step'] - 0.12) < 1e-9
+    assert abs(r['all_gemm_tflops'] - 1000.0) < 1e-6 and r['algorithmic_bytes'] == 15e9
+    table['gemm B']['ms'] = 40.0
+    r = bench.roofline_of(table, steps, step_ms, peaks)
+    assert r['bound'] == 'tensor' and r['unit'] == 'TFLOP/s' and abs(r['achieved'] - 300.0) < 1e-6
+    assert abs(r['frac'] - 300.0 / 1400.0) < 1e-9 and r['algorithmic_flops'] == 3e12
+    assert bench.roofline_of({'tiny': table['tiny']}, steps, step_ms, peaks) is None
