@@ -13,9 +13,10 @@ with torchrun (one rank per GPU, NCCL); the gradient all-reduce is bucketed and 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event timed, max over ranks.  `e2e`: the same step
 through the public API from pinned HOST buffers (per step one H2D copy of both batches, issued on a copy stream one step
 ahead like a training input pipeline, and a D2H read of both losses; all inside the timed region).
-`roofline`: the C-ABI call with the largest share of the timed region (every call is bracketed with CUDA events), its
-ALGORITHMIC FLOPs or bytes over the measured duration against MEASURED_PEAKS.json (tensor peak for the tcgen05 GEMMs, HBM
-bandwidth for the streaming kernels).  `cpu_baseline`: the oracle (port of the reference algorithm, plain fp32 PyTorch) on
+`roofline`: the C-ABI call with the largest share of the step -- measured in a repetition of the timed region's K steps in
+which every call is bracketed with CUDA events (the brackets cost 3-4 % of a step, so the timed region itself runs without
+them) --, its ALGORITHMIC FLOPs or bytes over the measured duration against MEASURED_PEAKS.json (tensor peak for the tcgen05
+GEMMs, HBM bandwidth for the streaming kernels).  `cpu_baseline`: the oracle (port of the reference algorithm, plain fp32 PyTorch) on
 the host cores over a bounded sample.  `gpu_eager_baseline`: the same oracle under stock PyTorch eager on the SAME GPU
 (fp32 TF32-off and autocast bf16).  `extra`: the other BASELINE configurations (FPN neck, ConvNeXt backbone only, 2048^2
 rough inference) and the step with the fused clip + AdamW tail, each timed like `value` with fewer steps.
