@@ -143,3 +143,43 @@ def test_cosine_warm_restarts_schedule_equals_torch(vk):
         nxt = theirs['last_epoch'] + 1.25
         ref2.step(nxt)
         assert abs(resumed.step(nxt) - ref2.get_last_lr()[0]) <= 1e-15
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, 'vkit_open_model')), reason='reference checkout not present (GPU box)')
+def test_debug_gradient_helpers_equal_the_reference(vk, caplog):
+    """AdaptiveScaling.debug_get_rough_name_to_grad / debug_get_precise_name_to_grad / debug_inspect_name_to_grad (SURVEY
+    8 a19; model/adaptive_scaling.py:179-237, called from train.py:420-462): the reference's static helpers and ours, run on
+    the same module with the same hand-set gradients, give the same tables and log the same statistics."""
+    import logging
+    sys.path.insert(0, REFERENCE)
+    try:
+        from vkit_open_model import model as ref_model
+        model, _ = _model(vk, 'fpn')
+        g = torch.Generator().manual_seed(21)
+        named = list(model.named_parameters())
+        for i, (_, p) in enumerate(named):
+            p.grad = None if i % 7 == 3 else torch.randn(p.shape, generator=g)       # some parameters without a gradient
+        ours_r = vk.model.AdaptiveScaling.debug_get_rough_name_to_grad(model)
+        ref_r = ref_model.AdaptiveScaling.debug_get_rough_name_to_grad(model)
+        for i, (_, p) in enumerate(named):                                        # "after the precise backward"
+            if i % 5 == 1:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad = p.grad + torch.randn(p.shape, generator=g)
+            else:
+                p.grad = torch.randn(p.shape, generator=g)
+        ours_p = vk.model.AdaptiveScaling.debug_get_precise_name_to_grad(model, ours_r)
+        ref_p = ref_model.AdaptiveScaling.debug_get_precise_name_to_grad(model, ref_r)
+        for ours, ref in ((ours_r, ref_r), (ours_p, ref_p)):
+            assert list(ours) == list(ref) and len(ours) > 100
+            assert all(torch.equal(ours[k], ref[k]) for k in ref)
+        numbers = []
+        for cls in (vk.model.AdaptiveScaling, ref_model.AdaptiveScaling):
+            caplog.clear()
+            with caplog.at_level(logging.INFO):
+                cls.debug_inspect_name_to_grad(ours_r, ours_p)
+            text = ' '.join(r.getMessage() for r in caplog.records)
+            numbers.append([float(t) for t in __import__('re').findall(r'= ([0-9.eE+-]+)', text)])
+        assert len(numbers[0]) == 5 and numbers[0] == pytest.approx(numbers[1], rel=1e-6)
+    finally:
+        sys.path.remove(REFERENCE)
