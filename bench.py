@@ -337,6 +337,8 @@ def build_workload(vk, workload: str, neck: str, batch: int, size: int, dev, ran
 def release(w) -> None:
     import gc
     import torch
+    if hasattr(getattr(w, 'step', None), 'close'):
+        w.step.close()          # a GraphedTrainStep: release the captured graph before anything else goes away
     if w.dp is not None:
         w.dp.close()
     for k in list(vars(w)):

@@ -431,13 +431,16 @@ def test_graphed_train_step_replays_the_eager_step(vk):
                     assert_close(got, want, 1e-4, f'bucket {name}')
             with pytest.raises(ValueError):
                 step({**batches[0][0], 'downsampled_shape': (1, 1)}, batches[0][1])
-            del step
+            step.close()
+            with pytest.raises(RuntimeError):
+                step(*batches[0])
             model.train()
             torch.manual_seed(5)
             step = GraphedTrainStep(model, rough_fn, precise_fn, *batches[0], dp, warmup=1)
             a = [float(x) for x in step(*batches[0])]
             b = [float(x) for x in step(*batches[0])]
             assert all(np.isfinite(a + b)) and a != b, (a, b)     # other drop-path masks -> other losses
+            step.close()
     finally:
         dp.close()
 

@@ -62,6 +62,7 @@ pb2 = {k: (v[perm] if isinstance(v, torch.Tensor) else v) for k, v in w.pb.items
 l_e = [float(x) for x in train_step(model, rough_fn, precise_fn, rb2, pb2, dp)]
 l_g = [float(x) for x in g_eval(rb2, pb2)]
 out['eval_losses_other_batch_eager_graph'] = [l_e, l_g]
+g_eval.close()
 del g_eval
 torch.cuda.empty_cache()
 
@@ -76,7 +77,7 @@ out['graph_ms'], losses = timed(lambda: g_train(w.rb, w.pb), steps)
 out['graph_losses_train_mode'] = [float(x) for x in losses]
 out['config'] = {'neck': neck, 'batch': batch, 'size': size, 'steps': steps, 'world': world, 'rank': rank}
 print(json.dumps(out), flush=True)
-del g_train            # a live graph that captured NCCL kernels makes destroy_process_group() wait forever
+g_train.close()        # a live graph that captured NCCL kernels makes destroy_process_group() wait forever
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()

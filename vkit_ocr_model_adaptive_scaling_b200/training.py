@@ -71,7 +71,7 @@ class GraphedTrainStep:
     depth draws fresh masks on every replay (torch's graph-safe Philox offsets).  With several processes the bucketed NCCL
     all-reduces are captured too: the side stream forks from the compute stream at each bucket's last gradient and joins it
     again in ``finish_step``, which is a legal cross-stream capture (measured at 2 GPUs: 87.3 -> 85.3 ms per step, gradients
-    equal to the eager step's; delete the object BEFORE ``destroy_process_group()`` -- a live graph that holds captured NCCL
+    equal to the eager step's; ``close()`` the object BEFORE ``destroy_process_group()`` -- a live graph that holds captured NCCL
     kernels keeps the communicator's teardown waiting).  The parameters may change between replays (the
     fused optimizer updates them in place) only if the kernel-layout weight copies are refreshed inside the graph:
     pass ``repack_weights=True`` when an optimizer steps between replays."""
@@ -124,7 +124,18 @@ class GraphedTrainStep:
             elif not cls._same(new[k], v):
                 raise ValueError(f'GraphedTrainStep: batch entry {k!r} is part of the captured graph and cannot change')
 
+    def close(self) -> None:
+        """Release the captured graph (its kernels, its private memory pool, the NCCL work it holds).  Call it before
+        ``torch.distributed.destroy_process_group()``."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+            self.losses = None
+
     def __call__(self, rough_batch: Dict[str, object], precise_batch: Dict[str, object]) -> Tuple[Tensor, Tensor]:
+        if self.graph is None:
+            raise RuntimeError('GraphedTrainStep: closed')
         self._refill(self.rough_batch, rough_batch)
         self._refill(self.precise_batch, precise_batch)
         self.graph.replay()
